@@ -1,0 +1,15 @@
+"""dunk_b200: B200-native (sm_100a) implementation of DUNK's registration hot path.
+
+Sub-modules mirror the reference crates on the path:
+  feature_extraction  (feature_extraction/src/lib.rs)
+  homographier        (homographier/src/homographier/mod.rs)
+  feature_database    (feature_database/src/{keypointdb,models}.rs, read/load side)
+Everything numeric happens in libdunk_b200.so (csrc/, C ABI in include/dunk_b200.h).
+"""
+from . import _lib
+from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, TOP2_DTYPE, Context, DunkError, default_context)
+from . import feature_extraction
+from . import feature_database
+
+__all__ = ["_lib", "Context", "DunkError", "default_context", "feature_extraction", "feature_database",
+           "DMATCH_DTYPE", "KEYPOINT_DTYPE", "TOP2_DTYPE"]

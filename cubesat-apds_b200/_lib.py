@@ -1,0 +1,195 @@
+"""ctypes binding of libdunk_b200.so (include/dunk_b200.h).
+
+The library is the product; this module only marshals numpy buffers across the C ABI.
+There is no CPU fallback: if the shared object is missing or no B200 is present the
+calls raise (`DunkError`), they never route anywhere else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdunk_b200.so")
+
+# status codes (include/dunk_b200.h)
+OK = 0
+ERR_NO_MEM = -4
+ERR_BAD_ARG = -5
+ERR_VEC_LENGTH = -28
+ERR_OUT_OF_RANGE = -211
+ERR_ASSERT = -215
+ERR_CUDA = -217
+
+MAX_POINTS_SHIFT = 18
+MAX_POINTS = (1 << MAX_POINTS_SHIFT) - 1
+DESC_BYTES = 61
+
+KEYPOINT_DTYPE = np.dtype(
+    [("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+     ("octave", "<i4"), ("class_id", "<i4")]
+)
+DMATCH_DTYPE = np.dtype(
+    [("query_idx", "<i4"), ("train_idx", "<i4"), ("img_idx", "<i4"), ("distance", "<f4")]
+)
+TOP2_DTYPE = np.dtype([("d1", "<u4"), ("i1", "<u4"), ("d2", "<u4"), ("i2", "<u4")])
+assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16
+
+
+class DunkError(RuntimeError):
+    """Mirror of `opencv::Error { code, message }` (feature_extraction/src/lib.rs:61)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"dunk_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_vp, _i, _i64, _u32, _u64, _f, _d = (C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64,
+                                      C.c_float, C.c_double)
+_pi = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/dunk_b200.h declares
+SIGNATURES = {
+    "dunk_ctx_create": (_i, [_i, _i, C.POINTER(_vp)]),
+    "dunk_ctx_destroy": (None, [_vp]),
+    "dunk_last_error": (C.c_char_p, []),
+    "dunk_version": (C.c_char_p, []),
+    "dunk_ctx_stream": (_vp, [_vp, _i]),
+    "dunk_ctx_device": (_i, [_vp]),
+    "dunk_ctx_sm_count": (_i, [_vp]),
+    "dunk_ctx_launch_count": (_u64, [_vp]),
+    "dunk_timer_begin": (_i, [_vp, _i]),
+    "dunk_timer_end": (_i, [_vp, _i, C.POINTER(_f)]),
+    "dunk_sync": (_i, [_vp, _i]),
+    "dunk_ctx_reserve_slot": (_i, [_vp]),
+    "dunk_ctx_release_slot": (_i, [_vp, _i]),
+    "dunk_knn_match_hamming": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _f, _vp, _i, _pi]),
+    "dunk_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "dunk_match_crosscheck_hamming": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i, _pi]),
+    "dunk_db_create": (_i, [_vp, _i64, _i, C.POINTER(_vp)]),
+    "dunk_db_destroy": (None, [_vp]),
+    "dunk_db_append": (_i, [_vp, _vp, _vp, _vp, _i64]),
+    "dunk_db_append_random": (_i, [_vp, _i64, _u64]),
+    "dunk_db_size": (_i64, [_vp]),
+    "dunk_db_read": (_i, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "dunk_db_match": (_i, [_vp, _vp, _i, _f, _vp, _i, _pi]),
+    "dunk_db_knn2": (_i, [_vp, _vp, _i, _u32, _vp]),
+    "dunk_db_knn2_dev": (_i, [_vp, _i, _vp, _i, _u32, _vp]),
+    "dunk_top2_merge_dev": (_i, [_vp, _i, _vp, _i, _i, _vp]),
+    "dunk_top2_ratio_dev": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp]),
+    "dunk_pad_desc_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp]),
+}
+
+
+def load():
+    """dlopen the in-tree library; raises if it has not been built (no fallback)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise DunkError(ERR_CUDA, f"{LIB_PATH} not built; run `python -c 'import "
+                            "__graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise DunkError(rc, load().dunk_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """`dunk_ctx`: one per process and GPU; owns the stream/workspace slots."""
+
+    def __init__(self, device: int = 0, n_slots: int = 4):
+        lib = load()
+        h = C.c_void_p()
+        check(lib.dunk_ctx_create(device, n_slots, C.byref(h)))
+        self._h = h
+        self.device = device
+        self.n_slots = n_slots
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise DunkError(ERR_BAD_ARG, "context destroyed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            load().dunk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream(self, slot: int) -> int:
+        return int(load().dunk_ctx_stream(self.handle, slot) or 0)
+
+    @property
+    def sm_count(self) -> int:
+        return load().dunk_ctx_sm_count(self.handle)
+
+    @property
+    def launch_count(self) -> int:
+        return int(load().dunk_ctx_launch_count(self.handle))
+
+    def reserve_slot(self) -> int:
+        s = load().dunk_ctx_reserve_slot(self.handle)
+        if s < 0:
+            check(s)
+        return s
+
+    def release_slot(self, slot: int):
+        check(load().dunk_ctx_release_slot(self.handle, slot))
+
+    def sync(self, slot: int):
+        check(load().dunk_sync(self.handle, slot))
+
+    def timer_begin(self, slot: int):
+        check(load().dunk_timer_begin(self.handle, slot))
+
+    def timer_end(self, slot: int) -> float:
+        ms = C.c_float()
+        check(load().dunk_timer_end(self.handle, slot, C.byref(ms)))
+        return float(ms.value)
+
+
+_default_ctx = None
+_default_lock = threading.Lock()
+
+
+def default_context() -> Context:
+    """Process-wide context on cuda:LOCAL_RANK (what the Rust shim's lazy static would hold)."""
+    global _default_ctx
+    with _default_lock:
+        if _default_ctx is None:
+            _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")), 4)
+        return _default_ctx
+
+
+def as_desc(a, name="descriptors") -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim != 2:
+        raise DunkError(ERR_BAD_ARG, f"{name}: expected an N x desc_bytes u8 matrix, got shape {a.shape}")
+    return a

@@ -1,0 +1,90 @@
+// Internal: context, stream/workspace slots, error plumbing.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/dunk_b200.h"
+
+namespace dunk {
+
+void set_error(const char* fmt, ...);
+
+// One stream + growable device / pinned-host scratch.  A host-API call owns exactly one
+// slot for its duration (SURVEY 8b "Threading").
+struct Slot {
+    cudaStream_t stream = nullptr;
+    void* dev = nullptr;
+    size_t dev_bytes = 0;
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool busy = false;
+};
+
+}  // namespace dunk
+
+struct dunk_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::vector<dunk::Slot> slots;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<uint64_t> launches{0};
+
+    int acquire();          // blocks until a slot is free
+    void release(int s);
+    // grow-only scratch; returns nullptr (and sets error) on failure
+    void* dev_scratch(int s, size_t bytes);
+    void* pin_scratch(int s, size_t bytes);
+};
+
+namespace dunk {
+
+struct SlotGuard {
+    dunk_ctx* ctx;
+    int s;
+    explicit SlotGuard(dunk_ctx* c) : ctx(c), s(c->acquire()) { cudaSetDevice(c->device); }
+    ~SlotGuard() { ctx->release(s); }
+    Slot& slot() { return ctx->slots[s]; }
+    cudaStream_t stream() { return ctx->slots[s].stream; }
+};
+
+// bump allocator over a scratch block (256-B aligned pieces)
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base((char*)b) {}
+    template <class T>
+    T* take(size_t n) {
+        T* p = (T*)(base + off);
+        off += ((n * sizeof(T)) + 255) & ~size_t(255);
+        return p;
+    }
+    static size_t need(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+#define DUNK_CUDA(expr)                                                                    \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            dunk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                     \
+            return DUNK_ERR_CUDA;                                                          \
+        }                                                                                  \
+    } while (0)
+
+#define DUNK_REQUIRE(cond, code, ...)      \
+    do {                                   \
+        if (!(cond)) {                     \
+            dunk::set_error(__VA_ARGS__);  \
+            return (code);                 \
+        }                                  \
+    } while (0)
+
+inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace dunk

@@ -1,0 +1,35 @@
+// Internal declarations for the Hamming matcher (not part of the ABI).
+#pragma once
+#include "ctx.h"
+
+namespace dunk {
+
+struct KnnPlan {
+    int threads;        // CTA size (warps chosen to minimise query padding)
+    int gx, gy;         // DB slabs x query groups
+    int tiles_per_cta;  // 128-row tiles per slab
+    size_t smem;
+};
+
+KnnPlan plan_knn2(dunk_ctx* ctx, int nq, uint32_t nt);
+// scratch needed for slab partials
+inline size_t knn2_partial_bytes(const KnnPlan& p, int nq) { return (size_t)p.gx * nq * 16; }
+
+// all launches are asynchronous on `st`
+int launch_pad_rows(dunk_ctx* ctx, cudaStream_t st, const uint8_t* src, int64_t n, int desc_bytes,
+                    uint4* dst64);
+int launch_unpad_rows(dunk_ctx* ctx, cudaStream_t st, const uint4* src64, int64_t n, int desc_bytes,
+                      uint8_t* dst);
+int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, const uint4* q64,
+                int nq, uint32_t index_base, uint4* partial, uint4* top2_out, const KnnPlan& plan);
+int launch_top2_merge(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_parts, int nq,
+                      uint4* out);
+int launch_top2_ratio(dunk_ctx* ctx, cudaStream_t st, const uint4* top2, int nq, float ratio,
+                      DunkDMatch* out, int* count);
+// cross-check (BFMatcher crossCheck=true): mutual nearest neighbours from both 1-NN passes
+int launch_crosscheck(dunk_ctx* ctx, cudaStream_t st, const uint4* q2t_top2, const uint4* t2q_top2,
+                      int nq, DunkDMatch* out, int* count);
+int launch_fill_random_rows(dunk_ctx* ctx, cudaStream_t st, uint4* dst64, int64_t n, uint64_t seed,
+                            uint64_t row_offset);
+
+}  // namespace dunk

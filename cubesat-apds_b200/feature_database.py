@@ -1,0 +1,118 @@
+"""Host-side mirror of the reference crate `feature_database`, READ / LOAD side only
+(feature_database/src/keypointdb.rs:38-109, src/models.rs:30-55, src/schema.rs:27-40).
+
+The reference keeps keypoints as AoS Postgres rows (`descriptor bytea`); here the same rows
+live in HBM as SoA arrays (x, y, size, angle, response, octave, class_id, image_id and an
+N x 64-B descriptor array), one `DescriptorDatabase` per GPU shard.  Postgres / diesel I/O is
+out of scope: `create_keypoint` takes the row fields the reference's
+`InsertKeypoint` carries and appends them to the shard.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import DMATCH_DTYPE, KEYPOINT_DTYPE, TOP2_DTYPE, DunkError, check, ptr
+
+# keypointdb.rs:12
+OPENCV_KEYPOINT_LIMIT = 2 ** 18 - 1
+
+
+class DescriptorDatabase:
+    """One HBM-resident shard of the `keypoint` table (schema.rs:27-40)."""
+
+    def __init__(self, ctx: Optional[_lib.Context] = None, capacity: int = 1 << 20,
+                 desc_bytes: int = _lib.DESC_BYTES):
+        self.ctx = ctx or _lib.default_context()
+        self.desc_bytes = desc_bytes
+        h = C.c_void_p()
+        check(_lib.load().dunk_db_create(self.ctx.handle, int(capacity), int(desc_bytes), C.byref(h)))
+        self._h = h
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise DunkError(_lib.ERR_BAD_ARG, "database closed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.load().dunk_db_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(_lib.load().dunk_db_size(self.handle))
+
+    # -- write side: what `create_keypoint(Keypoint::Multiple(..))` inserts (keypointdb.rs:100-109)
+    def append(self, descriptors: np.ndarray, keypoints: Optional[np.ndarray] = None,
+               image_ids: Optional[np.ndarray] = None):
+        d = _lib.as_desc(descriptors)
+        if d.shape[0] and d.shape[1] != self.desc_bytes:
+            raise DunkError(_lib.ERR_ASSERT, f"descriptor width {d.shape[1]} != {self.desc_bytes}")
+        k = None if keypoints is None else np.ascontiguousarray(keypoints, dtype=KEYPOINT_DTYPE)
+        if image_ids is not None and np.isscalar(image_ids):
+            image_ids = np.full(d.shape[0], image_ids, dtype=np.int32)
+        im = None if image_ids is None else np.ascontiguousarray(image_ids, dtype=np.int32)
+        for a in (k, im):
+            if a is not None and a.shape[0] != d.shape[0]:
+                raise DunkError(_lib.ERR_VEC_LENGTH, "row-count mismatch between columns")
+        check(_lib.load().dunk_db_append(self.handle, ptr(d), ptr(k), ptr(im), d.shape[0]))
+
+    def append_random(self, n: int, seed: int):
+        check(_lib.load().dunk_db_append_random(self.handle, int(n), int(seed)))
+
+    # -- read side
+    def read_descriptors(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.desc_bytes), dtype=np.uint8)
+        check(_lib.load().dunk_db_read(self.handle, first, n, ptr(out), None, None))
+        return out
+
+    def read_rows(self, first: int, n: int):
+        d = np.empty((n, self.desc_bytes), dtype=np.uint8)
+        k = np.empty(n, dtype=KEYPOINT_DTYPE)
+        im = np.empty(n, dtype=np.int32)
+        check(_lib.load().dunk_db_read(self.handle, first, n, ptr(d), ptr(k), ptr(im)))
+        return d, k, im
+
+    # -- matching against the shard
+    def match(self, query_desc: np.ndarray, ratio: float) -> np.ndarray:
+        q = _lib.as_desc(query_desc)
+        out = np.empty(max(q.shape[0], 1), dtype=DMATCH_DTYPE)
+        n = C.c_int(0)
+        check(_lib.load().dunk_db_match(self.handle, ptr(q), q.shape[0], float(ratio), ptr(out),
+                                        out.shape[0], C.byref(n)))
+        return out[: n.value].copy()
+
+    def knn2(self, query_desc: np.ndarray, index_base: int = 0) -> np.ndarray:
+        q = _lib.as_desc(query_desc)
+        out = np.empty(q.shape[0], dtype=TOP2_DTYPE)
+        check(_lib.load().dunk_db_knn2(self.handle, ptr(q), q.shape[0], int(index_base), ptr(out)))
+        return out
+
+
+def merge_top2(ctx: _lib.Context, parts: Sequence[np.ndarray]) -> np.ndarray:
+    """(distance, index)-lexicographic merge of per-shard top-2 records on the GPU — the step
+    that follows the allgather in the sharded matcher.  Host arrays in/out."""
+    import torch  # device memory plumbing only
+    nq = parts[0].shape[0]
+    stacked = np.ascontiguousarray(np.stack([np.asarray(p, dtype=TOP2_DTYPE) for p in parts]))
+    dev = torch.device("cuda", ctx.device)
+    t = torch.from_numpy(stacked.view(np.uint8).reshape(-1)).to(dev)
+    out = torch.empty(nq * 16, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    slot = ctx.reserve_slot()
+    try:
+        check(_lib.load().dunk_top2_merge_dev(ctx.handle, slot, t.data_ptr(), len(parts), nq, out.data_ptr()))
+        ctx.sync(slot)
+    finally:
+        ctx.release_slot(slot)
+    return out.cpu().numpy().view(TOP2_DTYPE).copy()

@@ -1,0 +1,155 @@
+/*
+ * dunk_b200.h — C ABI of libdunk_b200.so, the sm_100a implementation of DUNK's
+ * image-to-reference registration hot path (extract -> 2-NN match -> RANSAC).
+ *
+ * This is the drop-in boundary: every entry point below is what the reference's Rust
+ * crates would bind through `extern "C"` in place of the `opencv` crate call they make
+ * today.  Citations are file:line under the reference tree (Murmeldyret/cubesat-APDS).
+ *
+ * Conventions
+ *   - All pointers are HOST pointers unless the name ends in `_dev`.
+ *   - Outputs are caller-allocated with an explicit capacity; the count comes back
+ *     through an out parameter.  Nothing allocated by the library crosses the ABI
+ *     except the opaque handles (dunk_ctx, dunk_db).
+ *   - Return value: 0 = ok, negative = OpenCV-compatible status code (the reference
+ *     surfaces `opencv::Error{code,message}`): DUNK_ERR_ASSERT (-215),
+ *     DUNK_ERR_OUT_OF_RANGE (-211), DUNK_ERR_VEC_LENGTH (-28), DUNK_ERR_BAD_ARG (-5),
+ *     DUNK_ERR_NO_MEM (-4), DUNK_ERR_CUDA (-217, "GpuApiCallError").
+ *     The message is available from dunk_last_error() (thread-local).
+ *   - Calls are synchronous and re-entrant: a context owns a pool of CUDA streams +
+ *     workspaces; concurrent callers (the reference calls from rayon workers,
+ *     preprocessor/src/main.rs:233-243) each take one slot and synchronise only it.
+ *   - There is no CPU fallback: without a CUDA device dunk_ctx_create fails.
+ */
+#ifndef DUNK_B200_H
+#define DUNK_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUNK_OK 0
+#define DUNK_ERR_NO_MEM (-4)
+#define DUNK_ERR_BAD_ARG (-5)
+#define DUNK_ERR_VEC_LENGTH (-28)
+#define DUNK_ERR_OUT_OF_RANGE (-211)
+#define DUNK_ERR_ASSERT (-215)
+#define DUNK_ERR_CUDA (-217)
+
+/* reference: feature_extraction/src/lib.rs:12-13 */
+#define DUNK_MAX_POINTS_SHIFT 18
+#define DUNK_MAX_POINTS ((1 << DUNK_MAX_POINTS_SHIFT) - 1)
+#define DUNK_DESC_BYTES 61 /* MLDB-486 -> 61 bytes (lib.rs:64-73 descriptor_size=0, channels=3) */
+#define DUNK_DESC_STRIDE 64 /* HBM row stride (16 x u32) */
+
+/* cv::KeyPoint layout (28 B) — the element type of Vector<KeyPoint>, lib.rs:15-18, :33-59 */
+typedef struct DunkKeyPoint {
+    float x, y;      /* pt */
+    float size;
+    float angle;     /* degrees */
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} DunkKeyPoint;
+
+/* cv::DMatch layout (16 B) — element of Vector<DMatch>, lib.rs:94-126 */
+typedef struct DunkDMatch {
+    int32_t query_idx;
+    int32_t train_idx;
+    int32_t img_idx;
+    float distance;
+} DunkDMatch;
+
+/* device-side local/global top-2 record: one per query (16 B) */
+typedef struct DunkTop2 {
+    uint32_t d1, i1, d2, i2; /* distance, row index; empty slot = 0xFFFFFFFF */
+} DunkTop2;
+
+/* homographier/src/homographier/mod.rs:25-31 */
+enum DunkHomographyMethod { DUNK_H_DEFAULT = 0, DUNK_H_LMEDS = 4, DUNK_H_RANSAC = 8, DUNK_H_RHO = 16 };
+/* opencv SolvePnPMethod values used by mod.rs:320-361 */
+enum DunkPnPMethod { DUNK_PNP_ITERATIVE = 0, DUNK_PNP_EPNP = 1, DUNK_PNP_P3P = 2 };
+
+typedef struct dunk_ctx dunk_ctx;
+typedef struct dunk_db dunk_db;
+
+/* ---- context ------------------------------------------------------------------ */
+int dunk_ctx_create(int device, int n_slots, dunk_ctx** out);
+void dunk_ctx_destroy(dunk_ctx* ctx);
+const char* dunk_last_error(void);
+const char* dunk_version(void);
+/* cudaStream_t of slot i (for callers that time with their own CUDA events) */
+void* dunk_ctx_stream(dunk_ctx* ctx, int slot);
+int dunk_ctx_device(dunk_ctx* ctx);
+int dunk_ctx_sm_count(dunk_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py `gpu_launches`) */
+uint64_t dunk_ctx_launch_count(dunk_ctx* ctx);
+/* CUDA-event timing on the library's own stream: begin/end bracket, returns ms */
+int dunk_timer_begin(dunk_ctx* ctx, int slot);
+int dunk_timer_end(dunk_ctx* ctx, int slot, float* ms);
+int dunk_sync(dunk_ctx* ctx, int slot);
+/* take a slot out of the pool for the caller's exclusive use with the `_dev` entry points
+ * (returns the slot index, or a negative status); give it back with dunk_ctx_release_slot */
+int dunk_ctx_reserve_slot(dunk_ctx* ctx);
+int dunk_ctx_release_slot(dunk_ctx* ctx, int slot);
+
+/* ---- stage 2: Hamming brute-force matching -------------------------------------- */
+/* replaces BFMatcher(NORM_HAMMING,false).knnMatch + Lowe ratio filter,
+ * feature_extraction/src/lib.rs:94-114.  query/train: n x desc_bytes u8 row-major.
+ * Keeps m[0] iff (float)d0 < (float)d1 * ratio (f32, strict).  k < 2 or nt < 2 ->
+ * DUNK_ERR_OUT_OF_RANGE (the reference's `i.get(1)?`, lib.rs:108); nt >= 2^18 is
+ * accepted (OpenCV asserts; the HBM path uses 32-bit row indices). */
+int dunk_knn_match_hamming(dunk_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train,
+                           int64_t nt, int desc_bytes, int k, float ratio, DunkDMatch* out,
+                           int out_cap, int* n_out);
+/* unfiltered 2-NN lists (what knn_train_match_def returns, lib.rs:103): idx/dist nq x 2 */
+int dunk_knn2_hamming(dunk_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train,
+                      int64_t nt, int desc_bytes, int32_t* idx, int32_t* dist);
+/* replaces BFMatcher(NORM_HAMMING,true).match, lib.rs:116-126 */
+int dunk_match_crosscheck_hamming(dunk_ctx* ctx, const uint8_t* query, int nq,
+                                  const uint8_t* train, int64_t nt, int desc_bytes,
+                                  DunkDMatch* out, int out_cap, int* n_out);
+
+/* ---- HBM-resident reference descriptor database (feature_database read side) ----
+ * rows = models::Keypoint (feature_database/src/models.rs:30-41): SoA arrays in HBM,
+ * descriptors padded to 64-B rows.  One dunk_db is one shard (one GPU). */
+int dunk_db_create(dunk_ctx* ctx, int64_t capacity_rows, int desc_bytes, dunk_db** out);
+void dunk_db_destroy(dunk_db* db);
+/* append n rows; kps / image_ids may be NULL (descriptor-only DB) */
+int dunk_db_append(dunk_db* db, const uint8_t* desc, const DunkKeyPoint* kps,
+                   const int32_t* image_ids, int64_t n);
+/* fill n rows with device-generated uniform random descriptors (seeded; bench config 3) */
+int dunk_db_append_random(dunk_db* db, int64_t n, uint64_t seed);
+int64_t dunk_db_size(dunk_db* db);
+/* read back rows [first, first+n) (any of the outputs may be NULL) */
+int dunk_db_read(dunk_db* db, int64_t first, int64_t n, uint8_t* desc, DunkKeyPoint* kps,
+                 int32_t* image_ids);
+/* 2-NN + ratio of host queries against the shard; train_idx = index_base + local row */
+int dunk_db_match(dunk_db* db, const uint8_t* query, int nq, float ratio, DunkDMatch* out,
+                  int out_cap, int* n_out);
+/* local top-2 of host queries against the shard (for an external merge), out: nq records */
+int dunk_db_knn2(dunk_db* db, const uint8_t* query, int nq, uint32_t index_base, DunkTop2* out);
+
+/* ---- device-pointer variants (async on slot's stream; no sync, no host copies) ---- */
+/* queries: nq x 64-B padded rows in device memory; top2_dev: nq DunkTop2 records */
+int dunk_db_knn2_dev(dunk_db* db, int slot, const void* query64_dev, int nq, uint32_t index_base,
+                     void* top2_dev);
+/* merge `n_parts` gathered DunkTop2 arrays (part-major, nq each) lexicographically by
+ * (distance,index) -> merged_dev (nq records).  SURVEY 8(e): the step after ncclAllGather */
+int dunk_top2_merge_dev(dunk_ctx* ctx, int slot, const void* parts_dev, int n_parts, int nq,
+                        void* merged_dev);
+/* ratio filter + ordered compaction of merged top-2 -> DunkDMatch list on device;
+ * count_dev: one int32 */
+int dunk_top2_ratio_dev(dunk_ctx* ctx, int slot, const void* merged_dev, int nq, float ratio,
+                        void* matches_dev, void* count_dev);
+/* pad n x desc_bytes rows to n x 64-B rows on device */
+int dunk_pad_desc_dev(dunk_ctx* ctx, int slot, const void* src_dev, int64_t n, int desc_bytes,
+                      void* dst64_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUNK_B200_H */
