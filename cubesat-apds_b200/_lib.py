@@ -85,6 +85,7 @@ SIGNATURES = {
     "dunk_top2_merge_dev": (_i, [_vp, _i, _vp, _i, _i, _vp]),
     "dunk_top2_ratio_dev": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp]),
     "dunk_pad_desc_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp]),
+    "dunk_microbench_popc": (_i, [_vp, _i, C.POINTER(_d)]),
 }
 
 
@@ -165,6 +166,12 @@ class Context:
 
     def sync(self, slot: int):
         check(load().dunk_sync(self.handle, slot))
+
+    def microbench_popc(self, iters: int = 4096) -> float:
+        """Measured POPC-pipe peak in Tpopc/s (roofline denominator of the Hamming matcher)."""
+        v = C.c_double()
+        check(load().dunk_microbench_popc(self.handle, iters, C.byref(v)))
+        return float(v.value)
 
     def timer_begin(self, slot: int):
         check(load().dunk_timer_begin(self.handle, slot))

@@ -149,6 +149,10 @@ int dunk_top2_ratio_dev(dunk_ctx* ctx, int slot, const void* merged_dev, int nq,
 int dunk_pad_desc_dev(dunk_ctx* ctx, int slot, const void* src_dev, int64_t n, int desc_bytes,
                       void* dst64_dev);
 
+/* ---- roofline denominators measured on the box ---------------------------------------- */
+/* POPC-pipe peak in 1e12 popc/s (best of 4 timed launches of `iters` x 32 popc per thread) */
+int dunk_microbench_popc(dunk_ctx* ctx, int iters, double* tpopc_per_s);
+
 #ifdef __cplusplus
 }
 #endif
