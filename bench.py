@@ -250,10 +250,13 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(nq, args.ratio)
         print(json.dumps(out), flush=True)
-    db.close()
-    ctx.release_slot(slot)
+    barrier()
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    # torch frees its tensors at interpreter exit with record_stream bookkeeping on our external
+    # stream; leave the context alive and skip the teardown race
+    os._exit(0)
 
 
 def _append_random_global(lib, db, n, seed, row_offset):

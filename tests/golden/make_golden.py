@@ -52,6 +52,39 @@ def make_match():
     print("match_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
+H_TRUE = np.array([[0.98, -0.12, 60], [0.10, 1.03, -40], [1e-5, -2e-5, 1]])
+
+
+def ransac_case(n, out_frac, sigma, seed, H=H_TRUE):
+    r = np.random.default_rng(seed)
+    src = r.uniform(0, 1024, (n, 2)).astype(np.float32)
+    p = np.c_[src, np.ones(n)] @ H.T
+    dst = (p[:, :2] / p[:, 2:]) + r.normal(0, sigma, (n, 2))
+    k = int(n * out_frac)
+    dst[:k] = r.uniform(0, 1024, (k, 2))
+    return src, dst.astype(np.float32)
+
+
+RANSAC_CASES = [(50, 0.2, 0.5), (200, 0.4, 0.5), (1000, 0.3, 1.0), (2000, 0.4, 0.5), (500, 0.6, 0.3),
+                (100, 0.0, 0.1), (300, 0.5, 1.5), (1500, 0.1, 0.8), (64, 0.7, 0.5), (800, 0.45, 0.7),
+                (5, 0.0, 0.0), (4, 0.0, 0.0)]
+
+
+def make_ransac():
+    """cv2.findHomography(src, dst, RANSAC, thr) — mod.rs:243-250 (maxIters 2000, conf 0.995)."""
+    out = {"opencv_version": np.array(cv2.__version__), "n_cases": np.array(len(RANSAC_CASES) + 1)}
+    cases = [ransac_case(n, of, sg, seed) + (3.0,) for seed, (n, of, sg) in enumerate(RANSAC_CASES)]
+    # the reference's own test homography_success (mod.rs:436-472): 10x10 grid onto itself, thr 1
+    grid = np.array([(i, j) for i in range(1, 11) for j in range(1, 11)], dtype=np.float32)
+    cases.append((grid, grid.copy(), 1.0))
+    for i, (src, dst, thr) in enumerate(cases):
+        H, mask = cv2.findHomography(src, dst, cv2.RANSAC, thr)
+        out[f"c{i}_src"], out[f"c{i}_dst"], out[f"c{i}_thr"] = src, dst, np.array(thr)
+        out[f"c{i}_H"], out[f"c{i}_mask"] = H, mask.ravel().astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "ransac_golden.npz"), **out)
+    print("ransac_golden.npz:", len(cases), "cases")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("match", "all"):

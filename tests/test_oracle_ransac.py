@@ -1,0 +1,54 @@
+"""CPU: the RANSAC-homography oracle reproduces cv2 4.13.0 `findHomography(RANSAC)` on the
+committed golden vectors: masks bit-exact, H within 1e-4 relative (north_star tolerance)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ransac_oracle as ro
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ransac_golden.npz"))
+N = int(G["n_cases"])
+H_RTOL = 1e-4
+
+
+def rel_err(H, Href):
+    return np.abs(H - Href).max() / np.abs(Href).max()
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_find_homography_matches_cv2(i):
+    src, dst, thr = G[f"c{i}_src"], G[f"c{i}_dst"], float(G[f"c{i}_thr"])
+    H, mask = ro.find_homography_ransac(src, dst, thr)
+    assert np.array_equal(mask, G[f"c{i}_mask"])
+    assert rel_err(H, G[f"c{i}_H"]) < H_RTOL
+
+
+def test_reference_test_identity_grid():
+    """homographier mod.rs:436-472 homography_success: rounded H is the identity."""
+    i = N - 1
+    H, mask = ro.find_homography_ransac(G[f"c{i}_src"], G[f"c{i}_dst"], 1.0)
+    assert np.array_equal(np.round(H), np.eye(3)) and mask.all()
+
+
+def test_too_few_points():
+    with pytest.raises(ValueError):
+        ro.find_homography_ransac(np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32))
+
+
+def test_rng_stream_known_values():
+    """cv::RNG MWC recurrence from state 2^64-1."""
+    r = ro.CvRNG()
+    seq = [r.next() for _ in range(3)]
+    s = 0xFFFFFFFFFFFFFFFF
+    exp = []
+    for _ in range(3):
+        s = ((s & 0xFFFFFFFF) * 4164903690 + (s >> 32)) & 0xFFFFFFFFFFFFFFFF
+        exp.append(s & 0xFFFFFFFF)
+    assert seq == exp
+
+
+def test_update_num_iters():
+    assert ro.ransac_update_num_iters(0.995, 0.0, 4, 2000) == 0
+    assert ro.ransac_update_num_iters(0.995, 1.0, 4, 2000) == 2000
+    assert ro.ransac_update_num_iters(0.995, 0.5, 4, 2000) == ro.cv_round(np.log(0.005) / np.log(1 - 0.5 ** 4))
