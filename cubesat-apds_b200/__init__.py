@@ -10,6 +10,7 @@ from . import _lib
 from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, TOP2_DTYPE, Context, DunkError, default_context)
 from . import feature_extraction
 from . import feature_database
+from . import homographier
 
-__all__ = ["_lib", "Context", "DunkError", "default_context", "feature_extraction", "feature_database",
+__all__ = ["_lib", "Context", "DunkError", "default_context", "feature_extraction", "feature_database", "homographier",
            "DMATCH_DTYPE", "KEYPOINT_DTYPE", "TOP2_DTYPE"]

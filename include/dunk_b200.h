@@ -149,6 +149,27 @@ int dunk_top2_ratio_dev(dunk_ctx* ctx, int slot, const void* merged_dev, int nq,
 int dunk_pad_desc_dev(dunk_ctx* ctx, int slot, const void* src_dev, int64_t n, int desc_bytes,
                       void* dst64_dev);
 
+/* ---- stage 3: RANSAC homography ---------------------------------------------------------
+ * replaces cv::findHomography(src, dst, mask, method, thr) as called by find_homography_mat,
+ * homographier/src/homographier/mod.rs:231-259 (5-arg overload: maxIters 2000, conf 0.995).
+ * src/dst: n x 2 f32 (Point2f).  H: 9 f64 row-major, H[8] = 1.  mask: n u8 (may be NULL).
+ * method: DUNK_H_RANSAC (8) or DUNK_H_DEFAULT (0, least squares on all pairs); LMEDS/RHO ->
+ * DUNK_ERR_BAD_ARG.  n < 4 -> DUNK_ERR_VEC_LENGTH (-28, OpenCV's StsVecLengthErr).
+ * *found = 0 when no model was found (OpenCV returns an empty Mat -> MatError::Empty). */
+int dunk_find_homography(dunk_ctx* ctx, const float* src, const float* dst, int n, int method,
+                         double thr, double* H, uint8_t* mask, int* found);
+/* batch of independent problems (one CTA each): points concatenated, offsets[n_problems+1];
+ * H: n_problems x 9; mask: offsets[n_problems] bytes; info: n_problems x 4 int32 =
+ * {found, inliers, RANSAC iterations run, hypotheses scored} */
+int dunk_find_homography_batch(dunk_ctx* ctx, const float* src, const float* dst,
+                               const int* offsets, int n_problems, int method, double thr,
+                               double* H, uint8_t* mask, int* info);
+/* parity hook (north_star: "identical seeded hypothesis sets giving identical inlier counts"):
+ * scores explicit 4-index samples; counts: n_hyp int32 (-1 = degenerate), Hs: n_hyp x 9 f64 */
+int dunk_ransac_score_hypotheses(dunk_ctx* ctx, const float* src, const float* dst, int n,
+                                 const int* samples, int n_hyp, double thr, int* counts,
+                                 double* Hs);
+
 /* ---- roofline denominators measured on the box ---------------------------------------- */
 /* POPC-pipe peak in 1e12 popc/s (best of 4 timed launches of `iters` x 32 popc per thread) */
 int dunk_microbench_popc(dunk_ctx* ctx, int iters, double* tpopc_per_s);

@@ -260,14 +260,16 @@ def lm_refine(H, src, dst, max_iters=10):
 def _solve_eig(A, b):
     """cv::solve(A, b, DECOMP_EIG) for symmetric A: x = V diag(1/w) V^T b (tiny w -> 0)."""
     w, V = np.linalg.eigh(A)
+    thr = 2 * DBL_EPSILON * np.abs(w).sum()      # SVBkSb threshold
     y = V.T @ b
-    y = np.where(np.abs(w) > DBL_EPSILON, y / np.where(w == 0, 1, w), 0.0)
+    y = np.where(np.abs(w) > thr, y / np.where(w == 0, 1, w), 0.0)
     return V @ y
 
 
 def _inv_eig(A):
     w, V = np.linalg.eigh(A)
-    wi = np.where(np.abs(w) > DBL_EPSILON, 1.0 / np.where(w == 0, 1, w), 0.0)
+    thr = 2 * DBL_EPSILON * np.abs(w).sum()
+    wi = np.where(np.abs(w) > thr, 1.0 / np.where(w == 0, 1, w), 0.0)
     return (V * wi) @ V.T
 
 

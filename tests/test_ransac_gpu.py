@@ -1,0 +1,110 @@
+"""GPU parity: batched RANSAC homography vs the oracle / cv2 4.13.0 goldens.
+Contract (north_star): identical hypothesis sets -> identical inlier counts; masks bit-exact;
+homography entries within 1e-4 relative error."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ransac_oracle as ro
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ransac_golden.npz"))
+N = int(G["n_cases"])
+H_RTOL = 1e-4
+
+
+def rel_err(H, Href):
+    return np.abs(H - Href).max() / np.abs(Href).max()
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_find_homography_vs_cv2_golden(dunk, ctx, i):
+    hg = dunk.homographier
+    src, dst, thr = G[f"c{i}_src"], G[f"c{i}_dst"], float(G[f"c{i}_thr"])
+    H, mask = hg.find_homography_mat(src, dst, hg.HomographyMethod.RANSAC, thr, ctx)
+    assert np.array_equal(mask.mat.ravel(), G[f"c{i}_mask"])
+    assert rel_err(H.mat, G[f"c{i}_H"]) < H_RTOL
+
+
+@pytest.mark.parametrize("i", [0, 1, 3, 4, 8])
+def test_identical_hypothesis_sets_identical_counts(dunk, ctx, i):
+    src, dst, thr = G[f"c{i}_src"], G[f"c{i}_dst"], float(G[f"c{i}_thr"])
+    samples = ro.hypothesis_stream(src, dst, 300)
+    counts, Hs = dunk.homographier.score_hypotheses(src, dst, samples, thr, ctx)
+    oc, oH = ro.score_hypotheses(src, dst, samples, thr)
+    assert np.array_equal(counts, oc)
+    ok = np.isfinite(oH).all(axis=1)
+    scale = np.abs(oH[ok]).max(axis=1, keepdims=True)
+    assert (np.abs(Hs[ok] - oH[ok]) / scale).max() < 1e-6
+
+
+def test_reference_homography_success(dunk, ctx):
+    """mod.rs:436-472: 10x10 grid onto itself, RANSAC thr 1.0 -> rounded identity."""
+    hg = dunk.homographier
+    pts = np.array([(i, j) for i in range(1, 11) for j in range(1, 11)], dtype=np.float32)
+    H, mask = hg.find_homography_mat(pts, pts.copy(), hg.HomographyMethod.RANSAC, 1.0, ctx)
+    for r in range(3):
+        for c in range(3):
+            assert round(float(H.at_2d(r, c))) == (1 if r == c else 0)
+    assert mask.mat.all()
+
+
+def test_batch_equals_single(dunk, ctx):
+    hg = dunk.homographier
+    ids = [0, 2, 5, 9]
+    Hb, masks, info = hg.find_homography_batch([G[f"c{i}_src"] for i in ids], [G[f"c{i}_dst"] for i in ids], 3.0,
+                                               hg.HomographyMethod.RANSAC, ctx)
+    for k, i in enumerate(ids):
+        assert np.array_equal(masks[k], G[f"c{i}_mask"]) and info[k, 0] == 1
+        assert info[k, 1] == int(G[f"c{i}_mask"].sum())
+        assert rel_err(Hb[k], G[f"c{i}_H"]) < H_RTOL
+
+
+def test_default_method_least_squares(dunk, ctx):
+    hg = dunk.homographier
+    src, dst = G["c5_src"], G["c5_dst"]            # no outliers
+    H, mask = hg.find_homography_mat(src, dst, None, None, ctx)
+    assert mask is None
+    import_ok = True
+    try:
+        import cv2
+    except Exception:
+        import_ok = False
+    if import_ok:
+        Hc, _ = cv2.findHomography(src, dst, 0)
+        assert rel_err(H.mat, Hc) < H_RTOL
+
+
+def test_errors(dunk, ctx):
+    hg = dunk.homographier
+    p3 = np.zeros((3, 2), np.float32)
+    with pytest.raises(hg.MatError) as e:
+        hg.find_homography_mat(p3, p3, hg.HomographyMethod.RANSAC, 3.0, ctx)
+    assert e.value.kind == "Opencv" and e.value.code == -28
+    # all points identical: no valid sample ever -> no model -> MatError::Empty
+    same = np.ones((20, 2), np.float32)
+    with pytest.raises(hg.MatError) as e:
+        hg.find_homography_mat(same, same, hg.HomographyMethod.RANSAC, 3.0, ctx)
+    assert e.value.kind == "Empty"
+    with pytest.raises(hg.MatError):
+        hg.find_homography_mat(G["c0_src"], G["c0_dst"], hg.HomographyMethod.RHO, 3.0, ctx)
+
+
+def test_random_cases_vs_oracle(dunk, ctx):
+    """fresh seeded cases (not in the golden file): GPU == oracle restatement."""
+    hg = dunk.homographier
+    Ht = np.array([[1.1, 0.05, -30], [-0.08, 0.95, 25], [3e-5, 1e-5, 1]])
+    for seed in range(20, 26):
+        r = np.random.default_rng(seed)
+        n = int(r.integers(30, 1500))
+        src = r.uniform(0, 1024, (n, 2)).astype(np.float32)
+        p = np.c_[src, np.ones(n)] @ Ht.T
+        dst = p[:, :2] / p[:, 2:] + r.normal(0, 0.7, (n, 2))
+        k = int(n * r.uniform(0, 0.6))
+        dst[:k] = r.uniform(0, 1024, (k, 2))
+        dst = dst.astype(np.float32)
+        Ho, mo = ro.find_homography_ransac(src, dst, 3.0)
+        H, mask = hg.find_homography_mat(src, dst, hg.HomographyMethod.RANSAC, 3.0, ctx)
+        assert np.array_equal(mask.mat.ravel(), mo)
+        assert rel_err(H.mat, Ho) < H_RTOL
