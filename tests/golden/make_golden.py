@@ -85,6 +85,44 @@ def make_ransac():
     print("ransac_golden.npz:", len(cases), "cases")
 
 
+def synth(n, seed, m=None):
+    """SURVEY 8d synthetic image: multi-scale smoothed noise, min-max normalised to u8 (h=n, w=m)."""
+    m = m or n
+    rng = np.random.default_rng(seed)
+    acc = np.zeros((n, m), np.float64)
+    for s in (1, 2, 4, 8, 16, 32):
+        acc += cv2.resize(rng.standard_normal((n // s + 1, m // s + 1)), (m, n), interpolation=cv2.INTER_CUBIC) * np.sqrt(s)
+    acc = (acc - acc.min()) / (acc.max() - acc.min())
+    return (acc * 255).astype(np.uint8)
+
+
+def akaze_cv(img, max_points=(1 << 18) - 1):
+    """lib.rs:64-79"""
+    ak = cv2.AKAZE_create(cv2.AKAZE_DESCRIPTOR_MLDB, 0, 3, 0.001, 4, 4, cv2.KAZE_DIFF_PM_G2, max_points)
+    kps, desc = ak.detectAndCompute(img, None)
+    k = np.array([(p.pt[0], p.pt[1], p.size, p.angle, p.response, p.octave, p.class_id) for p in kps],
+                 dtype=[("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                        ("octave", "<i4"), ("class_id", "<i4")])
+    return k, (desc if desc is not None else np.zeros((0, 61), np.uint8))
+
+
+def make_akaze():
+    out = {"opencv_version": np.array(cv2.__version__)}
+    imgs = {"a": synth(320, 21, 384),          # non-square, 3 octaves
+            "b": synth(512, 1)}                # 4 octaves
+    rng = np.random.default_rng(5)
+    g = synth(200, 22, 260)
+    col = np.clip(g[..., None].astype(np.int32) + rng.integers(-40, 40, (200, 260, 3)), 0, 255).astype(np.uint8)
+    imgs["c"] = col                            # BGR input (cvtColor path), 2 octaves
+    for name, img in imgs.items():
+        k, d = akaze_cv(img)
+        out[f"{name}_img"], out[f"{name}_kps"], out[f"{name}_desc"] = img, k, d
+    k, d = akaze_cv(imgs["b"], 100)            # max_points path (top-100 by response)
+    out["b100_kps"], out["b100_desc"] = k, d
+    np.savez_compressed(os.path.join(HERE, "akaze_golden.npz"), **out)
+    print("akaze_golden.npz:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("match", "all"):

@@ -1,0 +1,68 @@
+"""CPU: the AKAZE oracle reproduces cv2 4.13.0 detectAndCompute on the committed golden images
+within the tolerances stated in tests/akaze_compare.py (and far tighter in practice)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import akaze_oracle as ao
+from tests.akaze_compare import assert_parity, compare
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "akaze_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["a", "c"])
+def test_detect_and_compute_vs_cv2_golden(name):
+    kps, desc = ao.detect_and_compute(G[f"{name}_img"])
+    rep = compare(G[f"{name}_kps"], G[f"{name}_desc"], kps, desc)
+    assert_parity(rep)
+    # the restatement is in fact much closer than the contract tolerances
+    assert rep["recall"] == 1.0 and rep["precision"] == 1.0
+    assert rep["pos_err_max"] < 2e-3 and rep["desc_exact_frac"] >= 0.99
+    # same output order as OpenCV (levels ascending, row-major inside a level)
+    assert np.array_equal(kps["class_id"], G[f"{name}_kps"]["class_id"])
+
+
+def test_max_points_keeps_strongest():
+    """lib.rs:72 max_points: the 100 largest responses survive."""
+    kps, desc = ao.detect_and_compute(G["b_img"], max_points=100, want_desc=False)
+    ref = G["b100_kps"]
+    assert len(kps) == 100
+    assert np.allclose(np.sort(kps["response"]), np.sort(ref["response"]), rtol=1e-4)
+
+
+def test_level_table_1024():
+    """SURVEY Appendix B."""
+    lv = ao.level_table(1024, 1024)
+    assert len(lv) == 16
+    assert [e["sigma_size"] for e in lv] == [2, 3, 3, 4] * 4
+    assert [e["border"] for e in lv] == [29, 43, 43, 58] * 4
+    assert [len(e["tau"]) for e in lv] == [0, 3, 3, 4, 4, 5, 6, 7, 8, 10, 12, 14, 17, 20, 24, 29]
+    assert [e["w"] for e in lv] == [1024] * 4 + [512] * 4 + [256] * 4 + [128] * 4
+
+
+def test_small_image_octave_cut():
+    lv = ao.level_table(260, 200)        # 130x100 ok, 65x50 < 80 wide -> 2 octaves
+    assert len(lv) == 8
+
+
+def test_fed_tau_sums_to_process_time():
+    for T in (0.53, 1.5, 10.24, 68.0):
+        tau = ao.fed_tau_by_process_time(T)
+        assert abs(float(np.sum(tau)) - T) < 1e-4 * max(1, T)
+
+
+def test_primitives_against_cv2_when_available():
+    cv2 = pytest.importorskip("cv2")
+    g = G["a_img"].astype(np.float32) / 255
+    assert np.abs(cv2.GaussianBlur(g, (9, 9), 1.6, 1.6, borderType=cv2.BORDER_REPLICATE) - ao.gaussian_blur(g, 9, 1.6)).max() < 1e-6
+    sm = ao.gaussian_blur(g, 5, 1.0)
+    assert np.abs(cv2.Scharr(sm, cv2.CV_32F, 1, 0) - ao.scharr(sm, 1, 0)).max() < 1e-5
+    assert np.abs(cv2.resize(g, (192, 160), interpolation=cv2.INTER_AREA) - ao.halfsample_area(g)).max() < 1e-6
+    kx, ky = ao.derivative_kernels(0, 1, 4)
+    assert np.abs(cv2.sepFilter2D(sm, cv2.CV_32F, kx, ky) - ao.sep_filter(sm, kx, ky, "reflect101")).max() < 1e-6
+    y = np.random.default_rng(0).standard_normal(500).astype(np.float32)
+    x = np.random.default_rng(1).standard_normal(500).astype(np.float32)
+    assert np.array_equal(np.array([cv2.fastAtan2(float(a), float(b)) for a, b in zip(y, x)], np.float32), ao.fast_atan2_deg(y, x))
+    bgr = G["c_img"]
+    assert np.array_equal((ao.to_gray_f32(bgr) * 255).round().astype(np.uint8), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
