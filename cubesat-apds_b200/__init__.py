@@ -9,6 +9,7 @@ Everything numeric happens in libdunk_b200.so (csrc/, C ABI in include/dunk_b200
 from . import _lib
 from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, TOP2_DTYPE, Context, DunkError, default_context)
 from . import feature_extraction
+from . import _extract
 from . import feature_database
 from . import homographier
 

@@ -86,6 +86,9 @@ SIGNATURES = {
     "dunk_top2_ratio_dev": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp]),
     "dunk_pad_desc_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp]),
     "dunk_microbench_popc": (_i, [_vp, _i, C.POINTER(_d)]),
+    "dunk_akaze_extract": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _pi]),
+    "dunk_akaze_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _i, _vp, _vp, _i, _vp]),
+    "dunk_akaze_debug_level": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _pi, _pi, _pi]),
     "dunk_find_homography": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _pi]),
     "dunk_find_homography_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "dunk_ransac_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _vp, _vp]),

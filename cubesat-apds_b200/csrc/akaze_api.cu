@@ -1,0 +1,204 @@
+// C ABI for stage 1 (AKAZE extraction) + workspace management.
+#include <algorithm>
+#include <cstring>
+#include "akaze.h"
+#include "match.h"
+
+namespace dunk {
+
+static size_t al(size_t b) { return (b + 255) & ~size_t(255); }
+
+static int pow2_at_least(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+size_t akaze_workspace_bytes(const LevelTable& lt, int frames, int cand_cap, int kp_cap) {
+    const size_t pyr = lt.pyramid_floats, plane = (size_t)lt.width * lt.height;
+    int total_rows = 0;
+    for (int i = 0; i < lt.n_levels; ++i) total_rows += lt.lv[i].h;
+    size_t b = 0;
+    b += 4 * al(frames * pyr * 4);                       // Lt Lx Ly Ldet
+    b += 3 * al(frames * plane * 4);                     // Lsmooth Lflow Ltmp
+    b += al(frames * 4) + al((size_t)frames * 300 * 4) + al(frames * 4);
+    b += 2 * al((size_t)frames * cand_cap * sizeof(Cand));
+    b += al(frames * 4);
+    b += 2 * al((size_t)frames * (total_rows + 1) * 4) + al((size_t)frames * total_rows * 4);
+    b += al((size_t)frames * cand_cap);
+    b += al((size_t)frames * cand_cap * 3 * 4);
+    b += al((size_t)frames * kp_cap * sizeof(DunkKeyPoint));
+    b += al(frames * 4) + al((kMaxLevels + 1) * 4);
+    b += al((size_t)frames * kp_cap * 64);
+    b += al((size_t)frames * pow2_at_least(kp_cap) * 8);
+    return b;
+}
+
+void akaze_carve_workspace(void* base, const LevelTable& lt, int frames, int cand_cap, int kp_cap, AkazeWorkspace* ws) {
+    const size_t pyr = lt.pyramid_floats, plane = (size_t)lt.width * lt.height;
+    int total_rows = 0;
+    for (int i = 0; i < lt.n_levels; ++i) total_rows += lt.lv[i].h;
+    char* p = (char*)base;
+    auto take = [&](size_t bytes) { void* r = p; p += al(bytes); return r; };
+    ws->frames = frames; ws->cand_cap = cand_cap; ws->kp_cap = kp_cap; ws->total_rows = total_rows;
+    ws->Lt = (float*)take(frames * pyr * 4);
+    ws->Lx = (float*)take(frames * pyr * 4);
+    ws->Ly = (float*)take(frames * pyr * 4);
+    ws->Ldet = (float*)take(frames * pyr * 4);
+    ws->Lsmooth = (float*)take(frames * plane * 4);
+    ws->Lflow = (float*)take(frames * plane * 4);
+    ws->Ltmp = (float*)take(frames * plane * 4);
+    ws->hmax = (float*)take(frames * 4);
+    ws->hist = (int*)take((size_t)frames * 300 * 4);
+    ws->kcontrast = (float*)take(frames * 4);
+    ws->cand_raw = (Cand*)take((size_t)frames * cand_cap * sizeof(Cand));
+    ws->cand = (Cand*)take((size_t)frames * cand_cap * sizeof(Cand));
+    ws->cand_count = (int*)take(frames * 4);
+    ws->row_count = (int*)take((size_t)frames * (total_rows + 1) * 4);
+    ws->row_start = (int*)take((size_t)frames * (total_rows + 1) * 4);
+    ws->row_fill = (int*)take((size_t)frames * total_rows * 4);
+    ws->state = (unsigned char*)take((size_t)frames * cand_cap);
+    ws->aux = (int*)take((size_t)frames * cand_cap * 3 * 4);
+    ws->kps = (DunkKeyPoint*)take((size_t)frames * kp_cap * sizeof(DunkKeyPoint));
+    ws->kp_count = (int*)take(frames * 4);
+    ws->kp_level_start = (int*)take((kMaxLevels + 1) * 4);
+    ws->desc64 = (uint4*)take((size_t)frames * kp_cap * 64);
+    ws->sort_keys = (float*)take((size_t)frames * pow2_at_least(kp_cap) * 8);
+}
+
+// default raw-candidate capacity per frame: 3x3 maxima are sparse (<= 1/4 of the pixels in theory,
+// a few 1e-3 in practice); 1/32 of the level-0 pixels leaves a wide margin
+static int default_cand_cap(int w, int h) {
+    long long c = (long long)w * h / 32;
+    c = std::max<long long>(c, 2048);
+    c = std::min<long long>(c, 1 << 20);
+    return (int)c;
+}
+
+int akaze_run(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeWorkspace& ws,
+              const unsigned char* images_dev, size_t image_stride, int row_stride, int channels, int frames,
+              int max_points) {
+    int rc = akaze_build_scale_space(ctx, st, lt, ws, images_dev, image_stride, row_stride, channels, frames);
+    if (rc) return rc;
+    if ((rc = akaze_detect(ctx, st, lt, ws, frames, 0.001f, max_points))) return rc;
+    return akaze_describe(ctx, st, lt, ws, frames);
+}
+
+}  // namespace dunk
+
+using namespace dunk;
+
+extern "C" {
+
+int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames, int rows, int cols, int channels,
+                             int row_stride_bytes, size_t frame_stride_bytes, int max_points, DunkKeyPoint* kps,
+                             uint8_t* desc, int cap_per_frame, int* counts) {
+    DUNK_REQUIRE(ctx && counts, DUNK_ERR_BAD_ARG, "dunk_akaze_extract: NULL ctx / counts");
+    DUNK_REQUIRE(n_frames >= 0, DUNK_ERR_BAD_ARG, "dunk_akaze_extract: n_frames < 0");
+    if (n_frames == 0) return DUNK_OK;
+    // OpenCV: detectAndCompute on an empty image asserts (-215)
+    DUNK_REQUIRE(images && rows > 0 && cols > 0, DUNK_ERR_ASSERT, "dunk_akaze_extract: empty image");
+    DUNK_REQUIRE(channels == 1 || channels == 3 || channels == 4, DUNK_ERR_ASSERT,
+                 "dunk_akaze_extract: %d channels (8UC1, 8UC3 BGR or 8UC4 BGRA expected)", channels);
+    DUNK_REQUIRE(rows >= 16 && cols >= 16, DUNK_ERR_ASSERT, "dunk_akaze_extract: image %dx%d too small", cols, rows);
+    DUNK_REQUIRE(row_stride_bytes >= cols * channels, DUNK_ERR_BAD_ARG, "dunk_akaze_extract: row stride < row bytes");
+    DUNK_REQUIRE(kps && desc && cap_per_frame > 0, DUNK_ERR_BAD_ARG, "dunk_akaze_extract: NULL / empty output");
+    if (max_points <= 0) max_points = 0;   // AKAZE: max_points <= 0 means unlimited
+    const size_t img_bytes = (size_t)rows * row_stride_bytes;
+    if (frame_stride_bytes == 0) frame_stride_bytes = img_bytes;
+    DUNK_REQUIRE(frame_stride_bytes >= img_bytes, DUNK_ERR_BAD_ARG, "dunk_akaze_extract: frame stride < frame bytes");
+
+    const LevelTable lt = make_level_table(cols, rows);
+    const int cand_cap = default_cand_cap(cols, rows);
+    const int kp_cap = cand_cap;
+    SlotGuard g(ctx);
+    cudaStream_t st = g.stream();
+    // sub-batch so the workspace stays bounded (~100 MB per 1024^2 frame)
+    size_t free_b = 0, total_b = 0;
+    DUNK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_frame = akaze_workspace_bytes(lt, 1, cand_cap, kp_cap) + frame_stride_bytes + 4096;
+    size_t budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)8 << 30);
+    int sub = (int)std::max<size_t>(1, std::min<size_t>(n_frames, budget / per_frame));
+    sub = std::min(sub, 64);
+    const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cand_cap, kp_cap);
+    const size_t need = al(ws_bytes) + al((size_t)sub * frame_stride_bytes) + al((size_t)sub * kp_cap * 61);
+    void* scratch = ctx->dev_scratch(g.s, need);
+    if (!scratch) return DUNK_ERR_NO_MEM;
+    AkazeWorkspace ws;
+    akaze_carve_workspace(scratch, lt, sub, cand_cap, kp_cap, &ws);
+    unsigned char* d_img = (unsigned char*)scratch + al(ws_bytes);
+    uint8_t* d_desc61 = d_img + al((size_t)sub * frame_stride_bytes);
+    std::vector<int> h_counts(sub), h_cand(sub);
+    for (int f0 = 0; f0 < n_frames; f0 += sub) {
+        const int nf = std::min(sub, n_frames - f0);
+        DUNK_CUDA(cudaMemcpyAsync(d_img, images + (size_t)f0 * frame_stride_bytes, (size_t)nf * frame_stride_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        int rc = akaze_run(ctx, st, lt, ws, d_img, frame_stride_bytes, row_stride_bytes, channels, nf, max_points);
+        if (rc) return rc;
+        DUNK_CUDA(cudaMemcpyAsync(h_counts.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaMemcpyAsync(h_cand.data(), ws.cand_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaStreamSynchronize(st));
+        for (int f = 0; f < nf; ++f) {
+            DUNK_REQUIRE(h_cand[f] <= cand_cap, DUNK_ERR_NO_MEM,
+                         "dunk_akaze_extract: frame %d produced %d raw extrema, capacity %d", f0 + f, h_cand[f], cand_cap);
+            const int n = h_counts[f];
+            DUNK_REQUIRE(n <= cap_per_frame, DUNK_ERR_NO_MEM,
+                         "dunk_akaze_extract: frame %d has %d keypoints, output capacity %d", f0 + f, n, cap_per_frame);
+            counts[f0 + f] = n;
+            if (n == 0) continue;
+            rc = launch_unpad_rows(ctx, st, ws.desc64 + (size_t)f * kp_cap * 4, n, 61, d_desc61 + (size_t)f * kp_cap * 61);
+            if (rc) return rc;
+            DUNK_CUDA(cudaMemcpyAsync(kps + (size_t)(f0 + f) * cap_per_frame, ws.kps + (size_t)f * kp_cap,
+                                      (size_t)n * sizeof(DunkKeyPoint), cudaMemcpyDeviceToHost, st));
+            DUNK_CUDA(cudaMemcpyAsync(desc + (size_t)(f0 + f) * cap_per_frame * 61, d_desc61 + (size_t)f * kp_cap * 61,
+                                      (size_t)n * 61, cudaMemcpyDeviceToHost, st));
+        }
+        DUNK_CUDA(cudaStreamSynchronize(st));
+    }
+    return DUNK_OK;
+}
+
+int dunk_akaze_extract(dunk_ctx* ctx, const uint8_t* image, int rows, int cols, int channels, int row_stride_bytes,
+                       int max_points, DunkKeyPoint* kps, uint8_t* desc, int cap, int* n_out) {
+    DUNK_REQUIRE(n_out, DUNK_ERR_BAD_ARG, "dunk_akaze_extract: n_out is NULL");
+    *n_out = 0;
+    return dunk_akaze_extract_batch(ctx, image, 1, rows, cols, channels, row_stride_bytes, 0, max_points, kps, desc, cap,
+                                    n_out);
+}
+
+}  // extern "C"
+
+/* per-stage parity hook: scale space of one frame, planes of one evolution level copied back */
+extern "C" int dunk_akaze_debug_level(dunk_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
+                                      int row_stride_bytes, int level, float* Lt, float* Lx, float* Ly, float* Ldet,
+                                      float* kcontrast, int* level_w, int* level_h, int* n_levels) {
+    DUNK_REQUIRE(ctx && image && rows >= 16 && cols >= 16, DUNK_ERR_BAD_ARG, "dunk_akaze_debug_level: bad argument");
+    const LevelTable lt = make_level_table(cols, rows);
+    if (n_levels) *n_levels = lt.n_levels;
+    DUNK_REQUIRE(level >= 0 && level < lt.n_levels, DUNK_ERR_OUT_OF_RANGE, "dunk_akaze_debug_level: level %d of %d",
+                 level, lt.n_levels);
+    SlotGuard g(ctx);
+    cudaStream_t st = g.stream();
+    const int cand_cap = 2048;
+    const size_t ws_bytes = akaze_workspace_bytes(lt, 1, cand_cap, cand_cap);
+    const size_t img_bytes = (size_t)rows * row_stride_bytes;
+    void* scratch = ctx->dev_scratch(g.s, al(ws_bytes) + al(img_bytes));
+    if (!scratch) return DUNK_ERR_NO_MEM;
+    AkazeWorkspace ws;
+    akaze_carve_workspace(scratch, lt, 1, cand_cap, cand_cap, &ws);
+    unsigned char* d_img = (unsigned char*)scratch + al(ws_bytes);
+    DUNK_CUDA(cudaMemcpyAsync(d_img, image, img_bytes, cudaMemcpyHostToDevice, st));
+    int rc = akaze_build_scale_space(ctx, st, lt, ws, d_img, img_bytes, row_stride_bytes, channels, 1);
+    if (rc) return rc;
+    const LevelInfo& e = lt.lv[level];
+    const size_t n = (size_t)e.w * e.h * 4;
+    if (level_w) *level_w = e.w;
+    if (level_h) *level_h = e.h;
+    if (Lt) DUNK_CUDA(cudaMemcpyAsync(Lt, ws.Lt + e.plane_off, n, cudaMemcpyDeviceToHost, st));
+    if (Lx) DUNK_CUDA(cudaMemcpyAsync(Lx, ws.Lx + e.plane_off, n, cudaMemcpyDeviceToHost, st));
+    if (Ly) DUNK_CUDA(cudaMemcpyAsync(Ly, ws.Ly + e.plane_off, n, cudaMemcpyDeviceToHost, st));
+    if (Ldet) DUNK_CUDA(cudaMemcpyAsync(Ldet, ws.Ldet + e.plane_off, n, cudaMemcpyDeviceToHost, st));
+    if (kcontrast) DUNK_CUDA(cudaMemcpyAsync(kcontrast, ws.kcontrast, 4, cudaMemcpyDeviceToHost, st));
+    DUNK_CUDA(cudaStreamSynchronize(st));
+    return DUNK_OK;
+}

@@ -1,0 +1,261 @@
+// AKAZE stage 1c: dominant orientation + MLDB-486 descriptor, one warp per keypoint.
+// Follows Compute_Main_Orientation / MLDB_Full_Descriptor_Invoker of OpenCV's AKAZEFeatures.cpp as
+// restated in oracle/akaze_oracle.py: same sample tables, same f32 operation order (the sums are
+// kept sequential per window / per grid cell so that rounding matches), fastAtan2 polynomial.
+#include "akaze.h"
+#include <cfloat>
+#include <cmath>
+
+namespace dunk {
+
+namespace {
+
+struct OriTable {
+    signed char xi[109], yi[109];
+    float w[109];
+};
+__constant__ OriTable c_ori;
+__constant__ unsigned char c_cmp_a[486], c_cmp_b[486];   // value indices (cell * 3 + channel)
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    // cv::hal::fastAtan32f (mathfuncs_core), degrees
+    const float p1 = 0.9997878412794807f * (float)(180 / M_PI);
+    const float p3 = -0.3258083974640975f * (float)(180 / M_PI);
+    const float p5 = 0.1555786518463281f * (float)(180 / M_PI);
+    const float p7 = -0.04432655554792128f * (float)(180 / M_PI);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kSlices = 42, kWin = 7, kAng = 109;
+
+struct OriShared {
+    float rx[kAng], ry[kAng];
+    unsigned char bin[kAng], sorted[kAng];
+    int cum[kSlices + 1];
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_orientation(DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restrict__ kp_count,
+              const float* __restrict__ Lx, const float* __restrict__ Ly, size_t pyr_stride, LevelsDev lv) {
+    __shared__ OriShared sh_all[kWarpsPerBlock];
+    const int f = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ki = blockIdx.x * kWarpsPerBlock + warp;
+    if (ki >= kp_count[f]) return;
+    OriShared& sh = sh_all[warp];
+    DunkKeyPoint* kp = kps_all + (size_t)f * kp_cap + ki;
+    const LevelDev& e = lv.lv[kp->class_id];
+    const float ratio = e.ratio;
+    const int scale = __float2int_rn(__fdiv_rn(__fmul_rn(0.5f, kp->size), ratio));
+    const int x0 = __float2int_rn(__fdiv_rn(kp->x, ratio));
+    const int y0 = __float2int_rn(__fdiv_rn(kp->y, ratio));
+    const float* lx = Lx + (size_t)f * pyr_stride + e.plane_off;
+    const float* ly = Ly + (size_t)f * pyr_stride + e.plane_off;
+    const float ang_step = (float)(2.0 * M_PI / kSlices);
+    for (int s = lane; s < kAng; s += 32) {
+        const int y = min(max(y0 + c_ori.yi[s] * scale, 0), e.h - 1);
+        const int x = min(max(x0 + c_ori.xi[s] * scale, 0), e.w - 1);
+        const float w = c_ori.w[s];
+        const float rx = __fmul_rn(w, lx[(size_t)y * e.w + x]);
+        const float ry = __fmul_rn(w, ly[(size_t)y * e.w + x]);
+        sh.rx[s] = rx;
+        sh.ry[s] = ry;
+        const float ang = __fmul_rn(fast_atan2_deg(ry, rx), (float)(M_PI / 180.0));
+        int b = (int)__fdiv_rn(ang, ang_step);
+        if (b < 0 || b >= kSlices) b = 0;
+        sh.bin[s] = (unsigned char)b;
+    }
+    __syncwarp();
+    if (lane == 0) {   // quantized_counting_sort (unstable: descending index inside a slice)
+        for (int i = 0; i <= kSlices; ++i) sh.cum[i] = 0;
+        for (int i = 0; i < kAng; ++i) sh.cum[sh.bin[i]]++;
+        for (int i = 1; i <= kSlices; ++i) sh.cum[i] += sh.cum[i - 1];
+        for (int i = 0; i < kAng; ++i) sh.sorted[--sh.cum[sh.bin[i]]] = (unsigned char)i;
+    }
+    __syncwarp();
+    float bestN = -1.f, bestX = 0.f, bestY = 0.f;
+    int bestW = 1 << 30;
+    for (int sn = lane; sn < kSlices; sn += 32) {
+        float sx = 0.f, sy = 0.f;
+        if (sn <= kSlices - kWin) {
+            for (int i = sh.cum[sn]; i < sh.cum[sn + kWin]; ++i) {
+                sx = __fadd_rn(sx, sh.rx[sh.sorted[i]]);
+                sy = __fadd_rn(sy, sh.ry[sh.sorted[i]]);
+            }
+        } else {
+            const int remain = sn + kWin - kSlices;
+            for (int i = sh.cum[sn]; i < sh.cum[kSlices]; ++i) {
+                sx = __fadd_rn(sx, sh.rx[sh.sorted[i]]);
+                sy = __fadd_rn(sy, sh.ry[sh.sorted[i]]);
+            }
+            for (int i = sh.cum[0]; i < sh.cum[remain]; ++i) {
+                sx = __fadd_rn(sx, sh.rx[sh.sorted[i]]);
+                sy = __fadd_rn(sy, sh.ry[sh.sorted[i]]);
+            }
+        }
+        const float nrm = __fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy));
+        if (nrm > bestN) { bestN = nrm; bestX = sx; bestY = sy; bestW = sn; }   // lower sn first per lane
+    }
+    // arg-max with first-window-wins ties (the source replaces only on strictly greater)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float n2 = __shfl_xor_sync(0xffffffffu, bestN, o);
+        const float x2 = __shfl_xor_sync(0xffffffffu, bestX, o);
+        const float y2 = __shfl_xor_sync(0xffffffffu, bestY, o);
+        const int w2 = __shfl_xor_sync(0xffffffffu, bestW, o);
+        if (n2 > bestN || (n2 == bestN && w2 < bestW)) { bestN = n2; bestX = x2; bestY = y2; bestW = w2; }
+    }
+    if (lane == 0) kp->angle = fast_atan2_deg(bestY, bestX);   // degrees (cv2 4.13 stores fastAtan2)
+}
+
+__device__ __forceinline__ int toggle_flt(float v) {
+    const int x = __float_as_int(v);
+    return x ^ ((x < 0) ? 0x7fffffff : 0);   // CV_TOGGLE_FLT
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restrict__ kp_count,
+       const float* __restrict__ Lt, const float* __restrict__ Lx, const float* __restrict__ Ly, size_t pyr_stride,
+       LevelsDev lv, uint4* __restrict__ desc64_all) {
+    __shared__ int vals_all[kWarpsPerBlock][29 * 3];
+    const int f = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ki = blockIdx.x * kWarpsPerBlock + warp;
+    if (ki >= kp_count[f]) return;
+    int* vals = vals_all[warp];
+    const DunkKeyPoint kp = kps_all[(size_t)f * kp_cap + ki];
+    const LevelDev& e = lv.lv[kp.class_id];
+    const float ratio = (float)(1 << kp.octave);
+    const int scale = __float2int_rn(__fdiv_rn(__fmul_rn(0.5f, kp.size), ratio));
+    const float fscale = (float)scale;
+    const float xf = __fdiv_rn(kp.x, ratio), yf = __fdiv_rn(kp.y, ratio);
+    const float angle = __fmul_rn(kp.angle, (float)(M_PI / 180.0));
+    const float co = cosf(angle), si = sinf(angle);
+    const float* lt = Lt + (size_t)f * pyr_stride + e.plane_off;
+    const float* lx = Lx + (size_t)f * pyr_stride + e.plane_off;
+    const float* ly = Ly + (size_t)f * pyr_stride + e.plane_off;
+    if (lane < 29) {
+        // cell -> (grid, i, j): pattern 10; steps 10, 7, 5 -> 2x2, 3x3, 4x4 cells starting at -10
+        int step, n, local;
+        if (lane < 4) { step = 10; n = 2; local = lane; }
+        else if (lane < 13) { step = 7; n = 3; local = lane - 4; }
+        else { step = 5; n = 4; local = lane - 13; }
+        const int i0 = -10 + (local / n) * step, j0 = -10 + (local % n) * step;
+        float di = 0.f, dx = 0.f, dy = 0.f;
+        int nsamples = 0;
+        for (int k = i0; k < i0 + step; ++k)
+            for (int l = j0; l < j0 + step; ++l) {
+                const float sy = __fadd_rn(yf, __fadd_rn(__fmul_rn(__fmul_rn((float)l, co), fscale),
+                                                         __fmul_rn(__fmul_rn((float)k, si), fscale)));
+                const float sx = __fadd_rn(xf, __fadd_rn(__fmul_rn(__fmul_rn((float)(-l), si), fscale),
+                                                         __fmul_rn(__fmul_rn((float)k, co), fscale)));
+                const int y1 = __float2int_rn(sy), x1 = __float2int_rn(sx);
+                if (y1 < 0 || y1 >= e.h || x1 < 0 || x1 >= e.w) continue;
+                const size_t o = (size_t)y1 * e.w + x1;
+                const float ri = lt[o], rx = lx[o], ry = ly[o];
+                di = __fadd_rn(di, ri);
+                const float rry = __fadd_rn(__fmul_rn(rx, co), __fmul_rn(ry, si));
+                const float rrx = __fadd_rn(__fmul_rn(-rx, si), __fmul_rn(ry, co));
+                dx = __fadd_rn(dx, rrx);
+                dy = __fadd_rn(dy, rry);
+                ++nsamples;
+            }
+        if (nsamples > 0) {
+            const float inv = __fdiv_rn(1.0f, (float)nsamples);
+            di = __fmul_rn(di, inv); dx = __fmul_rn(dx, inv); dy = __fmul_rn(dy, inv);
+        }
+        vals[lane * 3 + 0] = toggle_flt(di);
+        vals[lane * 3 + 1] = toggle_flt(dx);
+        vals[lane * 3 + 2] = toggle_flt(dy);
+    }
+    __syncwarp();
+    unsigned word[16];
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        const int dpos = w * 32 + lane;
+        bool bit = false;
+        if (dpos < 486) bit = vals[c_cmp_a[dpos]] > vals[c_cmp_b[dpos]];
+        word[w] = __ballot_sync(0xffffffffu, bit);
+    }
+    if (lane < 4) {
+        uint4 v;
+        v.x = word[lane * 4 + 0]; v.y = word[lane * 4 + 1]; v.z = word[lane * 4 + 2]; v.w = word[lane * 4 + 3];
+        // word[] is warp-uniform; select with a switch-free copy
+        desc64_all[((size_t)f * kp_cap + ki) * 4 + lane] = v;
+    }
+}
+
+bool g_tables_ready = false;
+
+int upload_tables() {
+    if (g_tables_ready) return DUNK_OK;
+    OriTable t;
+    int k = 0;
+    for (int i = -6; i <= 6; ++i)
+        for (int j = -6; j <= 6; ++j)
+            if (i * i + j * j < 36) {
+                // gauss25[|i|][|j|]: 2-D Gaussian sigma 2.5, tabulated to 8 decimals in the source
+                const double g = std::exp(-(double)(i * i + j * j) / (2 * 2.5 * 2.5)) / (2 * M_PI * 2.5 * 2.5);
+                t.w[k] = (float)(std::round(g * 1e8) / 1e8);
+                t.xi[k] = (signed char)i;
+                t.yi[k] = (signed char)j;
+                ++k;
+            }
+    if (k != 109) {
+        set_error("orientation table has %d entries", k);
+        return DUNK_ERR_ASSERT;
+    }
+    unsigned char a[486], b[486];
+    int dpos = 0, base = 0;
+    for (int z = 0; z < 3; ++z) {
+        const int count = (z + 2) * (z + 2);
+        for (int pos = 0; pos < 3; ++pos)
+            for (int i = 0; i < count; ++i)
+                for (int j = i + 1; j < count; ++j) {
+                    a[dpos] = (unsigned char)((base + i) * 3 + pos);
+                    b[dpos] = (unsigned char)((base + j) * 3 + pos);
+                    ++dpos;
+                }
+        base += count;
+    }
+    if (dpos != 486) {
+        set_error("MLDB comparison table has %d entries", dpos);
+        return DUNK_ERR_ASSERT;
+    }
+    DUNK_CUDA(cudaMemcpyToSymbol(c_ori, &t, sizeof t));
+    DUNK_CUDA(cudaMemcpyToSymbol(c_cmp_a, a, sizeof a));
+    DUNK_CUDA(cudaMemcpyToSymbol(c_cmp_b, b, sizeof b));
+    g_tables_ready = true;
+    return DUNK_OK;
+}
+
+}  // namespace
+
+int akaze_describe(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeWorkspace& ws, int frames) {
+    int rc = upload_tables();
+    if (rc) return rc;
+    const LevelsDev lv = make_levels_dev(lt);
+    const dim3 grid(div_up(ws.kp_cap, kWarpsPerBlock), frames);
+    k_orientation<<<grid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lx, ws.Ly, lt.pyramid_floats, lv);
+    DUNK_KERNEL_CHECK(ctx);
+    k_mldb<<<grid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lt, ws.Lx, ws.Ly, lt.pyramid_floats, lv,
+                                                 ws.desc64);
+    DUNK_KERNEL_CHECK(ctx);
+    return DUNK_OK;
+}
+
+}  // namespace dunk

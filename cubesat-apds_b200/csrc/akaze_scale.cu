@@ -1,0 +1,594 @@
+// AKAZE stage 1a: nonlinear scale space + determinant-of-Hessian response, batched over frames.
+// Every kernel is a shared-memory tiled stencil over f32 planes (HBM-bound):
+//   gray+Gauss9 | Gauss5+Scharr+|grad| (k-contrast) | 2x area decimation | Gauss5+Scharr+PM-G2 |
+//   FED diffusion, K explicit steps per launch temporally blocked in shared memory |
+//   fused Hessian (Lx, Ly, Lxx, Lxy, Lyy -> Ldet).
+// Follows OpenCV's AKAZEFeatures.cpp / nldiffusion_functions.cpp / fed.cpp as restated in
+// oracle/akaze_oracle.py; the FED step keeps OpenCV's f32 operation order
+// (no FMA contraction) because 166 dependent steps amplify reassociation noise.
+#include "akaze.h"
+#include <cmath>
+
+namespace dunk {
+
+namespace {
+
+constexpr int kBX = 32, kBY = 8;           // thread block 32 x 8
+constexpr int kTW = 64, kTH = 32;          // generic stencil tile
+constexpr int kFedT = 64;                  // FED tile (square)
+constexpr int kFedMaxK = 8;                // FED steps fused per launch
+constexpr int kNBins = 300;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int reflect101(int v, int n) {
+    if (n == 1) return 0;
+    while (v < 0 || v >= n) v = v < 0 ? -v : 2 * (n - 1) - v;
+    return v;
+}
+
+struct Gauss9 { float k[5]; };   // k[0] = centre
+struct Gauss5 { float k[3]; };
+
+__device__ __forceinline__ float load_gray(const unsigned char* __restrict__ img, int row_stride, int channels,
+                                           int x, int y) {
+    const unsigned char* p = img + (size_t)y * row_stride + (size_t)x * channels;
+    int v;
+    if (channels == 1) v = p[0];
+    else v = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15;   // cvtColor BGR(A)2GRAY, 8U
+    return __fmul_rn((float)v, (float)(1.0 / 255.0));                    // convertTo(CV_32F, 1/255)
+}
+
+// ---- level 0: gray -> GaussianBlur 9x9 sigma 1.6 (BORDER_REPLICATE) -> Lt0 (= Lsmooth0) ----------
+__global__ void __launch_bounds__(kBX* kBY)
+k_gray_gauss9(const unsigned char* __restrict__ images, size_t image_stride, int row_stride, int channels,
+              int W, int H, Gauss9 g, float* __restrict__ Lt0, size_t pyr_stride) {
+    __shared__ float A[kTH + 8][kTW + 8];
+    __shared__ float T[kTH + 8][kTW];
+    const int f = blockIdx.z;
+    const unsigned char* img = images + (size_t)f * image_stride;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ly = ty; ly < kTH + 8; ly += kBY)
+        for (int lx = tx; lx < kTW + 8; lx += kBX)
+            A[ly][lx] = load_gray(img, row_stride, channels, clampi(x0 + lx - 4, 0, W - 1),
+                                  clampi(y0 + ly - 4, 0, H - 1));
+    __syncthreads();
+    for (int ly = ty; ly < kTH + 8; ly += kBY)
+        for (int lx = tx; lx < kTW; lx += kBX) {
+            const float* a = &A[ly][lx + 4];
+            T[ly][lx] = g.k[0] * a[0] + g.k[1] * (a[-1] + a[1]) + g.k[2] * (a[-2] + a[2]) +
+                        g.k[3] * (a[-3] + a[3]) + g.k[4] * (a[-4] + a[4]);
+        }
+    __syncthreads();
+    float* out = Lt0 + (size_t)f * pyr_stride;
+    for (int ly = ty; ly < kTH; ly += kBY)
+        for (int lx = tx; lx < kTW; lx += kBX) {
+            const int gx = x0 + lx, gy = y0 + ly;
+            if (gx < W && gy < H) {
+                const int c = ly + 4;
+                out[(size_t)gy * W + gx] = g.k[0] * T[c][lx] + g.k[1] * (T[c - 1][lx] + T[c + 1][lx]) +
+                                           g.k[2] * (T[c - 2][lx] + T[c + 2][lx]) + g.k[3] * (T[c - 3][lx] + T[c + 3][lx]) +
+                                           g.k[4] * (T[c - 4][lx] + T[c + 4][lx]);
+            }
+        }
+}
+
+// Gauss5 (replicate) of a clamped-loaded tile A (tile + halo 3) -> B (tile + halo 1), then the
+// out-of-image ring of B is filled by reflect-101 (what Scharr's BORDER_DEFAULT sees)
+template <int TW, int TH>
+__device__ __forceinline__ void gauss5_tile(float (&A)[TH + 6][TW + 6], float (&T)[TH + 6][TW + 2],
+                                            float (&B)[TH + 2][TW + 2], const Gauss5& g, int x0, int y0, int W, int H) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ly = ty; ly < TH + 6; ly += kBY)
+        for (int lx = tx; lx < TW + 2; lx += kBX) {
+            const float* a = &A[ly][lx + 2];
+            T[ly][lx] = g.k[0] * a[0] + g.k[1] * (a[-1] + a[1]) + g.k[2] * (a[-2] + a[2]);
+        }
+    __syncthreads();
+    for (int ly = ty; ly < TH + 2; ly += kBY)
+        for (int lx = tx; lx < TW + 2; lx += kBX) {
+            const int c = ly + 2;
+            B[ly][lx] = g.k[0] * T[c][lx] + g.k[1] * (T[c - 1][lx] + T[c + 1][lx]) + g.k[2] * (T[c - 2][lx] + T[c + 2][lx]);
+        }
+    __syncthreads();
+    // B(lx,ly) sits at global (x0-1+lx, y0-1+ly); cells outside the image take the reflected value
+    for (int ly = ty; ly < TH + 2; ly += kBY)
+        for (int lx = tx; lx < TW + 2; lx += kBX) {
+            const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+            if (gx < 0 || gx >= W || gy < 0 || gy >= H) {
+                const int rx = reflect101(gx, W), ry = reflect101(gy, H);
+                const int sx = rx - (x0 - 1), sy = ry - (y0 - 1);
+                if (sx >= 0 && sx < TW + 2 && sy >= 0 && sy < TH + 2 && rx >= 0 && ry >= 0) B[ly][lx] = B[sy][sx];
+            }
+        }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void scharr_at(const float* up, const float* mid, const float* dn, float& lx, float& ly) {
+    // cv::Scharr, scale 1: [-1 0 1] x [3 10 3] (un-normalised)
+    lx = 3.f * (up[1] - up[-1]) + 10.f * (mid[1] - mid[-1]) + 3.f * (dn[1] - dn[-1]);
+    ly = 3.f * (dn[-1] - up[-1]) + 10.f * (dn[0] - up[0]) + 3.f * (dn[1] - up[1]);
+}
+
+// ---- k-contrast pass 1: Gauss5(sigma 1) -> Scharr -> |grad| plane + per-frame max ---------------
+__global__ void __launch_bounds__(kBX* kBY)
+k_contrast_modg(const unsigned char* __restrict__ images, size_t image_stride, int row_stride, int channels,
+                int W, int H, Gauss5 g, float* __restrict__ modg, size_t plane_stride, float* __restrict__ hmax) {
+    __shared__ float A[kTH + 6][kTW + 6];
+    __shared__ float T[kTH + 6][kTW + 2];
+    __shared__ float B[kTH + 2][kTW + 2];
+    __shared__ float red[kBX * kBY / 32];
+    const int f = blockIdx.z;
+    const unsigned char* img = images + (size_t)f * image_stride;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ly = ty; ly < kTH + 6; ly += kBY)
+        for (int lx = tx; lx < kTW + 6; lx += kBX)
+            A[ly][lx] = load_gray(img, row_stride, channels, clampi(x0 + lx - 3, 0, W - 1),
+                                  clampi(y0 + ly - 3, 0, H - 1));
+    __syncthreads();
+    gauss5_tile<kTW, kTH>(A, T, B, g, x0, y0, W, H);
+    float m = 0.f;
+    float* out = modg + (size_t)f * plane_stride;
+    for (int ly = ty; ly < kTH; ly += kBY)
+        for (int lx = tx; lx < kTW; lx += kBX) {
+            const int gx = x0 + lx, gy = y0 + ly;
+            if (gx < W && gy < H) {
+                float dx, dy;
+                scharr_at(&B[ly][lx + 1], &B[ly + 1][lx + 1], &B[ly + 2][lx + 1], dx, dy);
+                const float v = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                out[(size_t)gy * W + gx] = v;
+                if (gx >= 1 && gx < W - 1 && gy >= 1 && gy < H - 1) m = fmaxf(m, v);   // interior only
+            }
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int tid = ty * kBX + tx;
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < kBX * kBY / 32; ++i) m = fmaxf(m, red[i]);
+        atomicMax((int*)&hmax[f], __float_as_int(m));   // non-negative floats order like ints
+    }
+}
+
+// ---- k-contrast pass 2: 300-bin histogram of the interior gradient magnitudes ---------------------
+__global__ void __launch_bounds__(256)
+k_contrast_hist(const float* __restrict__ modg, size_t plane_stride, int W, int H, const float* __restrict__ hmax,
+                int* __restrict__ hist) {
+    __shared__ int sh[kNBins];
+    const int f = blockIdx.y;
+    for (int i = threadIdx.x; i < kNBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const float hm = hmax[f];
+    if (hm > 0.f) {
+        const float scale = __fdiv_rn((float)(kNBins - 1), hm);
+        const float* src = modg + (size_t)f * plane_stride;
+        const int iw = W - 2, ih = H - 2;
+        const long long total = (long long)iw * ih;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const int y = (int)(i / iw) + 1, x = (int)(i % iw) + 1;
+            int b = (int)__fmul_rn(src[(size_t)y * W + x], scale);
+            b = min(max(b, 0), kNBins - 1);
+            atomicAdd(&sh[b], 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kNBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[f * kNBins + i], sh[i]);
+}
+
+// compute_kcontrast tail: 70th percentile of the non-background histogram
+__global__ void k_contrast_final(const int* __restrict__ hist, const float* __restrict__ hmax, int W, int H,
+                                 float perc, float* __restrict__ kcontrast, int frames) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= frames) return;
+    const float hm = hmax[f];
+    float k = 0.03f;
+    if (hm > 0.f) {
+        const int total = (W - 2) * (H - 2);
+        const int* h = hist + f * kNBins;
+        const int nthreshold = (int)((float)(total - h[0]) * perc);
+        int nelements = 0;
+        for (int b = 1; b < kNBins; ++b) {
+            if (nelements >= nthreshold) {
+                k = __fdiv_rn(__fmul_rn(hm, (float)b), (float)kNBins);
+                break;
+            }
+            nelements += h[b];
+        }
+    }
+    kcontrast[f] = k;
+}
+
+// ---- octave change: cv::resize(INTER_AREA) by ~2 ------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_halfsample(const float* __restrict__ src, size_t src_stride, int sw, int sh, float* __restrict__ dst,
+             size_t dst_stride, int dw, int dh) {
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    const float* s = src + (size_t)f * src_stride;
+    float v;
+    if (sw == 2 * dw && sh == 2 * dh) {
+        const float* r0 = s + (size_t)(2 * y) * sw + 2 * x;
+        const float* r1 = r0 + sw;
+        v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(r0[0], r0[1]), r1[0]), r1[1]), 0.25f);
+    } else {
+        // general area resize: fractional coverage weights (computeResizeAreaTab)
+        const double scx = (double)sw / dw, scy = (double)sh / dh;
+        const double fx0 = x * scx, fx1 = fx0 + scx, fy0 = y * scy, fy1 = fy0 + scy;
+        const double cellx = fmin(scx, sw - fx0), celly = fmin(scy, sh - fy0);
+        const int sx0 = (int)ceil(fx0), sx1 = min((int)floor(fx1), sw);
+        const int sy0 = (int)ceil(fy0), sy1 = min((int)floor(fy1), sh);
+        float acc = 0.f;
+        for (int yy = sy0 - 1; yy <= sy1; ++yy) {
+            float wy;
+            if (yy == sy0 - 1) wy = (sy0 - fy0 > 1e-3) ? (float)((sy0 - fy0) / celly) : 0.f;
+            else if (yy == sy1) wy = (fy1 - sy1 > 1e-3 && sy1 < sh) ? (float)(fmin(fmin(fy1 - sy1, 1.0), celly) / celly) : 0.f;
+            else wy = (float)(1.0 / celly);
+            if (wy == 0.f || yy < 0 || yy >= sh) continue;
+            float racc = 0.f;
+            for (int xx = sx0 - 1; xx <= sx1; ++xx) {
+                float wx;
+                if (xx == sx0 - 1) wx = (sx0 - fx0 > 1e-3) ? (float)((sx0 - fx0) / cellx) : 0.f;
+                else if (xx == sx1) wx = (fx1 - sx1 > 1e-3 && sx1 < sw) ? (float)(fmin(fmin(fx1 - sx1, 1.0), cellx) / cellx) : 0.f;
+                else wx = (float)(1.0 / cellx);
+                if (wx == 0.f || xx < 0 || xx >= sw) continue;
+                racc += s[(size_t)yy * sw + xx] * wx;
+            }
+            acc += racc * wy;
+        }
+        v = acc;
+    }
+    dst[(size_t)f * dst_stride + (size_t)y * dw + x] = v;
+}
+
+// ---- per level: Lsmooth = Gauss5(Lt_init), Lflow = PM-G2(Scharr(Lsmooth), k) --------------------
+__global__ void __launch_bounds__(kBX* kBY)
+k_prep_level(const float* __restrict__ Lt, size_t lt_stride, int W, int H, Gauss5 g,
+             const float* __restrict__ kcontrast, float kscale, float* __restrict__ Lsmooth,
+             float* __restrict__ Lflow, size_t plane_stride) {
+    __shared__ float A[kTH + 6][kTW + 6];
+    __shared__ float T[kTH + 6][kTW + 2];
+    __shared__ float B[kTH + 2][kTW + 2];
+    const int f = blockIdx.z;
+    const float* src = Lt + (size_t)f * lt_stride;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ly = ty; ly < kTH + 6; ly += kBY)
+        for (int lx = tx; lx < kTW + 6; lx += kBX)
+            A[ly][lx] = src[(size_t)clampi(y0 + ly - 3, 0, H - 1) * W + clampi(x0 + lx - 3, 0, W - 1)];
+    __syncthreads();
+    gauss5_tile<kTW, kTH>(A, T, B, g, x0, y0, W, H);
+    const float k = __fmul_rn(kcontrast[f], kscale);
+    const float inv_k = __fdiv_rn(1.f, __fmul_rn(k, k));
+    float* sm = Lsmooth + (size_t)f * plane_stride;
+    float* fl = Lflow + (size_t)f * plane_stride;
+    for (int ly = ty; ly < kTH; ly += kBY)
+        for (int lx = tx; lx < kTW; lx += kBX) {
+            const int gx = x0 + lx, gy = y0 + ly;
+            if (gx < W && gy < H) {
+                float dx, dy;
+                scharr_at(&B[ly][lx + 1], &B[ly + 1][lx + 1], &B[ly + 2][lx + 1], dx, dy);
+                sm[(size_t)gy * W + gx] = B[ly + 1][lx + 1];
+                // pm_g2: 1 / (1 + (Lx^2 + Ly^2) / k^2)
+                fl[(size_t)gy * W + gx] =
+                    __fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(inv_k, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)))));
+            }
+        }
+}
+
+// ---- FED: K explicit diffusion steps per launch, temporally blocked in shared memory ------------
+struct FedSteps {
+    int k;
+    float step[kFedMaxK];   // tau * 0.5
+};
+
+__global__ void __launch_bounds__(kBX* kBY)
+k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout, size_t out_stride,
+      const float* __restrict__ Lflow, size_t flow_stride, int W, int H, FedSteps fs) {
+    extern __shared__ float smem[];
+    const int K = fs.k;
+    const int S = kFedT + 2 * K;          // smem tile edge
+    float* A = smem;
+    float* B = smem + S * S;
+    float* C = smem + 2 * S * S;
+    const int f = blockIdx.z;
+    const float* lin = Lin + (size_t)f * in_stride;
+    const float* lfl = Lflow + (size_t)f * flow_stride;
+    const int x0 = blockIdx.x * kFedT - K, y0 = blockIdx.y * kFedT - K;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ly = ty; ly < S; ly += kBY)
+        for (int lx = tx; lx < S; lx += kBX) {
+            const int gx = x0 + lx, gy = y0 + ly;
+            float a = 0.f, c = 0.f;
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
+                a = lin[(size_t)gy * W + gx];
+                c = lfl[(size_t)gy * W + gx];
+            }
+            A[ly * S + lx] = a;
+            C[ly * S + lx] = c;
+        }
+    __syncthreads();
+    for (int s = 0; s < K; ++s) {
+        const float step = fs.step[s];
+        const int lo = s + 1, hi = S - 2 - s;   // cells whose 4 neighbours are still valid
+        for (int ly = lo + ty; ly <= hi; ly += kBY)
+            for (int lx = lo + tx; lx <= hi; lx += kBX) {
+                const int gx = x0 + lx, gy = y0 + ly;
+                if (gx < 0 || gx >= W || gy < 0 || gy >= H) continue;
+                const int i = ly * S + lx;
+                const float L = A[i], c = C[i];
+                // nld_step_scalar: ((xpos + xneg) + ypos) + yneg, border terms dropped, f32, no FMA
+                const float xpos = gx + 1 < W ? __fmul_rn(__fadd_rn(c, C[i + 1]), __fsub_rn(A[i + 1], L)) : 0.f;
+                const float xneg = gx > 0 ? __fmul_rn(__fadd_rn(c, C[i - 1]), __fsub_rn(A[i - 1], L)) : 0.f;
+                const float ypos = gy + 1 < H ? __fmul_rn(__fadd_rn(c, C[i + S]), __fsub_rn(A[i + S], L)) : 0.f;
+                const float yneg = gy > 0 ? __fmul_rn(__fadd_rn(c, C[i - S]), __fsub_rn(A[i - S], L)) : 0.f;
+                float r = __fadd_rn(__fadd_rn(__fadd_rn(xpos, xneg), ypos), yneg);
+                r = __fmul_rn(r, step);
+                if ((gy == 0 || gy == H - 1) && (gx == 0 || gx == W - 1)) r = 0.f;   // corners are written 0
+                B[i] = __fadd_rn(L, r);
+            }
+        __syncthreads();
+        float* t = A; A = B; B = t;
+    }
+    float* lout = Lout + (size_t)f * out_stride;
+    for (int ly = ty; ly < kFedT; ly += kBY)
+        for (int lx = tx; lx < kFedT; lx += kBX) {
+            const int gx = x0 + K + lx, gy = y0 + K + ly;
+            if (gx < W && gy < H) lout[(size_t)gy * W + gx] = A[(ly + K) * S + (lx + K)];
+        }
+}
+
+// ---- fused Hessian: Lsmooth -> Lx, Ly (kept for orientation/descriptor) and Ldet ------------------
+// kernels of compute_derivative_kernels(scale s): taps at -s, 0, +s: smoothing [w0, w1, w0],
+// derivative [-1, 0, 1]; sepFilter2D = row pass (kx) then column pass (ky), BORDER_REFLECT_101.
+__global__ void __launch_bounds__(kBX* kBY)
+k_hessian(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, int s, float w0, float w1,
+          float sigma_quat, float* __restrict__ Lx, float* __restrict__ Ly, float* __restrict__ Ldet,
+          size_t pyr_stride) {
+    extern __shared__ float smem[];
+    const int SW = kTW + 4 * s, SH = kTH + 4 * s;      // Lsmooth region (halo 2s)
+    const int DW = kTW + 2 * s, DH = kTH + 2 * s;      // first-derivative region (halo s)
+    float* S0 = smem;                 // SH x SW
+    float* DX = S0 + SW * SH;         // DH x DW
+    float* DY = DX + DW * DH;         // DH x DW
+    const int f = blockIdx.z;
+    const float* src = Lsm + (size_t)f * sm_stride;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int ly = ty; ly < SH; ly += kBY)
+        for (int lx = tx; lx < SW; lx += kBX)
+            S0[ly * SW + lx] = src[(size_t)reflect101(y0 - 2 * s + ly, H) * W + reflect101(x0 - 2 * s + lx, W)];
+    __syncthreads();
+    for (int ly = ty; ly < DH; ly += kBY)
+        for (int lx = tx; lx < DW; lx += kBX) {
+            const float* c = &S0[(ly + s) * SW + (lx + s)];
+            const float* u = c - s * SW;
+            const float* d = c + s * SW;
+            // Lx: rows [-1 0 1], columns [w0 w1 w0]
+            DX[ly * DW + lx] = w0 * (u[s] - u[-s]) + w1 * (c[s] - c[-s]) + w0 * (d[s] - d[-s]);
+            // Ly: rows [w0 w1 w0], columns [-1 0 1]
+            DY[ly * DW + lx] = (w0 * d[-s] + w1 * d[0] + w0 * d[s]) - (w0 * u[-s] + w1 * u[0] + w0 * u[s]);
+        }
+    __syncthreads();
+    float* ox = Lx + (size_t)f * pyr_stride;
+    float* oy = Ly + (size_t)f * pyr_stride;
+    float* od = Ldet + (size_t)f * pyr_stride;
+    for (int ly = ty; ly < kTH; ly += kBY)
+        for (int lx = tx; lx < kTW; lx += kBX) {
+            const int gx = x0 + lx, gy = y0 + ly;
+            if (gx >= W || gy >= H) continue;
+            const float* cx = &DX[(ly + s) * DW + (lx + s)];
+            const float* cy = &DY[(ly + s) * DW + (lx + s)];
+            const float* ux = cx - s * DW;
+            const float* dx = cx + s * DW;
+            const float* uy = cy - s * DW;
+            const float* dy = cy + s * DW;
+            const float lxx = w0 * (ux[s] - ux[-s]) + w1 * (cx[s] - cx[-s]) + w0 * (dx[s] - dx[-s]);
+            const float lxy = (w0 * dx[-s] + w1 * dx[0] + w0 * dx[s]) - (w0 * ux[-s] + w1 * ux[0] + w0 * ux[s]);
+            const float lyy = (w0 * dy[-s] + w1 * dy[0] + w0 * dy[s]) - (w0 * uy[-s] + w1 * uy[0] + w0 * uy[s]);
+            const size_t o = (size_t)gy * W + gx;
+            ox[o] = cx[0];
+            oy[o] = cy[0];
+            od[o] = __fmul_rn(__fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy)), sigma_quat);
+        }
+}
+
+bool is_prime(int n) {
+    if (n < 2) return false;
+    for (int d = 2; d * d <= n; ++d)
+        if (n % d == 0) return false;
+    return true;
+}
+
+// kaze/fed.cpp fed_tau_by_process_time(T, 1, 0.25, reordering = true)
+int fed_tau(float T, float* tau) {
+    const float tau_max = 0.25f;
+    const int n = (int)ceilf(sqrtf(3.0f * T / tau_max + 0.25f) - 0.5f - 1.0e-8f);
+    if (n <= 0) return 0;
+    const float scale = 3.0f * T / (tau_max * (float)(n * (n + 1)));
+    const float c = 1.0f / (4.0f * (float)n + 2.0f);
+    const float d = scale * tau_max / 2.0f;
+    float tauh[kMaxFedSteps];
+    for (int k = 0; k < n; ++k) {
+        const float h = cosf((float)M_PI * (2.0f * (float)k + 1.0f) * c);
+        tauh[k] = d / (h * h);
+    }
+    const int kappa = n / 2;
+    int prime = n + 1;
+    while (!is_prime(prime)) prime++;
+    for (int k = 0, l = 0; l < n; ++k, ++l) {
+        int index;
+        while ((index = ((k + 1) * kappa) % prime - 1) >= n) k++;
+        tau[l] = tauh[index];
+    }
+    return n;
+}
+
+void gaussian_kernel(int ksize, double sigma, float* out /*centre first*/) {
+    double k[16], sum = 0;
+    for (int i = 0; i < ksize; ++i) {
+        const double x = i - (ksize - 1) * 0.5;
+        k[i] = std::exp(-0.5 / (sigma * sigma) * x * x);
+        sum += k[i];
+    }
+    for (int i = 0; i <= ksize / 2; ++i) out[i] = (float)(k[ksize / 2 + i] / sum);
+}
+
+}  // namespace
+
+LevelTable make_level_table(int width, int height) {
+    LevelTable t{};
+    t.width = width;
+    t.height = height;
+    int n = 0;
+    size_t off = 0;
+    for (int o = 0; o < 4; ++o) {
+        const int power = 1 << o;
+        const float rf = 1.0f / power;
+        const int lw = (int)(width * rf), lh = (int)(height * rf);
+        if ((lw < 80 || lh < 40) && o != 0) break;
+        for (int j = 0; j < 4; ++j) {
+            LevelInfo& e = t.lv[n];
+            e.w = lw; e.h = lh; e.octave = o; e.sublevel = j;
+            e.esigma = 1.6f * powf(2.f, (float)j / 4.f + o);
+            e.sigma_size = (int)lrint((double)(e.esigma * 1.5f / power));
+            e.ratio = (float)power;
+            e.border = (int)lrint((double)(10.0f * sqrtf(2.0f) * e.sigma_size)) + 1;
+            e.plane_off = off;
+            off += (size_t)lw * lh;
+            e.n_tau = 0;
+            ++n;
+        }
+    }
+    t.n_levels = n;
+    t.pyramid_floats = off;
+    for (int i = 1; i < n; ++i) {
+        const float et = 0.5f * (t.lv[i].esigma * t.lv[i].esigma), ep = 0.5f * (t.lv[i - 1].esigma * t.lv[i - 1].esigma);
+        t.lv[i].n_tau = fed_tau(et - ep, t.lv[i].tau);
+    }
+    return t;
+}
+
+LevelsDev make_levels_dev(const LevelTable& lt) {
+    LevelsDev d{};
+    d.n = lt.n_levels;
+    for (int i = 0; i < lt.n_levels; ++i) {
+        d.lv[i].w = lt.lv[i].w; d.lv[i].h = lt.lv[i].h;
+        d.lv[i].sigma_size = lt.lv[i].sigma_size; d.lv[i].border = lt.lv[i].border;
+        d.lv[i].octave = lt.lv[i].octave; d.lv[i].ratio = lt.lv[i].ratio; d.lv[i].esigma = lt.lv[i].esigma;
+        d.lv[i].plane_off = lt.lv[i].plane_off;
+    }
+    return d;
+}
+
+int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeWorkspace& ws,
+                            const unsigned char* images, size_t image_stride_bytes, int row_stride, int channels,
+                            int frames) {
+    const int W = lt.width, H = lt.height;
+    const size_t pyr = lt.pyramid_floats, plane = (size_t)W * H;
+    const dim3 blk(kBX, kBY);
+    Gauss9 g9;
+    Gauss5 g5;
+    gaussian_kernel(9, 1.6, g9.k);
+    gaussian_kernel(5, 1.0, g5.k);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             3 * (kFedT + 2 * kFedMaxK) * (kFedT + 2 * kFedMaxK) * 4);
+        cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+    }
+    // level 0
+    {
+        const dim3 grid(div_up(W, kTW), div_up(H, kTH), frames);
+        k_gray_gauss9<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g9,
+                                            ws.Lt + lt.lv[0].plane_off, pyr);
+        DUNK_KERNEL_CHECK(ctx);
+        if (lt.n_levels > 1) {
+            DUNK_CUDA(cudaMemsetAsync(ws.hmax, 0, (size_t)frames * 4, st));
+            DUNK_CUDA(cudaMemsetAsync(ws.hist, 0, (size_t)frames * kNBins * 4, st));
+            k_contrast_modg<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g5,
+                                                  ws.Lflow, plane, ws.hmax);
+            DUNK_KERNEL_CHECK(ctx);
+            const int hb = std::max(1, std::min(64, div_up((long long)(W - 2) * (H - 2), 256 * 16)));
+            k_contrast_hist<<<dim3(hb, frames), 256, 0, st>>>(ws.Lflow, plane, W, H, ws.hmax, ws.hist);
+            DUNK_KERNEL_CHECK(ctx);
+            k_contrast_final<<<div_up(frames, 64), 64, 0, st>>>(ws.hist, ws.hmax, W, H, 0.7f, ws.kcontrast, frames);
+            DUNK_KERNEL_CHECK(ctx);
+        }
+    }
+    auto hessian = [&](int i, const float* lsm, size_t lsm_stride) -> int {
+        const LevelInfo& e = lt.lv[i];
+        const int s = e.sigma_size;
+        float w0, w1;
+        if (s == 1) {
+            w0 = 3.f / 32.f; w1 = 10.f / 32.f;
+        } else {
+            const float w = 10.0f / 3.0f;
+            w0 = 1.0f / (2.0f * s * (w + 2.0f));
+            w1 = w * w0;
+        }
+        const size_t smem = ((size_t)(kTW + 4 * s) * (kTH + 4 * s) + 2 * (size_t)(kTW + 2 * s) * (kTH + 2 * s)) * 4;
+        const dim3 grid(div_up(e.w, kTW), div_up(e.h, kTH), frames);
+        k_hessian<<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, s, w0, w1, (float)(s * s * s * s),
+                                           ws.Lx + e.plane_off, ws.Ly + e.plane_off, ws.Ldet + e.plane_off, pyr);
+        DUNK_KERNEL_CHECK(ctx);
+        return DUNK_OK;
+    };
+    int rc = hessian(0, ws.Lt + lt.lv[0].plane_off, pyr);
+    if (rc) return rc;
+
+    float kscale = 1.0f;
+    for (int i = 1; i < lt.n_levels; ++i) {
+        const LevelInfo& e = lt.lv[i];
+        const LevelInfo& p = lt.lv[i - 1];
+        const int n = e.n_tau;
+        const int m = div_up(n, kFedMaxK);
+        float* P = ws.Lt + e.plane_off;   // final home of this level's Lt (stride pyr)
+        float* Q = ws.Ltmp;               // ping-pong partner (stride plane)
+        const float* init;
+        size_t init_stride;
+        if (e.octave > p.octave) {
+            kscale *= 0.75f;
+            // first FED launch writes to ((m-1) even ? P : Q); decimate into the other one
+            const bool out0_is_P = ((m - 1) % 2 == 0);
+            float* dstbuf = out0_is_P ? Q : P;
+            const size_t dstride = out0_is_P ? plane : pyr;
+            k_halfsample<<<dim3(div_up(e.w, 256), e.h, frames), 256, 0, st>>>(ws.Lt + p.plane_off, pyr, p.w, p.h, dstbuf,
+                                                                           dstride, e.w, e.h);
+            DUNK_KERNEL_CHECK(ctx);
+            init = dstbuf;
+            init_stride = dstride;
+        } else {
+            init = ws.Lt + p.plane_off;
+            init_stride = pyr;
+        }
+        const dim3 grid(div_up(e.w, kTW), div_up(e.h, kTH), frames);
+        k_prep_level<<<grid, blk, 0, st>>>(init, init_stride, e.w, e.h, g5, ws.kcontrast, kscale, ws.Lsmooth, ws.Lflow, plane);
+        DUNK_KERNEL_CHECK(ctx);
+        if ((rc = hessian(i, ws.Lsmooth, plane))) return rc;
+        const float* in = init;
+        size_t in_stride = init_stride;
+        for (int j = 0; j < m; ++j) {
+            FedSteps fs{};
+            fs.k = std::min(kFedMaxK, n - j * kFedMaxK);
+            for (int k = 0; k < fs.k; ++k) fs.step[k] = e.tau[j * kFedMaxK + k] * 0.5f;
+            const bool out_is_P = ((m - 1 - j) % 2 == 0);
+            float* out = out_is_P ? P : Q;
+            const size_t out_stride = out_is_P ? pyr : plane;
+            const int S = kFedT + 2 * fs.k;
+            const dim3 fgrid(div_up(e.w, kFedT), div_up(e.h, kFedT), frames);
+            k_fed<<<fgrid, blk, (size_t)3 * S * S * 4, st>>>(in, in_stride, out, out_stride, ws.Lflow, plane, e.w, e.h, fs);
+            DUNK_KERNEL_CHECK(ctx);
+            in = out;
+            in_stride = out_stride;
+        }
+    }
+    return DUNK_OK;
+}
+
+}  // namespace dunk

@@ -149,6 +149,28 @@ int dunk_top2_ratio_dev(dunk_ctx* ctx, int slot, const void* merged_dev, int nq,
 int dunk_pad_desc_dev(dunk_ctx* ctx, int slot, const void* src_dev, int64_t n, int desc_bytes,
                       void* dst64_dev);
 
+/* ---- stage 1: AKAZE keypoints + MLDB-486 descriptors -------------------------------------
+ * replaces AKAZE::create(DESCRIPTOR_MLDB, 0, 3, 0.001, 4, 4, DIFF_PM_G2, max_points)
+ * .detectAndCompute(img, no mask) — akaze_keypoint_descriptor_extraction_def,
+ * feature_extraction/src/lib.rs:61-92.  image: rows x cols, 1 (gray) / 3 (BGR) / 4 (BGRA)
+ * interleaved u8 channels.  Outputs: kps (cv::KeyPoint layout, OpenCV's order: evolution level
+ * ascending, row-major inside a level) and desc (n x 61 u8); *n_out keypoints written.
+ * max_points <= 0: unlimited; otherwise the max_points strongest responses are kept.
+ * Errors: empty / unsupported image -> DUNK_ERR_ASSERT (-215); capacity exceeded -> DUNK_ERR_NO_MEM. */
+int dunk_akaze_extract(dunk_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
+                       int row_stride_bytes, int max_points, DunkKeyPoint* kps, uint8_t* desc,
+                       int cap, int* n_out);
+/* frame batch (same shape): frame f at images + f*frame_stride_bytes (0 = tightly packed);
+ * outputs strided by cap_per_frame; counts: n_frames int32 */
+int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames, int rows, int cols,
+                             int channels, int row_stride_bytes, size_t frame_stride_bytes,
+                             int max_points, DunkKeyPoint* kps, uint8_t* desc, int cap_per_frame,
+                             int* counts);
+/* per-stage parity hook: f32 planes (level_w x level_h) of one evolution level + k-contrast */
+int dunk_akaze_debug_level(dunk_ctx* ctx, const uint8_t* image, int rows, int cols, int channels,
+                           int row_stride_bytes, int level, float* Lt, float* Lx, float* Ly,
+                           float* Ldet, float* kcontrast, int* level_w, int* level_h, int* n_levels);
+
 /* ---- stage 3: RANSAC homography ---------------------------------------------------------
  * replaces cv::findHomography(src, dst, mask, method, thr) as called by find_homography_mat,
  * homographier/src/homographier/mod.rs:231-259 (5-arg overload: maxIters 2000, conf 0.995).
