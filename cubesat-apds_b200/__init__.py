@@ -7,9 +7,10 @@ Sub-modules mirror the reference crates on the path:
 Everything numeric happens in libdunk_b200.so (csrc/, C ABI in include/dunk_b200.h).
 """
 from . import _lib
-from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, TOP2_DTYPE, Context, DunkError, default_context)
+from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, REGISTRATION_DTYPE, TOP2_DTYPE, Context, DunkError, default_context)
 from . import feature_extraction
 from . import _extract
+from . import synth
 from . import feature_database
 from . import homographier
 

@@ -35,8 +35,12 @@ KEYPOINT_DTYPE = np.dtype(
 DMATCH_DTYPE = np.dtype(
     [("query_idx", "<i4"), ("train_idx", "<i4"), ("img_idx", "<i4"), ("distance", "<f4")]
 )
+REGISTRATION_DTYPE = np.dtype(
+    [("H", "<f8", (9,)), ("found", "<i4"), ("inliers", "<i4"), ("matches", "<i4"), ("keypoints", "<i4"),
+     ("ransac_iters", "<i4"), ("hypotheses", "<i4")]
+)
 TOP2_DTYPE = np.dtype([("d1", "<u4"), ("i1", "<u4"), ("d2", "<u4"), ("i2", "<u4")])
-assert KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16
+assert REGISTRATION_DTYPE.itemsize == 96 and KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16
 
 
 class DunkError(RuntimeError):
@@ -89,6 +93,10 @@ SIGNATURES = {
     "dunk_akaze_extract": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _pi]),
     "dunk_akaze_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _i, _vp, _vp, _i, _vp]),
     "dunk_akaze_debug_level": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _pi, _pi, _pi]),
+    "dunk_register_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _f, _d, _i, _vp]),
+    "dunk_register_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
+    "dunk_register_frames_dev": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, C.c_size_t, _f, _d, _i, _vp, C.c_size_t, _vp]),
+    "dunk_db_append_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _vp, _vp, _vp, _vp, _i, _vp]),
     "dunk_find_homography": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _pi]),
     "dunk_find_homography_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "dunk_ransac_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _vp, _vp]),

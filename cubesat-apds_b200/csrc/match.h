@@ -2,6 +2,19 @@
 #pragma once
 #include "ctx.h"
 
+// One HBM-resident shard of the reference descriptor database: SoA columns of the reference's
+// `keypoint` table (feature_database/src/models.rs:30-41, schema.rs:27-40)
+struct dunk_db {
+    dunk_ctx* ctx = nullptr;
+    int desc_bytes = 61;
+    int64_t capacity = 0;
+    int64_t size = 0;
+    uint4* desc64 = nullptr;        // capacity x 64 B descriptor rows
+    DunkKeyPoint* kps = nullptr;    // capacity x 28 B (x, y, size, angle, response, octave, class_id)
+    int32_t* image_id = nullptr;    // capacity
+    std::mutex mu;
+};
+
 namespace dunk {
 
 struct KnnPlan {

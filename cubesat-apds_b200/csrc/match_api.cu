@@ -2,18 +2,6 @@
 #include <algorithm>
 #include "match.h"
 
-struct dunk_db {
-    dunk_ctx* ctx = nullptr;
-    int desc_bytes = 61;
-    int64_t capacity = 0;
-    int64_t size = 0;
-    // SoA in HBM (feature_database/src/models.rs:30-41, one array per column)
-    uint4* desc64 = nullptr;        // capacity x 64 B
-    DunkKeyPoint* kps = nullptr;    // capacity x 28 B (x,y,size,angle,response,octave,class_id)
-    int32_t* image_id = nullptr;    // capacity
-    std::mutex mu;
-};
-
 using namespace dunk;
 
 namespace {

@@ -1,0 +1,385 @@
+// End-to-end registration of a frame batch against the HBM-resident reference database:
+// extract (stage 1) -> 2-NN + ratio (stage 2) -> RANSAC homography (stage 3), everything on the
+// device, one stream, no host round trips between the stages.  This is the composition the
+// reference only performs in a test (feature_extraction/src/lib.rs:196-249 extract -> knn ->
+// points) followed by find_homography_mat (homographier/src/homographier/mod.rs:231-259).
+#include <algorithm>
+#include "akaze.h"
+#include "match.h"
+#include "pipeline.h"
+
+namespace dunk {
+
+// from akaze_api.cu
+int akaze_run(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeWorkspace& ws,
+              const unsigned char* images_dev, size_t image_stride, int row_stride, int channels, int frames,
+              int max_points);
+
+namespace {
+
+// exclusive scan of per-frame keypoint counts -> query offsets (frames <= 1024), one CTA
+__global__ void __launch_bounds__(1024) k_frame_offsets(const int* __restrict__ counts, int frames, int* __restrict__ offsets) {
+    __shared__ int sh[1024];
+    const int t = threadIdx.x;
+    sh[t] = t < frames ? counts[t] : 0;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? sh[t - o] : 0;
+        __syncthreads();
+        sh[t] += v;
+        __syncthreads();
+    }
+    if (t < frames) offsets[t + 1] = sh[t];
+    if (t == 0) offsets[0] = 0;
+}
+
+// gather every frame's descriptor rows into one contiguous query array
+__global__ void __launch_bounds__(256)
+k_pack_queries(const uint4* __restrict__ desc64, int kp_cap, const int* __restrict__ counts, const int* __restrict__ offsets,
+               uint4* __restrict__ q64) {
+    const int f = blockIdx.y;
+    const int n = counts[f];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // uint4 index inside the frame
+    if (i >= n * 4) return;
+    q64[(size_t)offsets[f] * 4 + i] = desc64[(size_t)f * kp_cap * 4 + i];
+}
+
+// per frame: Lowe ratio test + ordered compaction of (query point, reference point) pairs
+// (get_knn_matches lib.rs:107-111 + get_points_from_matches lib.rs:161-180, intended semantics)
+__global__ void __launch_bounds__(1024)
+k_frame_pairs(const uint4* __restrict__ top2, const int* __restrict__ counts, const int* __restrict__ offsets, float ratio,
+              const DunkKeyPoint* __restrict__ kps, int kp_cap, const DunkKeyPoint* __restrict__ db_kps, uint32_t index_base,
+              float2* __restrict__ src, float2* __restrict__ dst, DunkDMatch* __restrict__ matches, int* __restrict__ n_pairs) {
+    __shared__ int wsum[32];
+    __shared__ int running, chunk_total;
+    const int f = blockIdx.x;
+    const int n = counts[f], off = offsets[f];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int qi = base + tid;
+        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (qi < n) v = top2[off + qi];
+        const bool keep = qi < n && v.z != ~0u && ((float)v.x < __fmul_rn((float)v.z, ratio));
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const int x = wsum[lane];
+            int incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            wsum[lane] = incl - x;
+            if (lane == 31) chunk_total = incl;
+        }
+        __syncthreads();
+        if (keep) {
+            const int pos = off + running + wsum[warp] + __popc(bal & ((1u << lane) - 1u));
+            const DunkKeyPoint q = kps[(size_t)f * kp_cap + qi];
+            const DunkKeyPoint r = db_kps[v.y - index_base];
+            src[pos] = make_float2(q.x, q.y);
+            dst[pos] = make_float2(r.x, r.y);
+            matches[pos] = DunkDMatch{qi, (int)v.y, 0, (float)v.x};
+        }
+        __syncthreads();
+        if (tid == 0) running += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) n_pairs[f] = running;
+}
+
+struct RegResult {   // DunkRegistration in the header
+    double H[9];
+    int found, inliers, matches, keypoints, ransac_iters, hypotheses;
+};
+
+__global__ void k_pack_results(const double* __restrict__ H, const int* __restrict__ info, const int* __restrict__ n_pairs,
+                               const int* __restrict__ counts, int frames, DunkRegistration* __restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= frames) return;
+    DunkRegistration r;
+    for (int i = 0; i < 9; ++i) r.H[i] = H[f * 9 + i];
+    r.found = info[f * 4 + 0];
+    r.inliers = info[f * 4 + 1];
+    r.ransac_iters = info[f * 4 + 2];
+    r.hypotheses = info[f * 4 + 3];
+    r.matches = n_pairs[f];
+    r.keypoints = counts[f];
+    out[f] = r;
+}
+
+size_t al(size_t b) { return (b + 255) & ~size_t(255); }
+
+struct PipelineBuffers {
+    AkazeWorkspace ws;
+    int* q_off;          // [frames + 1]
+    uint4* q64;          // [frames * kp_cap] rows
+    uint4* top2;         // [frames * kp_cap]
+    uint4* partial;      // knn slab partials
+    float2 *src, *dst;   // [frames * kp_cap]
+    DunkDMatch* matches; // [frames * kp_cap]
+    int* n_pairs;        // [frames]
+    double* H;           // [frames * 9]
+    uint8_t* mask;       // [frames * kp_cap]
+    int* info;           // [frames * 4]
+    DunkRegistration* results;  // [frames]
+};
+
+}  // namespace
+
+struct PipelinePlan {
+    LevelTable lt;
+    int frames, cand_cap, kp_cap;
+    size_t ws_bytes, total_bytes, partial_bytes;
+};
+
+static PipelinePlan plan_pipeline(dunk_ctx* ctx, int rows, int cols, int frames, int64_t db_rows) {
+    PipelinePlan p;
+    p.lt = make_level_table(cols, rows);
+    p.frames = frames;
+    long long c = (long long)cols * rows / 32;
+    c = std::max<long long>(c, 2048);
+    c = std::min<long long>(c, 1 << 20);
+    p.cand_cap = p.kp_cap = (int)c;
+    p.ws_bytes = akaze_workspace_bytes(p.lt, frames, p.cand_cap, p.kp_cap);
+    const size_t nq_max = (size_t)frames * p.kp_cap;
+    // worst-case slab count for the matcher: plan with the largest query count
+    const KnnPlan kp = plan_knn2(ctx, (int)std::min<size_t>(nq_max, 1u << 30), (uint32_t)std::max<int64_t>(db_rows, 1));
+    p.partial_bytes = (size_t)kp.gx * nq_max * 16;
+    p.total_bytes = al(p.ws_bytes) + al((frames + 1) * 4) + al(nq_max * 64) + al(nq_max * 16) + al(p.partial_bytes) +
+                    2 * al(nq_max * 8) + al(nq_max * 16) + al(frames * 4) + al((size_t)frames * 72) + al(nq_max) +
+                    al((size_t)frames * 16) + al((size_t)frames * sizeof(DunkRegistration));
+    return p;
+}
+
+static void carve_pipeline(void* base, const PipelinePlan& p, PipelineBuffers* b) {
+    char* ptr = (char*)base;
+    auto take = [&](size_t bytes) { void* r = ptr; ptr += al(bytes); return r; };
+    akaze_carve_workspace(take(p.ws_bytes), p.lt, p.frames, p.cand_cap, p.kp_cap, &b->ws);
+    const size_t nq_max = (size_t)p.frames * p.kp_cap;
+    b->q_off = (int*)take((p.frames + 1) * 4);
+    b->q64 = (uint4*)take(nq_max * 64);
+    b->top2 = (uint4*)take(nq_max * 16);
+    b->partial = (uint4*)take(p.partial_bytes);
+    b->src = (float2*)take(nq_max * 8);
+    b->dst = (float2*)take(nq_max * 8);
+    b->matches = (DunkDMatch*)take(nq_max * 16);
+    b->n_pairs = (int*)take(p.frames * 4);
+    b->H = (double*)take((size_t)p.frames * 72);
+    b->mask = (uint8_t*)take(nq_max);
+    b->info = (int*)take((size_t)p.frames * 16);
+    b->results = (DunkRegistration*)take((size_t)p.frames * sizeof(DunkRegistration));
+}
+
+// all three stages for `frames` device-resident images; results (device) in b.results
+static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const PipelinePlan& p, const PipelineBuffers& b,
+                        const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
+                        float ratio, float thr, int max_points, int* h_total_q /*pinned or NULL*/) {
+    int rc = akaze_run(ctx, st, p.lt, b.ws, images_dev, frame_stride, row_stride, channels, frames, max_points);
+    if (rc) return rc;
+    k_frame_offsets<<<1, 1024, 0, st>>>(b.ws.kp_count, frames, b.q_off);
+    DUNK_KERNEL_CHECK(ctx);
+    k_pack_queries<<<dim3(div_up((long long)p.kp_cap * 4, 256), frames), 256, 0, st>>>(b.ws.desc64, p.kp_cap, b.ws.kp_count,
+                                                                                      b.q_off, b.q64);
+    DUNK_KERNEL_CHECK(ctx);
+    // the matcher grid depends on the total query count: one 4-byte read back (the only host sync)
+    int total_q = 0;
+    DUNK_CUDA(cudaMemcpyAsync(h_total_q ? h_total_q : &total_q, b.q_off + frames, 4, cudaMemcpyDeviceToHost, st));
+    DUNK_CUDA(cudaStreamSynchronize(st));
+    if (h_total_q) total_q = *h_total_q;
+    if (total_q > 0 && db->size >= 2) {
+        const KnnPlan kp = plan_knn2(ctx, total_q, (uint32_t)db->size);
+        if ((size_t)kp.gx * total_q * 16 > p.partial_bytes) {
+            set_error("pipeline: matcher partial buffer too small");
+            return DUNK_ERR_NO_MEM;
+        }
+        if ((rc = launch_knn2(ctx, st, db->desc64, (uint32_t)db->size, b.q64, total_q, 0, b.partial, b.top2, kp))) return rc;
+    } else if (total_q > 0) {
+        DUNK_CUDA(cudaMemsetAsync(b.top2, 0xFF, (size_t)total_q * 16, st));
+    }
+    k_frame_pairs<<<frames, 1024, 0, st>>>(b.top2, b.ws.kp_count, b.q_off, ratio, b.ws.kps, p.kp_cap, db->kps, 0, b.src, b.dst,
+                                           b.matches, b.n_pairs);
+    DUNK_KERNEL_CHECK(ctx);
+    if ((rc = launch_find_homography(ctx, st, b.src, b.dst, b.q_off, b.n_pairs, frames, thr, b.H, b.mask, b.info))) return rc;
+    k_pack_results<<<div_up(frames, 128), 128, 0, st>>>(b.H, b.info, b.n_pairs, b.ws.kp_count, frames, b.results);
+    DUNK_KERNEL_CHECK(ctx);
+    return DUNK_OK;
+}
+
+}  // namespace dunk
+
+using namespace dunk;
+
+extern "C" {
+
+static int check_frames(const char* fn, int n_frames, int rows, int cols, int channels, int row_stride) {
+    DUNK_REQUIRE(n_frames >= 0 && n_frames <= 1024, DUNK_ERR_BAD_ARG, "%s: n_frames=%d (0..1024 per call)", fn, n_frames);
+    DUNK_REQUIRE(rows >= 16 && cols >= 16, DUNK_ERR_ASSERT, "%s: image %dx%d too small", fn, cols, rows);
+    DUNK_REQUIRE(channels == 1 || channels == 3 || channels == 4, DUNK_ERR_ASSERT, "%s: %d channels", fn, channels);
+    DUNK_REQUIRE(row_stride >= cols * channels, DUNK_ERR_BAD_ARG, "%s: row stride < row bytes", fn);
+    return DUNK_OK;
+}
+
+size_t dunk_register_workspace_bytes(dunk_db* db, int n_frames, int rows, int cols) {
+    if (!db || n_frames <= 0) return 0;
+    return plan_pipeline(db->ctx, rows, cols, n_frames, db->size).total_bytes;
+}
+
+int dunk_register_frames_dev(dunk_db* db, int slot, const void* images_dev, int n_frames, int rows, int cols, int channels,
+                             int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
+                             void* workspace_dev, size_t workspace_bytes, void* results_dev) {
+    DUNK_REQUIRE(db && images_dev && workspace_dev && results_dev, DUNK_ERR_BAD_ARG, "dunk_register_frames_dev: NULL argument");
+    dunk_ctx* ctx = db->ctx;
+    DUNK_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), DUNK_ERR_BAD_ARG, "dunk_register_frames_dev: bad slot");
+    int rc = check_frames("dunk_register_frames_dev", n_frames, rows, cols, channels, row_stride_bytes);
+    if (rc) return rc;
+    if (n_frames == 0) return DUNK_OK;
+    if (frame_stride_bytes == 0) frame_stride_bytes = (size_t)rows * row_stride_bytes;
+    DUNK_CUDA(cudaSetDevice(ctx->device));
+    const PipelinePlan p = plan_pipeline(ctx, rows, cols, n_frames, db->size);
+    DUNK_REQUIRE(workspace_bytes >= p.total_bytes, DUNK_ERR_NO_MEM, "dunk_register_frames_dev: workspace %zu < %zu bytes",
+                 workspace_bytes, p.total_bytes);
+    PipelineBuffers b;
+    carve_pipeline(workspace_dev, p, &b);
+    cudaStream_t st = ctx->slots[slot].stream;
+    if ((rc = run_pipeline(ctx, st, db, p, b, (const unsigned char*)images_dev, frame_stride_bytes, row_stride_bytes, channels,
+                           n_frames, ratio, (float)thr, max_points <= 0 ? 0 : max_points, nullptr)))
+        return rc;
+    DUNK_CUDA(cudaMemcpyAsync(results_dev, b.results, (size_t)n_frames * sizeof(DunkRegistration), cudaMemcpyDeviceToDevice, st));
+    return DUNK_OK;
+}
+
+int dunk_register_frames(dunk_db* db, const uint8_t* images, int n_frames, int rows, int cols, int channels,
+                         int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
+                         DunkRegistration* results) {
+    DUNK_REQUIRE(db && results, DUNK_ERR_BAD_ARG, "dunk_register_frames: NULL argument");
+    dunk_ctx* ctx = db->ctx;
+    int rc = check_frames("dunk_register_frames", n_frames, rows, cols, channels, row_stride_bytes);
+    if (rc) return rc;
+    if (n_frames == 0) return DUNK_OK;
+    DUNK_REQUIRE(images, DUNK_ERR_ASSERT, "dunk_register_frames: empty image");
+    if (frame_stride_bytes == 0) frame_stride_bytes = (size_t)rows * row_stride_bytes;
+    SlotGuard g(ctx);
+    cudaStream_t st = g.stream();
+    // sub-batches of <= 64 frames keep the workspace bounded
+    const int sub = std::min(n_frames, 64);
+    const PipelinePlan p = plan_pipeline(ctx, rows, cols, sub, db->size);
+    const size_t need = al(p.total_bytes) + al((size_t)sub * frame_stride_bytes);
+    void* scratch = ctx->dev_scratch(g.s, need);
+    if (!scratch) return DUNK_ERR_NO_MEM;
+    PipelineBuffers b;
+    carve_pipeline(scratch, p, &b);
+    unsigned char* d_img = (unsigned char*)scratch + al(p.total_bytes);
+    for (int f0 = 0; f0 < n_frames; f0 += sub) {
+        const int nf = std::min(sub, n_frames - f0);
+        DUNK_CUDA(cudaMemcpyAsync(d_img, images + (size_t)f0 * frame_stride_bytes, (size_t)nf * frame_stride_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        if ((rc = run_pipeline(ctx, st, db, p, b, d_img, frame_stride_bytes, row_stride_bytes, channels, nf, ratio, (float)thr,
+                               max_points <= 0 ? 0 : max_points, nullptr)))
+            return rc;
+        DUNK_CUDA(cudaMemcpyAsync(results + f0, b.results, (size_t)nf * sizeof(DunkRegistration), cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaStreamSynchronize(st));
+    }
+    return DUNK_OK;
+}
+
+static __global__ void __launch_bounds__(256)
+k_append_rows(const uint4* __restrict__ desc64, const DunkKeyPoint* __restrict__ kps, int kp_cap, const int* __restrict__ counts,
+              const int* __restrict__ offsets, const float* __restrict__ x_off, const float* __restrict__ y_off,
+              const float* __restrict__ scale, const int32_t* __restrict__ image_ids, int tile0, uint4* __restrict__ db_desc,
+              DunkKeyPoint* __restrict__ db_kps, int32_t* __restrict__ db_ids, long long db_base) {
+    const int f = blockIdx.y;
+    const int n = counts[f];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long row = db_base + offsets[f] + i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) db_desc[row * 4 + k] = desc64[((size_t)f * kp_cap + i) * 4 + k];
+    DunkKeyPoint kp = kps[(size_t)f * kp_cap + i];
+    const float s = scale ? scale[tile0 + f] : 1.f;
+    // preprocessor/src/main.rs:300-301: x * 2^lod + column offset
+    kp.x = kp.x * s + (x_off ? x_off[tile0 + f] : 0.f);
+    kp.y = kp.y * s + (y_off ? y_off[tile0 + f] : 0.f);
+    db_kps[row] = kp;
+    db_ids[row] = image_ids ? image_ids[tile0 + f] : tile0 + f;
+}
+
+/* extract a tile batch and append keypoints + descriptors to the shard, mapping keypoint
+ * coordinates into scene pixels: x*scale + x_off (preprocessor/src/main.rs:296-304) */
+int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int rows, int cols, int channels,
+                         int row_stride_bytes, size_t frame_stride_bytes, const float* x_off, const float* y_off,
+                         const float* scale, const int32_t* image_ids, int max_points, int* counts) {
+    DUNK_REQUIRE(db, DUNK_ERR_BAD_ARG, "dunk_db_append_tiles: db is NULL");
+    dunk_ctx* ctx = db->ctx;
+    DUNK_REQUIRE(n_tiles >= 0, DUNK_ERR_BAD_ARG, "dunk_db_append_tiles: n_tiles < 0");
+    if (n_tiles == 0) return DUNK_OK;
+    int rc = check_frames("dunk_db_append_tiles", std::min(n_tiles, 1024), rows, cols, channels, row_stride_bytes);
+    if (rc) return rc;
+    DUNK_REQUIRE(images, DUNK_ERR_ASSERT, "dunk_db_append_tiles: empty image");
+    if (frame_stride_bytes == 0) frame_stride_bytes = (size_t)rows * row_stride_bytes;
+    std::lock_guard<std::mutex> lk(db->mu);
+    SlotGuard g(ctx);
+    cudaStream_t st = g.stream();
+    const int sub = std::min(n_tiles, 32);
+    const LevelTable lt = make_level_table(cols, rows);
+    long long c = (long long)cols * rows / 32;
+    c = std::min<long long>(std::max<long long>(c, 2048), 1 << 20);
+    const int cap = (int)c;
+    const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cap, cap);
+    const size_t meta = al((size_t)n_tiles * 4);
+    const size_t need = al(ws_bytes) + al((size_t)sub * frame_stride_bytes) + al((sub + 1) * 4) + 4 * meta;
+    void* scratch = ctx->dev_scratch(g.s, need);
+    if (!scratch) return DUNK_ERR_NO_MEM;
+    char* ptr = (char*)scratch;
+    AkazeWorkspace ws;
+    akaze_carve_workspace(ptr, lt, sub, cap, cap, &ws);
+    ptr += al(ws_bytes);
+    unsigned char* d_img = (unsigned char*)ptr; ptr += al((size_t)sub * frame_stride_bytes);
+    int* d_off = (int*)ptr; ptr += al((sub + 1) * 4);
+    float* d_xo = (float*)ptr; ptr += meta;
+    float* d_yo = (float*)ptr; ptr += meta;
+    float* d_sc = (float*)ptr; ptr += meta;
+    int32_t* d_id = (int32_t*)ptr;
+    if (x_off) DUNK_CUDA(cudaMemcpyAsync(d_xo, x_off, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
+    if (y_off) DUNK_CUDA(cudaMemcpyAsync(d_yo, y_off, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
+    if (scale) DUNK_CUDA(cudaMemcpyAsync(d_sc, scale, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
+    if (image_ids) DUNK_CUDA(cudaMemcpyAsync(d_id, image_ids, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
+    std::vector<int> h_off(sub + 1), h_cnt(sub);
+    for (int t0 = 0; t0 < n_tiles; t0 += sub) {
+        const int nf = std::min(sub, n_tiles - t0);
+        DUNK_CUDA(cudaMemcpyAsync(d_img, images + (size_t)t0 * frame_stride_bytes, (size_t)nf * frame_stride_bytes,
+                                  cudaMemcpyHostToDevice, st));
+        if ((rc = akaze_run(ctx, st, lt, ws, d_img, frame_stride_bytes, row_stride_bytes, channels, nf, max_points <= 0 ? 0 : max_points)))
+            return rc;
+        k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off);
+        DUNK_KERNEL_CHECK(ctx);
+        DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 1) * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaMemcpyAsync(h_cnt.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaStreamSynchronize(st));
+        const int total = h_off[nf];
+        DUNK_REQUIRE(db->size + total <= db->capacity, DUNK_ERR_NO_MEM,
+                     "dunk_db_append_tiles: %lld + %d rows exceed capacity %lld", (long long)db->size, total,
+                     (long long)db->capacity);
+        int maxc = 0;
+        for (int f = 0; f < nf; ++f) {
+            maxc = std::max(maxc, h_cnt[f]);
+            if (counts) counts[t0 + f] = h_cnt[f];
+        }
+        if (maxc > 0) {
+            k_append_rows<<<dim3(div_up(maxc, 256), nf), 256, 0, st>>>(ws.desc64, ws.kps, cap, ws.kp_count, d_off,
+                                                                      x_off ? d_xo : nullptr, y_off ? d_yo : nullptr,
+                                                                      scale ? d_sc : nullptr, image_ids ? d_id : nullptr, t0,
+                                                                      db->desc64, db->kps, db->image_id, db->size);
+            DUNK_KERNEL_CHECK(ctx);
+            DUNK_CUDA(cudaStreamSynchronize(st));
+        }
+        db->size += total;
+    }
+    return DUNK_OK;
+}
+
+}  // extern "C"

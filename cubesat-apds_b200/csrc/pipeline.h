@@ -1,0 +1,8 @@
+// Internal: cross-stage launchers used by the end-to-end registration pipeline.
+#pragma once
+#include "ctx.h"
+
+namespace dunk {
+int launch_find_homography(dunk_ctx* ctx, cudaStream_t st, const float2* src, const float2* dst, const int* starts,
+                           const int* counts, int n_problems, float thr, double* H, uint8_t* mask, int* info);
+}

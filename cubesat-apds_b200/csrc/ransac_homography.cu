@@ -13,6 +13,7 @@
 //   * refit on the inliers (normalised DLT, 9x9 symmetric Jacobi eigen, f64), <= 10
 //     Levenberg-Marquardt iterations with block-wide f64 reductions, final mask from the final H.
 #include "ctx.h"
+#include "pipeline.h"
 #include <cfloat>
 #include <cmath>
 
@@ -511,12 +512,12 @@ __device__ void lm_refine(Shared& sh, const float2* __restrict__ src, const floa
 // method: 8 = RANSAC, 0 = all points least squares (+LM)
 __global__ void __launch_bounds__(kThreads)
 find_homography_kernel(const float2* __restrict__ src_all, const float2* __restrict__ dst_all,
-                       const int* __restrict__ offsets, int method, float thr, int max_iters,
+                       const int* __restrict__ starts, const int* __restrict__ counts, int method, float thr, int max_iters,
                        double confidence, double* __restrict__ H_out, uint8_t* __restrict__ mask_out,
                        int* __restrict__ info_out /* [B][4]: found, inliers, iterations, hypotheses */) {
     __shared__ Shared sh;
     const int b = blockIdx.x;
-    const int off = offsets[b], n = offsets[b + 1] - off;
+    const int off = starts[b], n = counts[b];
     const float2* src = src_all + off;
     const float2* dst = dst_all + off;
     uint8_t* mask = mask_out ? mask_out + off : nullptr;
@@ -531,7 +532,7 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
         if (tid < 9) H_out[b * 9 + tid] = found ? sh.bestH[tid] : 0.0;
     };
 
-    if (n < 4) {  // callers reject this earlier (-28); keep the kernel safe
+    if (n < 4) {  // the host API rejects this earlier (-28); the pipeline reports "not found"
         for (int i = tid; i < n && mask; i += kThreads) mask[i] = 0;
         finish(0, 0, 0, 0);
         return;
@@ -688,6 +689,18 @@ score_hypotheses_kernel(const float2* __restrict__ src, const float2* __restrict
 }  // namespace
 }  // namespace dunk
 
+namespace dunk {
+int launch_find_homography(dunk_ctx* ctx, cudaStream_t st, const float2* src, const float2* dst, const int* starts,
+                           const int* counts, int n_problems, float thr, double* H, uint8_t* mask, int* info) {
+    if (n_problems <= 0) return DUNK_OK;
+    find_homography_kernel<<<n_problems, kThreads, 0, st>>>(src, dst, starts, counts, DUNK_H_RANSAC, thr, 2000, 0.995, H,
+                                                            mask, info);
+    ctx->launches.fetch_add(1);
+    DUNK_CUDA(cudaGetLastError());
+    return DUNK_OK;
+}
+}  // namespace dunk
+
 using namespace dunk;
 
 extern "C" {
@@ -710,7 +723,7 @@ int dunk_find_homography_batch(dunk_ctx* ctx, const float* src, const float* dst
     DUNK_REQUIRE(src && dst, DUNK_ERR_BAD_ARG, "dunk_find_homography_batch: NULL points");
     SlotGuard g(ctx);
     cudaStream_t st = g.stream();
-    size_t need = 2 * Carver::need((size_t)total * 8) + Carver::need((size_t)(n_problems + 1) * 4) +
+    size_t need = 2 * Carver::need((size_t)total * 8) + 2 * Carver::need((size_t)(n_problems + 1) * 4) +
                   Carver::need((size_t)n_problems * 72) + Carver::need((size_t)total) +
                   Carver::need((size_t)n_problems * 16);
     void* scratch = ctx->dev_scratch(g.s, need);
@@ -719,13 +732,17 @@ int dunk_find_homography_batch(dunk_ctx* ctx, const float* src, const float* dst
     float2* d_src = cv.take<float2>(total);
     float2* d_dst = cv.take<float2>(total);
     int* d_off = cv.take<int>(n_problems + 1);
+    int* d_cnt = cv.take<int>(n_problems + 1);
     double* d_H = cv.take<double>((size_t)n_problems * 9);
     uint8_t* d_mask = cv.take<uint8_t>(total);
     int* d_info = cv.take<int>((size_t)n_problems * 4);
     DUNK_CUDA(cudaMemcpyAsync(d_src, src, (size_t)total * 8, cudaMemcpyHostToDevice, st));
     DUNK_CUDA(cudaMemcpyAsync(d_dst, dst, (size_t)total * 8, cudaMemcpyHostToDevice, st));
     DUNK_CUDA(cudaMemcpyAsync(d_off, offsets, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, st));
-    find_homography_kernel<<<n_problems, kThreads, 0, st>>>(d_src, d_dst, d_off, method, (float)thr, 2000,
+    std::vector<int> h_cnt(n_problems);
+    for (int b = 0; b < n_problems; ++b) h_cnt[b] = offsets[b + 1] - offsets[b];
+    DUNK_CUDA(cudaMemcpyAsync(d_cnt, h_cnt.data(), (size_t)n_problems * 4, cudaMemcpyHostToDevice, st));
+    find_homography_kernel<<<n_problems, kThreads, 0, st>>>(d_src, d_dst, d_off, d_cnt, method, (float)thr, 2000,
                                                             0.995, d_H, d_mask, d_info);
     ctx->launches.fetch_add(1);
     DUNK_CUDA(cudaGetLastError());

@@ -67,6 +67,45 @@ class DescriptorDatabase:
                 raise DunkError(_lib.ERR_VEC_LENGTH, "row-count mismatch between columns")
         check(_lib.load().dunk_db_append(self.handle, ptr(d), ptr(k), ptr(im), d.shape[0]))
 
+    def append_tiles(self, tiles: np.ndarray, x_off=None, y_off=None, scale=None, image_ids=None,
+                     max_points: int = _lib.MAX_POINTS) -> np.ndarray:
+        """Reference-DB build for a tile batch [T, H, W(, C)] u8: AKAZE on every tile, rows appended
+        with keypoint coordinates mapped to scene pixels `x * scale + x_off` — what
+        preprocessor::feature_extraction_to_database does per tile (preprocessor/src/main.rs:248-327)
+        minus GDAL / Postgres.  Returns the rows added per tile."""
+        a = np.asarray(tiles)
+        if a.ndim == 3:
+            a = a[..., None]
+        if a.dtype != np.uint8 or a.ndim != 4:
+            raise DunkError(_lib.ERR_ASSERT, f"tile batch shape {a.shape} / dtype {a.dtype} unsupported")
+        a = np.ascontiguousarray(a)
+        T, rows, cols, ch = a.shape
+
+        def col(v, dt):
+            return None if v is None else np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=dt), (T,)))
+        xo, yo, sc, ids = col(x_off, np.float32), col(y_off, np.float32), col(scale, np.float32), col(image_ids, np.int32)
+        counts = np.zeros(T, dtype=np.int32)
+        check(_lib.load().dunk_db_append_tiles(self.handle, ptr(a), T, rows, cols, ch, cols * ch, rows * cols * ch,
+                                               ptr(xo), ptr(yo), ptr(sc), ptr(ids), int(max_points), ptr(counts)))
+        return counts
+
+    def register_frames(self, frames: np.ndarray, ratio: float = 0.8, reproj_threshold: float = 3.0,
+                        max_points: int = _lib.MAX_POINTS) -> np.ndarray:
+        """The whole hot path for a frame batch [B, H, W(, C)] u8 against this shard: extract ->
+        2-NN + Lowe ratio -> RANSAC homography.  Returns REGISTRATION_DTYPE records (H maps frame
+        pixels to scene pixels)."""
+        a = np.asarray(frames)
+        if a.ndim == 3:
+            a = a[..., None]
+        if a.dtype != np.uint8 or a.ndim != 4:
+            raise DunkError(_lib.ERR_ASSERT, f"frame batch shape {a.shape} / dtype {a.dtype} unsupported")
+        a = np.ascontiguousarray(a)
+        B, rows, cols, ch = a.shape
+        out = np.zeros(B, dtype=_lib.REGISTRATION_DTYPE)
+        check(_lib.load().dunk_register_frames(self.handle, ptr(a), B, rows, cols, ch, cols * ch, rows * cols * ch,
+                                               float(ratio), float(reproj_threshold), int(max_points), ptr(out)))
+        return out
+
     def append_random(self, n: int, seed: int):
         check(_lib.load().dunk_db_append_random(self.handle, int(n), int(seed)))
 

@@ -1,0 +1,70 @@
+"""Synthetic imagery for benchmarks and tests: multi-scale smoothed noise tiles and
+known-homography warps.  numpy only — input generation, not part of the measured path."""
+from __future__ import annotations
+
+import numpy as np
+
+# SURVEY 8d config 1
+H_CONFIG1 = np.array([[0.98, -0.12, 60.0], [0.10, 1.03, -40.0], [1e-5, -2e-5, 1.0]])
+
+
+def _upsample_bilinear(a: np.ndarray, h: int, w: int) -> np.ndarray:
+    ys = np.linspace(0, a.shape[0] - 1, h)
+    xs = np.linspace(0, a.shape[1] - 1, w)
+    y0 = np.clip(np.floor(ys).astype(int), 0, a.shape[0] - 2)
+    x0 = np.clip(np.floor(xs).astype(int), 0, a.shape[1] - 2)
+    fy = (ys - y0)[:, None]
+    fx = (xs - x0)[None, :]
+    a00 = a[y0][:, x0]; a01 = a[y0][:, x0 + 1]; a10 = a[y0 + 1][:, x0]; a11 = a[y0 + 1][:, x0 + 1]
+    return (a00 * (1 - fx) + a01 * fx) * (1 - fy) + (a10 * (1 - fx) + a11 * fx) * fy
+
+
+def synth_image(h: int, w: int | None = None, seed: int = 0) -> np.ndarray:
+    """u8 image: sum over s in {1,2,4,8,16,32} of upsampled N(0,1) noise * sqrt(s), box-smoothed and
+    min-max normalised (same recipe as SURVEY 8d's `synth`, with numpy interpolation)."""
+    w = w or h
+    rng = np.random.default_rng(seed)
+    acc = np.zeros((h, w), np.float32)
+    for s in (1, 2, 4, 8, 16, 32):
+        n = rng.standard_normal((h // s + 2, w // s + 2)).astype(np.float32)
+        acc += _upsample_bilinear(n, h, w).astype(np.float32) * np.float32(np.sqrt(s))
+    # light 3x3 smoothing so that single-pixel noise does not dominate
+    p = np.pad(acc, 1, mode="edge")
+    acc = (p[:-2, :-2] + p[:-2, 1:-1] + p[:-2, 2:] + p[1:-1, :-2] + p[1:-1, 1:-1] + p[1:-1, 2:] +
+           p[2:, :-2] + p[2:, 1:-1] + p[2:, 2:]) / 9.0
+    acc = (acc - acc.min()) / (acc.max() - acc.min())
+    return (acc * 255).astype(np.uint8)
+
+
+def warp_perspective(img: np.ndarray, H: np.ndarray, out_h: int, out_w: int, border: int = 1) -> np.ndarray:
+    """dst(x, y) = src(H^-1 (x, y)) with bilinear interpolation and a constant border (the reference
+    warps with BORDER_CONSTANT value 1, homographier mod.rs:286-294).  H maps src -> dst."""
+    Hi = np.linalg.inv(H)
+    ys, xs = np.mgrid[0:out_h, 0:out_w].astype(np.float64)
+    d = Hi[2, 0] * xs + Hi[2, 1] * ys + Hi[2, 2]
+    sx = (Hi[0, 0] * xs + Hi[0, 1] * ys + Hi[0, 2]) / d
+    sy = (Hi[1, 0] * xs + Hi[1, 1] * ys + Hi[1, 2]) / d
+    x0 = np.floor(sx).astype(np.int64); y0 = np.floor(sy).astype(np.int64)
+    fx = (sx - x0).astype(np.float32); fy = (sy - y0).astype(np.float32)
+    h, w = img.shape[:2]
+    src = img.astype(np.float32)
+
+    def at(yy, xx):
+        ok = (yy >= 0) & (yy < h) & (xx >= 0) & (xx < w)
+        v = src[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)]
+        return np.where(ok, v, np.float32(border))
+    out = (at(y0, x0) * (1 - fx) + at(y0, x0 + 1) * fx) * (1 - fy) + (at(y0 + 1, x0) * (1 - fx) + at(y0 + 1, x0 + 1) * fx) * fy
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def window_homography(x0: float, y0: float, seed: int, jitter: float = 1.0) -> np.ndarray:
+    """scene -> frame homography of a query frame looking at the scene window with top-left (x0, y0):
+    small rotation / scale / perspective around the window (config 5: "known-H warp of a window")."""
+    r = np.random.default_rng(seed)
+    ang = r.uniform(-0.12, 0.12) * jitter
+    s = 1.0 + r.uniform(-0.05, 0.05) * jitter
+    A = np.array([[s * np.cos(ang), -s * np.sin(ang), 0.0], [s * np.sin(ang), s * np.cos(ang), 0.0],
+                  [r.uniform(-2e-5, 2e-5) * jitter, r.uniform(-2e-5, 2e-5) * jitter, 1.0]])
+    T = np.array([[1.0, 0, -x0], [0, 1.0, -y0], [0, 0, 1.0]])
+    C = np.array([[1.0, 0, -512.0], [0, 1.0, -512.0], [0, 0, 1.0]])
+    return np.linalg.inv(C) @ A @ C @ T

@@ -192,6 +192,35 @@ int dunk_ransac_score_hypotheses(dunk_ctx* ctx, const float* src, const float* d
                                  const int* samples, int n_hyp, double thr, int* counts,
                                  double* Hs);
 
+/* ---- the whole path: frame batch -> extract -> 2-NN + ratio vs the shard -> RANSAC homography
+ * The composition the reference performs in feature_extraction/src/lib.rs:196-249 followed by
+ * find_homography_mat (mod.rs:231-259), for a batch of same-shape frames, without leaving the
+ * device between the stages.  H maps query-frame pixels to reference (scene) pixels. */
+typedef struct DunkRegistration {
+    double H[9];        /* row-major, H[8] = 1; zeros when !found */
+    int32_t found;      /* 1 = a homography was found */
+    int32_t inliers;    /* inliers of the final H */
+    int32_t matches;    /* ratio-test survivors fed to RANSAC */
+    int32_t keypoints;  /* keypoints extracted from the frame */
+    int32_t ransac_iters, hypotheses;
+} DunkRegistration;
+int dunk_register_frames(dunk_db* db, const uint8_t* images, int n_frames, int rows, int cols,
+                         int channels, int row_stride_bytes, size_t frame_stride_bytes, float ratio,
+                         double thr, int max_points, DunkRegistration* results);
+/* device-resident variant (async on the slot's stream; results_dev: n_frames records) */
+size_t dunk_register_workspace_bytes(dunk_db* db, int n_frames, int rows, int cols);
+int dunk_register_frames_dev(dunk_db* db, int slot, const void* images_dev, int n_frames, int rows,
+                             int cols, int channels, int row_stride_bytes, size_t frame_stride_bytes,
+                             float ratio, double thr, int max_points, void* workspace_dev,
+                             size_t workspace_bytes, void* results_dev);
+/* reference-DB build (preprocessor/src/main.rs:248-327 minus GDAL/Postgres): extract a tile
+ * batch and append rows to the shard; keypoint coordinates become x*scale[t] + x_off[t]
+ * (main.rs:296-304); image_ids[t] -> image_id column.  counts (may be NULL): rows per tile. */
+int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int rows, int cols,
+                         int channels, int row_stride_bytes, size_t frame_stride_bytes,
+                         const float* x_off, const float* y_off, const float* scale,
+                         const int32_t* image_ids, int max_points, int* counts);
+
 /* ---- roofline denominators measured on the box ---------------------------------------- */
 /* POPC-pipe peak in 1e12 popc/s (best of 4 timed launches of `iters` x 32 popc per thread) */
 int dunk_microbench_popc(dunk_ctx* ctx, int iters, double* tpopc_per_s);

@@ -1,0 +1,77 @@
+"""GPU: the composed path (extract -> match -> RANSAC on the device) equals the stage-by-stage
+calls through the mirrored reference API, and recovers the known homography (config 1 shape)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import match_oracle as mo
+from oracle import ransac_oracle as ro
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "akaze_golden.npz"))
+
+
+def test_config1_small(dunk, ctx):
+    """a tile vs itself warped by a known homography: extract both, 2-NN match, RANSAC."""
+    fe, hg, fdb, synth = dunk.feature_extraction, dunk.homographier, dunk.feature_database, dunk.synth
+    ref = G["b_img"]                                   # 512 x 512
+    Ht = np.array([[0.99, -0.06, 20.0], [0.05, 1.02, -14.0], [1e-5, -2e-5, 1.0]])
+    qry = synth.warp_perspective(ref, Ht, 512, 512)
+    # --- composed path
+    db = fdb.DescriptorDatabase(ctx, capacity=20000)
+    counts = db.append_tiles(ref[None], x_off=0.0, y_off=0.0, scale=1.0, image_ids=[7])
+    res = db.register_frames(qry[None], ratio=0.8, reproj_threshold=3.0)[0]
+    # --- stage by stage through the mirrored reference API
+    kr = fe.akaze_keypoint_descriptor_extraction_def(ref, None, ctx)
+    kq = fe.akaze_keypoint_descriptor_extraction_def(qry, None, ctx)
+    assert counts[0] == len(kr.keypoints) == len(db)
+    d, k, ids = db.read_rows(0, len(db))
+    assert np.array_equal(d, kr.descriptors) and np.array_equal(k, kr.keypoints) and (ids == 7).all()
+    m = fe.get_knn_matches(kq.descriptors, kr.descriptors, 2, 0.8, ctx)
+    p_q, p_r = fe.get_points_from_matches(kq.keypoints, kr.keypoints, m)
+    H, mask = hg.find_homography_mat(p_q, p_r, hg.HomographyMethod.RANSAC, 3.0, ctx)
+    assert res["found"] == 1 and res["keypoints"] == len(kq.keypoints) and res["matches"] == len(m)
+    assert res["inliers"] == int(mask.mat.sum())
+    assert np.allclose(res["H"].reshape(3, 3), H.mat, rtol=1e-12, atol=1e-12)
+    # --- against the oracle fed the same descriptors / points (bit-exact matches; H within 1e-4)
+    qi, ti, dd = mo.knn_match(kq.descriptors, kr.descriptors, 0.8)
+    assert np.array_equal(m["query_idx"], qi) and np.array_equal(m["train_idx"], ti) and np.array_equal(m["distance"], dd)
+    Ho, mo_mask = ro.find_homography_ransac(p_q, p_r, 3.0)
+    assert np.array_equal(mask.mat.ravel(), mo_mask)
+    assert np.abs(H.mat - Ho).max() / np.abs(Ho).max() < 1e-4
+    # --- and the recovered homography is the inverse warp (query -> reference)
+    Hinv = np.linalg.inv(Ht)
+    Hinv /= Hinv[2, 2]
+    assert len(m) > 100 and res["inliers"] > 0.8 * len(m)
+    assert np.abs(H.mat - Hinv).max() / np.abs(Hinv).max() < 5e-3
+    db.close()
+
+
+def test_batch_registration_and_tile_offsets(dunk, ctx):
+    fdb, synth = dunk.feature_database, dunk.synth
+    scene = synth.synth_image(512, 768, seed=3)
+    tiles = np.stack([scene[:, :384], scene[:, 384:]])           # two 512 x 384 tiles
+    db = fdb.DescriptorDatabase(ctx, capacity=50000)
+    counts = db.append_tiles(tiles, x_off=[0.0, 384.0], y_off=[0.0, 0.0], scale=1.0, image_ids=[1, 2])
+    assert counts.sum() == len(db) and (counts > 50).all()
+    _, k, ids = db.read_rows(0, len(db))
+    assert (k["x"][ids == 2] >= 384).all() and (k["x"][ids == 1] < 384).all()
+    frames, Hs = [], []
+    for i, (x0, y0) in enumerate([(40, 30), (300, 100), (200, 0)]):
+        T = np.array([[1.0, 0, -x0], [0, 1.0, -y0], [0, 0, 1.0]])
+        A = np.array([[1.01, 0.03, 0.0], [-0.03, 0.99, 0.0], [1e-5, 0, 1.0]])
+        H = A @ T                                                 # scene -> frame
+        frames.append(synth.warp_perspective(scene, H, 384, 384))
+        Hs.append(H)
+    res = db.register_frames(np.stack(frames), ratio=0.8, reproj_threshold=3.0)
+    for r, H in zip(res, Hs):
+        Hi = np.linalg.inv(H)
+        Hi /= Hi[2, 2]                                            # frame -> scene
+        assert r["found"] == 1 and r["inliers"] >= 30
+        assert np.abs(r["H"].reshape(3, 3) - Hi).max() / np.abs(Hi).max() < 1e-2
+    # a frame of pure noise finds no registration but does not error
+    noise = np.random.default_rng(0).integers(0, 256, (1, 384, 384), dtype=np.uint8)
+    r = db.register_frames(noise)[0]
+    assert r["found"] in (0, 1) and r["inliers"] < 12
+    db.close()
