@@ -10,7 +10,6 @@ from . import _lib
 from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, REGISTRATION_DTYPE, TOP2_DTYPE, Context, DunkError, default_context)
 from . import feature_extraction
 from . import _extract
-from . import synth
 from . import feature_database
 from . import homographier
 

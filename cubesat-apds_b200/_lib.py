@@ -89,6 +89,8 @@ SIGNATURES = {
     "dunk_top2_merge_dev": (_i, [_vp, _i, _vp, _i, _i, _vp]),
     "dunk_top2_ratio_dev": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp]),
     "dunk_pad_desc_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp]),
+    "dunk_profile_begin": (_i, [_vp]),
+    "dunk_profile_end": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i]),
     "dunk_microbench_popc": (_i, [_vp, _i, C.POINTER(_d)]),
     "dunk_akaze_extract": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _pi]),
     "dunk_akaze_extract_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _i, _vp, _vp, _i, _vp]),

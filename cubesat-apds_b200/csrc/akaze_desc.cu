@@ -250,11 +250,17 @@ int akaze_describe(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const A
     if (rc) return rc;
     const LevelsDev lv = make_levels_dev(lt);
     const dim3 grid(div_up(ws.kp_cap, kWarpsPerBlock), frames);
-    k_orientation<<<grid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lx, ws.Ly, lt.pyramid_floats, lv);
-    DUNK_KERNEL_CHECK(ctx);
-    k_mldb<<<grid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lt, ws.Lx, ws.Ly, lt.pyramid_floats, lv,
-                                                 ws.desc64);
-    DUNK_KERNEL_CHECK(ctx);
+    {
+        ProfScope ps(ctx, st, "describe.orientation", 0.0);
+        k_orientation<<<grid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lx, ws.Ly, lt.pyramid_floats, lv);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, st, "describe.mldb", 0.0);
+        k_mldb<<<grid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lt, ws.Lx, ws.Ly, lt.pyramid_floats, lv,
+                                                     ws.desc64);
+        DUNK_KERNEL_CHECK(ctx);
+    }
     return DUNK_OK;
 }
 

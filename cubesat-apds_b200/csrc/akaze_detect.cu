@@ -411,24 +411,42 @@ int akaze_detect(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const Aka
         if (e.border + 1 >= e.h) continue;   // FindKeypointsSameScale: border too big
         const int iw = e.w - 2 * e.border, ih = e.h - 2 * e.border;
         if (iw <= 0 || ih <= 0) continue;
-        k_extrema<<<dim3(div_up(iw, 32), div_up(ih, 8), frames), dim3(32, 8), 0, st>>>(
-            ws.Ldet, pyr, lv.lv[i], i, row_base_h[i], dthreshold, ws.cand_raw, ws.cand_cap, ws.cand_count, ws.row_count,
-            ws.total_rows);
+        {
+            ProfScope ps(ctx, st, "detect.extrema", (double)frames * iw * ih * 4);
+            k_extrema<<<dim3(div_up(iw, 32), div_up(ih, 8), frames), dim3(32, 8), 0, st>>>(
+                ws.Ldet, pyr, lv.lv[i], i, row_base_h[i], dthreshold, ws.cand_raw, ws.cand_cap, ws.cand_count, ws.row_count,
+                ws.total_rows);
+            DUNK_KERNEL_CHECK(ctx);
+        }
+    }
+    {
+        ProfScope ps(ctx, st, "detect.row_scan", 0.0);
+        k_row_scan<<<frames, 1024, 0, st>>>(ws.row_count, ws.row_start, ws.row_fill, ws.total_rows);
         DUNK_KERNEL_CHECK(ctx);
     }
-    k_row_scan<<<frames, 1024, 0, st>>>(ws.row_count, ws.row_start, ws.row_fill, ws.total_rows);
-    DUNK_KERNEL_CHECK(ctx);
-    k_scatter<<<dim3(div_up(ws.cand_cap, 256), frames), 256, 0, st>>>(ws.cand_raw, ws.cand, ws.cand_count, ws.cand_cap,
-                                                                      ws.row_start, ws.row_fill, ws.total_rows, lv, row_base_d);
-    DUNK_KERNEL_CHECK(ctx);
-    k_sort_rows<<<dim3(div_up(ws.total_rows, 256), frames), 256, 0, st>>>(ws.cand, ws.cand_cap, ws.row_start, ws.total_rows);
-    DUNK_KERNEL_CHECK(ctx);
-    k_suppress<<<frames, 512, 0, st>>>(ws.cand, ws.cand_count, ws.cand_cap, ws.row_start, ws.total_rows, lv, row_base_d,
-                                       ws.state, ws.aux);
-    DUNK_KERNEL_CHECK(ctx);
-    k_refine<<<frames, 1024, 0, st>>>(ws.cand, ws.cand_count, ws.cand_cap, ws.state, ws.Ldet, pyr, lv, ws.kps, ws.kp_cap,
-                                      ws.kp_count);
-    DUNK_KERNEL_CHECK(ctx);
+    {
+        ProfScope ps(ctx, st, "detect.scatter", 0.0);
+        k_scatter<<<dim3(div_up(ws.cand_cap, 256), frames), 256, 0, st>>>(ws.cand_raw, ws.cand, ws.cand_count, ws.cand_cap,
+                                                                          ws.row_start, ws.row_fill, ws.total_rows, lv, row_base_d);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, st, "detect.sort_rows", 0.0);
+        k_sort_rows<<<dim3(div_up(ws.total_rows, 256), frames), 256, 0, st>>>(ws.cand, ws.cand_cap, ws.row_start, ws.total_rows);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, st, "detect.suppress", 0.0);
+        k_suppress<<<frames, 512, 0, st>>>(ws.cand, ws.cand_count, ws.cand_cap, ws.row_start, ws.total_rows, lv, row_base_d,
+                                           ws.state, ws.aux);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, st, "detect.refine", 0.0);
+        k_refine<<<frames, 1024, 0, st>>>(ws.cand, ws.cand_count, ws.cand_cap, ws.state, ws.Ldet, pyr, lv, ws.kps, ws.kp_cap,
+                                          ws.kp_count);
+        DUNK_KERNEL_CHECK(ctx);
+    }
     if (max_points > 0 && max_points < ws.kp_cap) {
         int p2 = 1;
         while (p2 < ws.kp_cap) p2 <<= 1;

@@ -505,20 +505,32 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
     // level 0
     {
         const dim3 grid(div_up(W, kTW), div_up(H, kTH), frames);
-        k_gray_gauss9<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g9,
-                                            ws.Lt + lt.lv[0].plane_off, pyr);
-        DUNK_KERNEL_CHECK(ctx);
+        {
+            ProfScope ps(ctx, st, "scale.gray_gauss9", (double)frames * plane * (channels + 4));
+            k_gray_gauss9<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g9,
+                                                ws.Lt + lt.lv[0].plane_off, pyr);
+            DUNK_KERNEL_CHECK(ctx);
+        }
         if (lt.n_levels > 1) {
             DUNK_CUDA(cudaMemsetAsync(ws.hmax, 0, (size_t)frames * 4, st));
             DUNK_CUDA(cudaMemsetAsync(ws.hist, 0, (size_t)frames * kNBins * 4, st));
-            k_contrast_modg<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g5,
-                                                  ws.Lflow, plane, ws.hmax);
-            DUNK_KERNEL_CHECK(ctx);
+            {
+                ProfScope ps(ctx, st, "scale.contrast_modg", (double)frames * plane * (channels + 4));
+                k_contrast_modg<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g5,
+                                                      ws.Lflow, plane, ws.hmax);
+                DUNK_KERNEL_CHECK(ctx);
+            }
             const int hb = std::max(1, std::min(64, div_up((long long)(W - 2) * (H - 2), 256 * 16)));
-            k_contrast_hist<<<dim3(hb, frames), 256, 0, st>>>(ws.Lflow, plane, W, H, ws.hmax, ws.hist);
-            DUNK_KERNEL_CHECK(ctx);
-            k_contrast_final<<<div_up(frames, 64), 64, 0, st>>>(ws.hist, ws.hmax, W, H, 0.7f, ws.kcontrast, frames);
-            DUNK_KERNEL_CHECK(ctx);
+            {
+                ProfScope ps(ctx, st, "scale.contrast_hist", (double)frames * plane * 4);
+                k_contrast_hist<<<dim3(hb, frames), 256, 0, st>>>(ws.Lflow, plane, W, H, ws.hmax, ws.hist);
+                DUNK_KERNEL_CHECK(ctx);
+            }
+            {
+                ProfScope ps(ctx, st, "scale.contrast_final", 0.0);
+                k_contrast_final<<<div_up(frames, 64), 64, 0, st>>>(ws.hist, ws.hmax, W, H, 0.7f, ws.kcontrast, frames);
+                DUNK_KERNEL_CHECK(ctx);
+            }
         }
     }
     auto hessian = [&](int i, const float* lsm, size_t lsm_stride) -> int {
@@ -534,9 +546,12 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
         }
         const size_t smem = ((size_t)(kTW + 4 * s) * (kTH + 4 * s) + 2 * (size_t)(kTW + 2 * s) * (kTH + 2 * s)) * 4;
         const dim3 grid(div_up(e.w, kTW), div_up(e.h, kTH), frames);
-        k_hessian<<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, s, w0, w1, (float)(s * s * s * s),
-                                           ws.Lx + e.plane_off, ws.Ly + e.plane_off, ws.Ldet + e.plane_off, pyr);
-        DUNK_KERNEL_CHECK(ctx);
+        {
+            ProfScope ps(ctx, st, "scale.hessian", (double)frames * e.w * e.h * 16);
+            k_hessian<<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, s, w0, w1, (float)(s * s * s * s),
+                                               ws.Lx + e.plane_off, ws.Ly + e.plane_off, ws.Ldet + e.plane_off, pyr);
+            DUNK_KERNEL_CHECK(ctx);
+        }
         return DUNK_OK;
     };
     int rc = hessian(0, ws.Lt + lt.lv[0].plane_off, pyr);
@@ -558,9 +573,12 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             const bool out0_is_P = ((m - 1) % 2 == 0);
             float* dstbuf = out0_is_P ? Q : P;
             const size_t dstride = out0_is_P ? plane : pyr;
-            k_halfsample<<<dim3(div_up(e.w, 256), e.h, frames), 256, 0, st>>>(ws.Lt + p.plane_off, pyr, p.w, p.h, dstbuf,
-                                                                           dstride, e.w, e.h);
-            DUNK_KERNEL_CHECK(ctx);
+            {
+                ProfScope ps(ctx, st, "scale.halfsample", (double)frames * ((double)p.w * p.h + (double)e.w * e.h) * 4);
+                k_halfsample<<<dim3(div_up(e.w, 256), e.h, frames), 256, 0, st>>>(ws.Lt + p.plane_off, pyr, p.w, p.h, dstbuf,
+                                                                               dstride, e.w, e.h);
+                DUNK_KERNEL_CHECK(ctx);
+            }
             init = dstbuf;
             init_stride = dstride;
         } else {
@@ -568,8 +586,11 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             init_stride = pyr;
         }
         const dim3 grid(div_up(e.w, kTW), div_up(e.h, kTH), frames);
-        k_prep_level<<<grid, blk, 0, st>>>(init, init_stride, e.w, e.h, g5, ws.kcontrast, kscale, ws.Lsmooth, ws.Lflow, plane);
-        DUNK_KERNEL_CHECK(ctx);
+        {
+            ProfScope ps(ctx, st, "scale.prep_level", (double)frames * e.w * e.h * 12);
+            k_prep_level<<<grid, blk, 0, st>>>(init, init_stride, e.w, e.h, g5, ws.kcontrast, kscale, ws.Lsmooth, ws.Lflow, plane);
+            DUNK_KERNEL_CHECK(ctx);
+        }
         if ((rc = hessian(i, ws.Lsmooth, plane))) return rc;
         const float* in = init;
         size_t in_stride = init_stride;
@@ -582,8 +603,11 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             const size_t out_stride = out_is_P ? pyr : plane;
             const int S = kFedT + 2 * fs.k;
             const dim3 fgrid(div_up(e.w, kFedT), div_up(e.h, kFedT), frames);
-            k_fed<<<fgrid, blk, (size_t)3 * S * S * 4, st>>>(in, in_stride, out, out_stride, ws.Lflow, plane, e.w, e.h, fs);
-            DUNK_KERNEL_CHECK(ctx);
+            {
+                ProfScope ps(ctx, st, "scale.fed", (double)frames * e.w * e.h * 12);
+                k_fed<<<fgrid, blk, (size_t)3 * S * S * 4, st>>>(in, in_stride, out, out_stride, ws.Lflow, plane, e.w, e.h, fs);
+                DUNK_KERNEL_CHECK(ctx);
+            }
             in = out;
             in_stride = out_stride;
         }

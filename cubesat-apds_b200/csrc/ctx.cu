@@ -159,6 +159,49 @@ int dunk_sync(dunk_ctx* c, int slot) {
     return DUNK_OK;
 }
 
+int dunk_profile_begin(dunk_ctx* c) {
+    DUNK_REQUIRE(c, DUNK_ERR_BAD_ARG, "dunk_profile_begin: ctx is NULL");
+    std::lock_guard<std::mutex> lk(c->prof_mu);
+    for (auto& p : c->prof)
+        for (auto& e : p.ev) {
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+    c->prof.clear();
+    c->prof_on = true;
+    return DUNK_OK;
+}
+
+int dunk_profile_end(dunk_ctx* c, char* names, int names_cap, double* ms, int* launches, double* alg, int cap) {
+    DUNK_REQUIRE(c && names && ms && launches && alg && names_cap > 0, DUNK_ERR_BAD_ARG, "dunk_profile_end: NULL argument");
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(c->prof_mu);
+    c->prof_on = false;
+    std::string all;
+    int n = 0;
+    for (auto& p : c->prof) {
+        if (n >= cap) break;
+        double t = 0;
+        for (auto& e : p.ev) {
+            float x = 0;
+            if (cudaEventElapsedTime(&x, e.first, e.second) == cudaSuccess) t += x;
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+        p.ev.clear();
+        ms[n] = t;
+        launches[n] = p.count;
+        alg[n] = p.alg;
+        all += p.name;
+        all += ';';
+        ++n;
+    }
+    c->prof.clear();
+    snprintf(names, names_cap, "%s", all.c_str());
+    return n;
+}
+
 int dunk_ctx_reserve_slot(dunk_ctx* c) {
     DUNK_REQUIRE(c, DUNK_ERR_BAD_ARG, "dunk_ctx_reserve_slot: ctx is NULL");
     std::lock_guard<std::mutex> lk(c->mu);

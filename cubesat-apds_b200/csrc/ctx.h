@@ -27,6 +27,16 @@ struct Slot {
 
 }  // namespace dunk
 
+namespace dunk {
+// optional per-kernel-class CUDA-event profiler (bench.py's per-stage times and roofline)
+struct ProfAccum {
+    std::string name;
+    double alg = 0;   // algorithmic bytes (or ops) accumulated by the launch sites
+    int count = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+};
+}  // namespace dunk
+
 struct dunk_ctx {
     int device = 0;
     int sm_count = 0;
@@ -34,6 +44,9 @@ struct dunk_ctx {
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<uint64_t> launches{0};
+    bool prof_on = false;
+    std::vector<dunk::ProfAccum> prof;
+    std::mutex prof_mu;
 
     int acquire();          // blocks until a slot is free
     void release(int s);
@@ -51,6 +64,35 @@ struct SlotGuard {
     ~SlotGuard() { ctx->release(s); }
     Slot& slot() { return ctx->slots[s]; }
     cudaStream_t stream() { return ctx->slots[s].stream; }
+};
+
+// RAII: when profiling is on, brackets the launches issued in its scope with two CUDA events
+struct ProfScope {
+    dunk_ctx* ctx;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(dunk_ctx* c, cudaStream_t s, const char* name, double alg) : ctx(c), st(s) {
+        if (!c->prof_on) return;
+        std::lock_guard<std::mutex> lk(c->prof_mu);
+        ProfAccum* a = nullptr;
+        for (auto& p : c->prof)
+            if (p.name == name) a = &p;
+        if (!a) {
+            c->prof.push_back(ProfAccum{});
+            a = &c->prof.back();
+            a->name = name;
+        }
+        cudaEvent_t e0;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        a->ev.emplace_back(e0, e1);
+        a->alg += alg;
+        a->count += 1;
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
 };
 
 // bump allocator over a scratch block (256-B aligned pieces)

@@ -364,9 +364,12 @@ int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, 
     }
     // with a single slab the kernel's partial IS the result
     uint4* dst = (p.gx == 1) ? top2_out : partial;
-    hamming_top2_kernel<kQT><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
-        db64, nt, q64, nq, p.tiles_per_cta, index_base, dst);
-    DUNK_LAUNCH_CHECK(ctx);
+    {
+        ProfScope ps(ctx, st, "match.hamming_top2", (double)nq * (double)nt);   // pairs
+        hamming_top2_kernel<kQT><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
+            db64, nt, q64, nq, p.tiles_per_cta, index_base, dst);
+        DUNK_LAUNCH_CHECK(ctx);
+    }
     if (p.gx > 1) return launch_top2_merge(ctx, st, partial, p.gx, nq, top2_out);
     return DUNK_OK;
 }
@@ -374,6 +377,7 @@ int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, 
 int launch_top2_merge(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_parts, int nq,
                       uint4* out) {
     if (nq <= 0) return DUNK_OK;
+    ProfScope ps(ctx, st, "match.top2_merge", (double)nq * n_parts * 16);
     top2_merge_kernel<<<div_up(nq, 128), 128, 0, st>>>(parts, n_parts, nq, out);
     DUNK_LAUNCH_CHECK(ctx);
     return DUNK_OK;

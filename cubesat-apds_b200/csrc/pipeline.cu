@@ -181,11 +181,17 @@ static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const Pipel
                         float ratio, float thr, int max_points, int* h_total_q /*pinned or NULL*/) {
     int rc = akaze_run(ctx, st, p.lt, b.ws, images_dev, frame_stride, row_stride, channels, frames, max_points);
     if (rc) return rc;
-    k_frame_offsets<<<1, 1024, 0, st>>>(b.ws.kp_count, frames, b.q_off);
-    DUNK_KERNEL_CHECK(ctx);
-    k_pack_queries<<<dim3(div_up((long long)p.kp_cap * 4, 256), frames), 256, 0, st>>>(b.ws.desc64, p.kp_cap, b.ws.kp_count,
-                                                                                      b.q_off, b.q64);
-    DUNK_KERNEL_CHECK(ctx);
+    {
+        ProfScope ps(ctx, st, "pipe.frame_offsets", 0.0);
+        k_frame_offsets<<<1, 1024, 0, st>>>(b.ws.kp_count, frames, b.q_off);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, st, "pipe.pack_queries", 0.0);
+        k_pack_queries<<<dim3(div_up((long long)p.kp_cap * 4, 256), frames), 256, 0, st>>>(b.ws.desc64, p.kp_cap, b.ws.kp_count,
+                                                                                          b.q_off, b.q64);
+        DUNK_KERNEL_CHECK(ctx);
+    }
     // the matcher grid depends on the total query count: one 4-byte read back (the only host sync)
     int total_q = 0;
     DUNK_CUDA(cudaMemcpyAsync(h_total_q ? h_total_q : &total_q, b.q_off + frames, 4, cudaMemcpyDeviceToHost, st));
@@ -201,12 +207,21 @@ static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const Pipel
     } else if (total_q > 0) {
         DUNK_CUDA(cudaMemsetAsync(b.top2, 0xFF, (size_t)total_q * 16, st));
     }
-    k_frame_pairs<<<frames, 1024, 0, st>>>(b.top2, b.ws.kp_count, b.q_off, ratio, b.ws.kps, p.kp_cap, db->kps, 0, b.src, b.dst,
-                                           b.matches, b.n_pairs);
-    DUNK_KERNEL_CHECK(ctx);
-    if ((rc = launch_find_homography(ctx, st, b.src, b.dst, b.q_off, b.n_pairs, frames, thr, b.H, b.mask, b.info))) return rc;
-    k_pack_results<<<div_up(frames, 128), 128, 0, st>>>(b.H, b.info, b.n_pairs, b.ws.kp_count, frames, b.results);
-    DUNK_KERNEL_CHECK(ctx);
+    {
+        ProfScope ps(ctx, st, "pipe.frame_pairs", 0.0);
+        k_frame_pairs<<<frames, 1024, 0, st>>>(b.top2, b.ws.kp_count, b.q_off, ratio, b.ws.kps, p.kp_cap, db->kps, 0, b.src, b.dst,
+                                               b.matches, b.n_pairs);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, st, "ransac.find_homography", 0.0);
+        if ((rc = launch_find_homography(ctx, st, b.src, b.dst, b.q_off, b.n_pairs, frames, thr, b.H, b.mask, b.info))) return rc;
+    }
+    {
+        ProfScope ps(ctx, st, "pipe.pack_results", 0.0);
+        k_pack_results<<<div_up(frames, 128), 128, 0, st>>>(b.H, b.info, b.n_pairs, b.ws.kp_count, frames, b.results);
+        DUNK_KERNEL_CHECK(ctx);
+    }
     return DUNK_OK;
 }
 

@@ -222,6 +222,12 @@ int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int ro
                          const int32_t* image_ids, int max_points, int* counts);
 
 /* ---- roofline denominators measured on the box ---------------------------------------- */
+/* per-kernel-class device times: between begin and end every launch site brackets its kernels
+ * with CUDA events on the launching stream.  end() returns the number of classes n and fills
+ * names ("a;b;...;"), ms / launches / alg (algorithmic bytes, or pairs for the matcher) [n]. */
+int dunk_profile_begin(dunk_ctx* ctx);
+int dunk_profile_end(dunk_ctx* ctx, char* names, int names_cap, double* ms, int* launches,
+                     double* alg, int cap);
 /* POPC-pipe peak in 1e12 popc/s (best of 4 timed launches of `iters` x 32 popc per thread) */
 int dunk_microbench_popc(dunk_ctx* ctx, int iters, double* tpopc_per_s);
 

@@ -1,5 +1,6 @@
 """Synthetic imagery for benchmarks and tests: multi-scale smoothed noise tiles and
-known-homography warps.  numpy only — input generation, not part of the measured path."""
+known-homography warps.  Input generation for bench.py / tests only (not the product; may use
+cv2.resize for speed when it is importable)."""
 from __future__ import annotations
 
 import numpy as np
@@ -9,6 +10,11 @@ H_CONFIG1 = np.array([[0.98, -0.12, 60.0], [0.10, 1.03, -40.0], [1e-5, -2e-5, 1.
 
 
 def _upsample_bilinear(a: np.ndarray, h: int, w: int) -> np.ndarray:
+    try:   # much faster for multi-megapixel scenes; input generation only
+        import cv2 as _cv
+        return _cv.resize(a, (w, h), interpolation=_cv.INTER_LINEAR)
+    except Exception:
+        pass
     ys = np.linspace(0, a.shape[0] - 1, h)
     xs = np.linspace(0, a.shape[1] - 1, w)
     y0 = np.clip(np.floor(ys).astype(int), 0, a.shape[0] - 2)

@@ -14,7 +14,8 @@ G = np.load(os.path.join(os.path.dirname(__file__), "golden", "akaze_golden.npz"
 
 def test_config1_small(dunk, ctx):
     """a tile vs itself warped by a known homography: extract both, 2-NN match, RANSAC."""
-    fe, hg, fdb, synth = dunk.feature_extraction, dunk.homographier, dunk.feature_database, dunk.synth
+    import synthdata as synth
+    fe, hg, fdb = dunk.feature_extraction, dunk.homographier, dunk.feature_database
     ref = G["b_img"]                                   # 512 x 512
     Ht = np.array([[0.99, -0.06, 20.0], [0.05, 1.02, -14.0], [1e-5, -2e-5, 1.0]])
     qry = synth.warp_perspective(ref, Ht, 512, 512)
@@ -49,7 +50,8 @@ def test_config1_small(dunk, ctx):
 
 
 def test_batch_registration_and_tile_offsets(dunk, ctx):
-    fdb, synth = dunk.feature_database, dunk.synth
+    import synthdata as synth
+    fdb = dunk.feature_database
     scene = synth.synth_image(512, 768, seed=3)
     tiles = np.stack([scene[:, :384], scene[:, 384:]])           # two 512 x 384 tiles
     db = fdb.DescriptorDatabase(ctx, capacity=50000)
