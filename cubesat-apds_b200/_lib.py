@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdunk_b200.so")
+LIB_PATH = os.environ.get("DUNK_B200_LIB") or os.path.join(_HERE, "libdunk_b200.so")   # env: kernel-variant A/B runs
 
 # status codes (include/dunk_b200.h)
 OK = 0

@@ -16,8 +16,9 @@ namespace dunk {
 
 namespace {
 
-constexpr int kTileRows = 128;           // DB rows per smem stage (8 KB)
-constexpr int kStages = 4;
+constexpr int kTileRows = 64;            // DB rows per smem stage (4 KB), one ring per warp
+constexpr int kStages = 3;
+constexpr int kWarpsPerCta = 8;
 constexpr int kQT = 4;                   // queries per thread
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
@@ -79,29 +80,73 @@ __device__ __forceinline__ void top2_insert_lex(uint32_t d, uint32_t gi, uint32_
     }
 }
 
-// 16 x (XOR, POPC) + adds: the algorithmic unit of the matcher roofline
-__device__ __forceinline__ uint32_t hamming512(const uint32_t (&q)[16], const uint4& a,
-                                               const uint4& b, const uint4& c, const uint4& d) {
-    uint32_t s0 = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w);
-    uint32_t s1 = __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
-    uint32_t s2 = __popc(q[8] ^ c.x) + __popc(q[9] ^ c.y) + __popc(q[10] ^ c.z) + __popc(q[11] ^ c.w);
-    uint32_t s3 = __popc(q[12] ^ d.x) + __popc(q[13] ^ d.y) + __popc(q[14] ^ d.z) + __popc(q[15] ^ d.w);
-    return (s0 + s1) + (s2 + s3);
+// carry-save adder on 32 bit lanes: (a, b, c) -> sum (weight 1) and carry (weight 2); 2 LOP3
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a ^ b));
 }
 
+// Hamming distance of two 512-bit rows.  The algorithmic unit of the matcher roofline is
+// 16 x (XOR, POPC); POPC issues at 16 lanes/clk/SM against 64 for LOP3, so kCsa
+// carry-save adders (Harley-Seal style) first compress the 16 XOR words to 16 - kCsa weighted
+// words: the POPC pipe and the ALU pipe then carry about the same load.
+#ifndef DUNK_MATCH_CSA
+#define DUNK_MATCH_CSA 7
+#endif
+__device__ __forceinline__ uint32_t hamming512(const uint32_t (&q)[16], const uint4& a,
+                                               const uint4& b, const uint4& c, const uint4& d) {
+    uint32_t x[16];
+    x[0] = q[0] ^ a.x; x[1] = q[1] ^ a.y; x[2] = q[2] ^ a.z; x[3] = q[3] ^ a.w;
+    x[4] = q[4] ^ b.x; x[5] = q[5] ^ b.y; x[6] = q[6] ^ b.z; x[7] = q[7] ^ b.w;
+    x[8] = q[8] ^ c.x; x[9] = q[9] ^ c.y; x[10] = q[10] ^ c.z; x[11] = q[11] ^ c.w;
+    x[12] = q[12] ^ d.x; x[13] = q[13] ^ d.y; x[14] = q[14] ^ d.z; x[15] = q[15] ^ d.w;
+#if DUNK_MATCH_CSA == 0
+    uint32_t s0 = __popc(x[0]) + __popc(x[1]) + __popc(x[2]) + __popc(x[3]);
+    uint32_t s1 = __popc(x[4]) + __popc(x[5]) + __popc(x[6]) + __popc(x[7]);
+    uint32_t s2 = __popc(x[8]) + __popc(x[9]) + __popc(x[10]) + __popc(x[11]);
+    uint32_t s3 = __popc(x[12]) + __popc(x[13]) + __popc(x[14]) + __popc(x[15]);
+    return (s0 + s1) + (s2 + s3);
+#else
+    // level 1: five CSAs over x0..x14 (x15 left over)
+    uint32_t s[5], t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) csa(x[3 * i], x[3 * i + 1], x[3 * i + 2], s[i], t[i]);
+    // level 2: one CSA on the weight-1 sums, one on the weight-2 carries
+    uint32_t s5, t5, u0, f0;
+    csa(s[0], s[1], s[2], s5, t5);
+    csa(t[0], t[1], t[2], u0, f0);
+#if DUNK_MATCH_CSA >= 8
+    uint32_t s6, t6;
+    csa(s5, s[3], s[4], s6, t6);
+    const uint32_t w1 = __popc(s6) + __popc(x[15]);
+    const uint32_t w2 = (__popc(u0) + __popc(t[3])) + (__popc(t[4]) + __popc(t5)) + __popc(t6);
+#else
+    const uint32_t w1 = (__popc(s5) + __popc(s[3])) + (__popc(s[4]) + __popc(x[15]));
+    const uint32_t w2 = (__popc(u0) + __popc(t[3])) + (__popc(t[4]) + __popc(t5));
+#endif
+    return w1 + 2u * w2 + 4u * __popc(f0);
+#endif
+}
+
+// One warp = one work item (query group of 32*QT queries, DB slab): the warp streams its slab through
+// its own 3-stage smem ring (lane 0 issues the bulk copies, all lanes wait on the mbarrier) and keeps
+// QT register-resident top-2 lists per lane.  Warps never synchronise with each other, so every
+// CTA has 8 busy warps (2 per SM sub-partition) whatever the query count is.
 template <int QT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __restrict__ q, int nq,
-                    int tiles_per_cta, uint32_t index_base, uint4* __restrict__ partial) {
+                    int n_qgroups, int n_slabs, int tiles_per_slab, uint32_t index_base,
+                    uint4* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4* tiles = reinterpret_cast<uint4*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kTileRows * 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (item >= (long long)n_qgroups * n_slabs) return;
+    const int qg = (int)(item % n_qgroups), slab = (int)(item / n_qgroups);
+    uint4* tiles = reinterpret_cast<uint4*>(smem_raw) + (size_t)warp * kStages * kTileRows * 4;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarpsPerCta * kStages * kTileRows * 64) +
+                     warp * kStages;
 
-    const int tid = threadIdx.x;
-    const int q0 = (blockIdx.y * blockDim.x + tid) * QT;  // first query of this thread
-    // a warp whose first lane has no query has no query at all (queries are thread-contiguous)
-    const bool warp_active = ((blockIdx.y * blockDim.x + (tid & ~31)) * QT) < nq;
-
+    const int q0 = (qg * 32 + lane) * QT;   // first query of this lane (queries are lane-contiguous)
     uint32_t qr[QT][16];
     uint32_t d1[QT], i1[QT], d2[QT], i2[QT];
 #pragma unroll
@@ -122,15 +167,15 @@ hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __re
     }
 
     const int total_tiles = (int)((nt + kTileRows - 1) / kTileRows);
-    const int t0 = blockIdx.x * tiles_per_cta;
-    const int ntile = max(0, min(t0 + tiles_per_cta, total_tiles) - t0);
+    const int t0 = slab * tiles_per_slab;
+    const int ntile = max(0, min(t0 + tiles_per_slab, total_tiles) - t0);
 
-    if (tid == 0) {
+    if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncwarp();
 
     auto issue = [&](int k) {
         const int st = k % kStages;
@@ -139,7 +184,7 @@ hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __re
         mbar_expect_tx(&full[st], rows * 64u);
         bulk_g2s(tiles + (size_t)st * kTileRows * 4, db + (size_t)row0 * 4, rows * 64u, &full[st]);
     };
-    if (tid == 0)
+    if (lane == 0)
         for (int k = 0; k < min(kStages, ntile); ++k) issue(k);
 
     for (int k = 0; k < ntile; ++k) {
@@ -147,27 +192,25 @@ hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __re
         mbar_wait(&full[st], (uint32_t)(k / kStages) & 1u);
         const uint32_t row0 = (uint32_t)(t0 + k) * kTileRows;
         const int rows = (int)min((uint32_t)kTileRows, nt - row0);
-        if (warp_active) {
-            const uint4* tp = tiles + (size_t)st * kTileRows * 4;
-            const uint32_t g0 = index_base + row0;
+        const uint4* tp = tiles + (size_t)st * kTileRows * 4;
+        const uint32_t g0 = index_base + row0;
 #pragma unroll 2
-            for (int r = 0; r < rows; ++r) {
-                const uint4 a = tp[r * 4 + 0], b = tp[r * 4 + 1], c = tp[r * 4 + 2], d = tp[r * 4 + 3];
+        for (int r = 0; r < rows; ++r) {
+            const uint4 a = tp[r * 4 + 0], b = tp[r * 4 + 1], c = tp[r * 4 + 2], d = tp[r * 4 + 3];
 #pragma unroll
-                for (int s = 0; s < QT; ++s) {
-                    const uint32_t dist = hamming512(qr[s], a, b, c, d);
-                    top2_insert_stream(dist, g0 + r, d1[s], i1[s], d2[s], i2[s]);
-                }
+            for (int s = 0; s < QT; ++s) {
+                const uint32_t dist = hamming512(qr[s], a, b, c, d);
+                top2_insert_stream(dist, g0 + r, d1[s], i1[s], d2[s], i2[s]);
             }
         }
-        __syncthreads();  // everyone is done with stage st before it is refilled
-        if (tid == 0 && k + kStages < ntile) issue(k + kStages);
+        __syncwarp();  // every lane is done with stage st before it is refilled
+        if (lane == 0 && k + kStages < ntile) issue(k + kStages);
     }
 
 #pragma unroll
     for (int s = 0; s < QT; ++s)
         if (q0 + s < nq)
-            partial[(size_t)blockIdx.x * nq + (q0 + s)] = make_uint4(d1[s], i1[s], d2[s], i2[s]);
+            partial[(size_t)slab * nq + (q0 + s)] = make_uint4(d1[s], i1[s], d2[s], i2[s]);
 }
 
 // lexicographic (distance, index) merge of n_parts top-2 arrays (part-major)
@@ -295,29 +338,24 @@ __global__ void fill_random_rows_kernel(uint2* __restrict__ dst, long long n, un
 
 KnnPlan plan_knn2(dunk_ctx* ctx, int nq, uint32_t nt) {
     KnnPlan p;
-    const int warps = div_up(nq, 32 * kQT);
-    // warps per CTA in 4..8 minimising idle (padding) warps; ties -> larger CTA
-    int best_w = 8, best_pad = 1 << 30;
-    for (int w = 8; w >= 4; --w) {
-        const int pad = div_up(warps, w) * w - warps;
-        if (pad < best_pad) best_pad = pad, best_w = w;
-    }
-    if (warps < 4) best_w = warps;
-    p.threads = best_w * 32;
-    p.gy = div_up(warps, best_w);
-    p.smem = (size_t)kStages * kTileRows * 64 + kStages * sizeof(uint64_t);
+    p.threads = kWarpsPerCta * 32;
+    p.gy = div_up(nq, 32 * kQT);          // query groups (one warp each)
+    p.smem = (size_t)kWarpsPerCta * kStages * kTileRows * 64 + kWarpsPerCta * kStages * sizeof(uint64_t);
     const int total_tiles = div_up(nt, kTileRows);
-    int occ = 2;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<kQT>, p.threads, p.smem);
-    if (occ < 1) occ = 1;
-    // two balanced waves of equal-sized slabs
-    int gx = (ctx->sm_count * occ * 2) / p.gy;
-    if (gx < 1) gx = 1;
-    if (gx > total_tiles) gx = total_tiles;
-    if (gx < 1) gx = 1;
-    p.tiles_per_cta = div_up(total_tiles, gx);
+    static int occ = 0;
+    if (occ == 0) {
+        cudaFuncSetAttribute(hamming_top2_kernel<kQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<kQT>, p.threads, p.smem);
+        if (occ < 1) occ = 1;
+    }
+    // equal-sized slabs so that (query groups x slabs) fills ~2 waves of warp slots
+    const long long slots = (long long)ctx->sm_count * occ * kWarpsPerCta;
+    long long slabs = (slots * 2 + p.gy - 1) / p.gy;
+    if (slabs > total_tiles) slabs = total_tiles;
+    if (slabs < 1) slabs = 1;
+    p.tiles_per_cta = div_up(total_tiles, slabs);
     if (p.tiles_per_cta < 1) p.tiles_per_cta = 1;
-    p.gx = div_up(total_tiles, p.tiles_per_cta);
+    p.gx = div_up(total_tiles, p.tiles_per_cta);   // slabs
     if (p.gx < 1) p.gx = 1;
     return p;
 }
@@ -356,18 +394,13 @@ int launch_unpad_rows(dunk_ctx* ctx, cudaStream_t st, const uint4* src64, int64_
 int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, const uint4* q64,
                 int nq, uint32_t index_base, uint4* partial, uint4* top2_out, const KnnPlan& p) {
     if (nq <= 0) return DUNK_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(hamming_top2_kernel<kQT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)p.smem);
-        attr_set = true;
-    }
     // with a single slab the kernel's partial IS the result
     uint4* dst = (p.gx == 1) ? top2_out : partial;
     {
         ProfScope ps(ctx, st, "match.hamming_top2", (double)nq * (double)nt);   // pairs
-        hamming_top2_kernel<kQT><<<dim3(p.gx, p.gy), p.threads, p.smem, st>>>(
-            db64, nt, q64, nq, p.tiles_per_cta, index_base, dst);
+        const long long items = (long long)p.gx * p.gy;
+        hamming_top2_kernel<kQT><<<(unsigned)div_up(items, kWarpsPerCta), p.threads, p.smem, st>>>(
+            db64, nt, q64, nq, p.gy, p.gx, p.tiles_per_cta, index_base, dst);
         DUNK_LAUNCH_CHECK(ctx);
     }
     if (p.gx > 1) return launch_top2_merge(ctx, st, partial, p.gx, nq, top2_out);
