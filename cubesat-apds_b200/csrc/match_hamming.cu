@@ -82,8 +82,9 @@ __device__ __forceinline__ void top2_insert_lex(uint32_t d, uint32_t gi, uint32_
 
 // carry-save adder on 32 bit lanes: (a, b, c) -> sum (weight 1) and carry (weight 2); 2 LOP3
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
-    sum = a ^ b ^ c;
-    carry = (a & b) | (c & (a ^ b));
+    // one LOP3 each: 0x96 = a ^ b ^ c, 0xE8 = majority(a, b, c)
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));
 }
 
 // Hamming distance of two 512-bit rows.  The algorithmic unit of the matcher roofline is
@@ -197,10 +198,18 @@ hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __re
 #pragma unroll 2
         for (int r = 0; r < rows; ++r) {
             const uint4 a = tp[r * 4 + 0], b = tp[r * 4 + 1], c = tp[r * 4 + 2], d = tp[r * 4 + 3];
+            uint32_t dist[QT];
+            bool hit = false;
 #pragma unroll
             for (int s = 0; s < QT; ++s) {
-                const uint32_t dist = hamming512(qr[s], a, b, c, d);
-                top2_insert_stream(dist, g0 + r, d1[s], i1[s], d2[s], i2[s]);
+                dist[s] = hamming512(qr[s], a, b, c, d);
+                hit |= dist[s] < d2[s];
+            }
+            // a row improves some lane's top-2 with probability ~256/rows_seen: keep the common
+            // path to QT compares + one vote + one warp-uniform branch
+            if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+                for (int s = 0; s < QT; ++s) top2_insert_stream(dist[s], g0 + r, d1[s], i1[s], d2[s], i2[s]);
             }
         }
         __syncwarp();  // every lane is done with stage st before it is refilled
