@@ -96,7 +96,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------ data
 def build_scene(size, seed=11):
     import synthdata as synth
-    return synth.synth_image(size, size, seed=seed)
+    return synth.synth_scene(size, seed=seed)
 
 
 def scene_tiles(scene, tile=FRAME, lods=4):

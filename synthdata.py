@@ -9,37 +9,40 @@ import numpy as np
 H_CONFIG1 = np.array([[0.98, -0.12, 60.0], [0.10, 1.03, -40.0], [1e-5, -2e-5, 1.0]])
 
 
-def _upsample_bilinear(a: np.ndarray, h: int, w: int) -> np.ndarray:
-    try:   # much faster for multi-megapixel scenes; input generation only
+def _upsample(a: np.ndarray, h: int, w: int) -> np.ndarray:
+    """bicubic up-sampling of a coarse noise field to (h, w)"""
+    try:   # SURVEY 8d recipe uses cv2.resize(INTER_CUBIC); much faster for multi-megapixel scenes
         import cv2 as _cv
-        return _cv.resize(a, (w, h), interpolation=_cv.INTER_LINEAR)
+        return _cv.resize(a, (w, h), interpolation=_cv.INTER_CUBIC)
     except Exception:
-        pass
-    ys = np.linspace(0, a.shape[0] - 1, h)
-    xs = np.linspace(0, a.shape[1] - 1, w)
-    y0 = np.clip(np.floor(ys).astype(int), 0, a.shape[0] - 2)
-    x0 = np.clip(np.floor(xs).astype(int), 0, a.shape[1] - 2)
-    fy = (ys - y0)[:, None]
-    fx = (xs - x0)[None, :]
-    a00 = a[y0][:, x0]; a01 = a[y0][:, x0 + 1]; a10 = a[y0 + 1][:, x0]; a11 = a[y0 + 1][:, x0 + 1]
-    return (a00 * (1 - fx) + a01 * fx) * (1 - fy) + (a10 * (1 - fx) + a11 * fx) * fy
+        from scipy import ndimage
+        return ndimage.zoom(a, (h / a.shape[0], w / a.shape[1]), order=3, mode="nearest", grid_mode=True)[:h, :w]
 
 
 def synth_image(h: int, w: int | None = None, seed: int = 0) -> np.ndarray:
-    """u8 image: sum over s in {1,2,4,8,16,32} of upsampled N(0,1) noise * sqrt(s), box-smoothed and
-    min-max normalised (same recipe as SURVEY 8d's `synth`, with numpy interpolation)."""
+    """SURVEY 8d `synth`: sum over s in {1,2,4,8,16,32} of resize(N(0,1)[(n/s+1)^2], cubic) * sqrt(s),
+    min-max normalised to u8 (~2-3 k AKAZE keypoints per 1024^2)."""
     w = w or h
     rng = np.random.default_rng(seed)
-    acc = np.zeros((h, w), np.float32)
+    acc = np.zeros((h, w), np.float64)
     for s in (1, 2, 4, 8, 16, 32):
-        n = rng.standard_normal((h // s + 2, w // s + 2)).astype(np.float32)
-        acc += _upsample_bilinear(n, h, w).astype(np.float32) * np.float32(np.sqrt(s))
-    # light 3x3 smoothing so that single-pixel noise does not dominate
-    p = np.pad(acc, 1, mode="edge")
-    acc = (p[:-2, :-2] + p[:-2, 1:-1] + p[:-2, 2:] + p[1:-1, :-2] + p[1:-1, 1:-1] + p[1:-1, 2:] +
-           p[2:, :-2] + p[2:, 1:-1] + p[2:, 2:]) / 9.0
+        n = rng.standard_normal((h // s + 1, w // s + 1))
+        acc += _upsample(n, h, w) * np.sqrt(s)
     acc = (acc - acc.min()) / (acc.max() - acc.min())
     return (acc * 255).astype(np.uint8)
+
+
+def synth_scene(size: int, seed: int = 11) -> np.ndarray:
+    """Large scene for configs 4/5: the same multi-scale noise field as `synth_image`, but mapped to u8
+    with a fixed contrast (mean +- 4.6 sigma -> 0..255, the range/sigma ratio a 1024^2 `synth_image` has)
+    instead of a global min-max, so that a 1024^2 window carries the keypoint density of a tile."""
+    rng = np.random.default_rng(seed)
+    acc = np.zeros((size, size), np.float32)
+    for s in (1, 2, 4, 8, 16, 32):
+        n = rng.standard_normal((size // s + 1, size // s + 1)).astype(np.float32)
+        acc += _upsample(n, size, size).astype(np.float32) * np.float32(np.sqrt(s))
+    acc = (acc - acc.mean()) / acc.std()
+    return np.clip(np.rint(127.5 + acc * (255.0 / 9.2)), 0, 255).astype(np.uint8)
 
 
 def warp_perspective(img: np.ndarray, H: np.ndarray, out_h: int, out_w: int, border: int = 1) -> np.ndarray:
