@@ -43,6 +43,13 @@ TOP2_DTYPE = np.dtype([("d1", "<u4"), ("i1", "<u4"), ("d2", "<u4"), ("i2", "<u4"
 assert REGISTRATION_DTYPE.itemsize == 96 and KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16
 
 
+class PipelineView(C.Structure):
+    """DunkPipelineView (include/dunk_b200.h)"""
+    _fields_ = [("query64_dev", C.c_void_p), ("query_offsets_dev", C.c_void_p), ("keypoints_dev", C.c_void_p),
+                ("keypoint_counts_dev", C.c_void_p), ("top2_dev", C.c_void_p), ("total_queries", C.c_int32),
+                ("keypoint_capacity", C.c_int32), ("query_capacity", C.c_int64)]
+
+
 class DunkError(RuntimeError):
     """Mirror of `opencv::Error { code, message }` (feature_extraction/src/lib.rs:61)."""
 
@@ -98,6 +105,12 @@ SIGNATURES = {
     "dunk_register_frames": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _f, _d, _i, _vp]),
     "dunk_register_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
     "dunk_register_frames_dev": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, C.c_size_t, _f, _d, _i, _vp, C.c_size_t, _vp]),
+    "dunk_pipeline_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
+    "dunk_pipeline_extract_dev": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, C.c_size_t, _i, _vp, C.c_size_t, _vp]),
+    "dunk_pipeline_finish_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i64, _i, _vp, _u32, _f, _d, _vp, C.c_size_t, _vp]),
+    "dunk_memcpy_dev": (_i, [_vp, _i, _vp, _vp, C.c_size_t]),
+    "dunk_db_keypoints_dev": (_vp, [_vp]),
+    "dunk_db_descriptors_dev": (_vp, [_vp]),
     "dunk_db_append_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _vp, _vp, _vp, _vp, _i, _vp]),
     "dunk_find_homography": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _pi]),
     "dunk_find_homography_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),

@@ -123,19 +123,21 @@ struct FrameLists {
     const int* row_base;    // [n_levels + 1]
 };
 
-// visit candidates of `level` inside the (2r+1)^2 window around (cx, cy) in window scan order
+// visit candidates of `level` inside the half-open window [c-r, c+r)^2 around (cx, cy) in window scan order
 // (rows ascending, x ascending) that lie within L2 distance r; fn(idx) returns true to stop
 template <class Fn>
 __device__ __forceinline__ void visit_window(const FrameLists& fl, int level, int cx, int cy, int r, Fn fn) {
     const LevelDev& e = fl.lv.lv[level];
-    const int y0 = max(cy - r, 0), y1 = min(cy + r, e.h - 1);
+    // OpenCV scans the HALF-OPEN window [c - r, c + r) in both axes (a neighbour at exactly +r along
+    // an axis is not seen), then tests dx^2 + dy^2 <= r^2
+    const int y0 = max(cy - r, 0), y1 = min(cy + r - 1, e.h - 1);
     const int rb = fl.row_base[level];
     for (int y = y0; y <= y1; ++y) {
         const int a = fl.row_start[rb + y], b = fl.row_start[rb + y + 1];
         for (int i = a; i < b; ++i) {
             const int x = fl.cand[i].x;
             if (x < cx - r) continue;
-            if (x > cx + r) break;
+            if (x >= cx + r) break;
             const int dx = x - cx, dy = y - cy;
             if (dx * dx + dy * dy <= r * r)
                 if (fn(i)) return;

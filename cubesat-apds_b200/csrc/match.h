@@ -37,6 +37,8 @@ int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, 
                 int nq, uint32_t index_base, uint4* partial, uint4* top2_out, const KnnPlan& plan);
 int launch_top2_merge(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_parts, int nq,
                       uint4* out);
+int launch_top2_merge_strided(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_parts, long long part_stride,
+                              int nq, uint4* out);
 int launch_top2_ratio(dunk_ctx* ctx, cudaStream_t st, const uint4* top2, int nq, float ratio,
                       DunkDMatch* out, int* count);
 // cross-check (BFMatcher crossCheck=true): mutual nearest neighbours from both 1-NN passes

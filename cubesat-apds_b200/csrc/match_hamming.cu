@@ -223,13 +223,13 @@ hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __re
 }
 
 // lexicographic (distance, index) merge of n_parts top-2 arrays (part-major)
-__global__ void top2_merge_kernel(const uint4* __restrict__ parts, int n_parts, int nq,
+__global__ void top2_merge_kernel(const uint4* __restrict__ parts, int n_parts, long long part_stride, int nq,
                                   uint4* __restrict__ out) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     uint32_t d1 = kEmpty, i1 = kEmpty, d2 = kEmpty, i2 = kEmpty;
     for (int p = 0; p < n_parts; ++p) {
-        const uint4 v = parts[(size_t)p * nq + qi];
+        const uint4 v = parts[(size_t)p * part_stride + qi];
         top2_insert_lex(v.x, v.y, d1, i1, d2, i2);
         top2_insert_lex(v.z, v.w, d1, i1, d2, i2);
     }
@@ -420,7 +420,15 @@ int launch_top2_merge(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_
                       uint4* out) {
     if (nq <= 0) return DUNK_OK;
     ProfScope ps(ctx, st, "match.top2_merge", (double)nq * n_parts * 16);
-    top2_merge_kernel<<<div_up(nq, 128), 128, 0, st>>>(parts, n_parts, nq, out);
+    top2_merge_kernel<<<div_up(nq, 128), 128, 0, st>>>(parts, n_parts, (long long)nq, nq, out);
+    DUNK_LAUNCH_CHECK(ctx);
+    return DUNK_OK;
+}
+
+int launch_top2_merge_strided(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_parts, long long part_stride,
+                              int nq, uint4* out) {
+    if (nq <= 0) return DUNK_OK;
+    top2_merge_kernel<<<div_up(nq, 128), 128, 0, st>>>(parts, n_parts, part_stride, nq, out);
     DUNK_LAUNCH_CHECK(ctx);
     return DUNK_OK;
 }

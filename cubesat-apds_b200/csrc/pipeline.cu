@@ -175,44 +175,35 @@ static void carve_pipeline(void* base, const PipelinePlan& p, PipelineBuffers* b
     b->results = (DunkRegistration*)take((size_t)p.frames * sizeof(DunkRegistration));
 }
 
-// all three stages for `frames` device-resident images; results (device) in b.results
-static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const PipelinePlan& p, const PipelineBuffers& b,
-                        const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
-                        float ratio, float thr, int max_points, int* h_total_q /*pinned or NULL*/) {
+// stage 1 for `frames` device-resident images + packing of every frame's descriptors into one
+// query array; returns the total query count (one 4-byte read back: the matcher grid depends on it)
+static int pipeline_extract(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& p, const PipelineBuffers& b,
+                            const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
+                            int max_points, int* total_q) {
     int rc = akaze_run(ctx, st, p.lt, b.ws, images_dev, frame_stride, row_stride, channels, frames, max_points);
     if (rc) return rc;
-    {
-        ProfScope ps(ctx, st, "pipe.frame_offsets", 0.0);
-        k_frame_offsets<<<1, 1024, 0, st>>>(b.ws.kp_count, frames, b.q_off);
-        DUNK_KERNEL_CHECK(ctx);
-    }
-    {
-        ProfScope ps(ctx, st, "pipe.pack_queries", 0.0);
-        k_pack_queries<<<dim3(div_up((long long)p.kp_cap * 4, 256), frames), 256, 0, st>>>(b.ws.desc64, p.kp_cap, b.ws.kp_count,
-                                                                                          b.q_off, b.q64);
-        DUNK_KERNEL_CHECK(ctx);
-    }
-    // the matcher grid depends on the total query count: one 4-byte read back (the only host sync)
-    int total_q = 0;
-    DUNK_CUDA(cudaMemcpyAsync(h_total_q ? h_total_q : &total_q, b.q_off + frames, 4, cudaMemcpyDeviceToHost, st));
+    k_frame_offsets<<<1, 1024, 0, st>>>(b.ws.kp_count, frames, b.q_off);
+    DUNK_KERNEL_CHECK(ctx);
+    k_pack_queries<<<dim3(div_up((long long)p.kp_cap * 4, 256), frames), 256, 0, st>>>(b.ws.desc64, p.kp_cap, b.ws.kp_count,
+                                                                                      b.q_off, b.q64);
+    DUNK_KERNEL_CHECK(ctx);
+    DUNK_CUDA(cudaMemcpyAsync(total_q, b.q_off + frames, 4, cudaMemcpyDeviceToHost, st));
     DUNK_CUDA(cudaStreamSynchronize(st));
-    if (h_total_q) total_q = *h_total_q;
-    if (total_q > 0 && db->size >= 2) {
-        const KnnPlan kp = plan_knn2(ctx, total_q, (uint32_t)db->size);
-        if ((size_t)kp.gx * total_q * 16 > p.partial_bytes) {
-            set_error("pipeline: matcher partial buffer too small");
-            return DUNK_ERR_NO_MEM;
-        }
-        if ((rc = launch_knn2(ctx, st, db->desc64, (uint32_t)db->size, b.q64, total_q, 0, b.partial, b.top2, kp))) return rc;
-    } else if (total_q > 0) {
-        DUNK_CUDA(cudaMemsetAsync(b.top2, 0xFF, (size_t)total_q * 16, st));
-    }
+    return DUNK_OK;
+}
+
+// stage 2 tail + stage 3: per-frame ratio test -> point pairs -> RANSAC homography -> result records.
+// top2: merged top-2 per query; db_kps: keypoints addressed by (train index - index_base)
+static int pipeline_finish(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& p, const PipelineBuffers& b,
+                           const uint4* top2, const DunkKeyPoint* db_kps, uint32_t index_base, int frames, float ratio,
+                           float thr) {
     {
         ProfScope ps(ctx, st, "pipe.frame_pairs", 0.0);
-        k_frame_pairs<<<frames, 1024, 0, st>>>(b.top2, b.ws.kp_count, b.q_off, ratio, b.ws.kps, p.kp_cap, db->kps, 0, b.src, b.dst,
-                                               b.matches, b.n_pairs);
+        k_frame_pairs<<<frames, 1024, 0, st>>>(top2, b.ws.kp_count, b.q_off, ratio, b.ws.kps, p.kp_cap, db_kps, index_base, b.src,
+                                               b.dst, b.matches, b.n_pairs);
         DUNK_KERNEL_CHECK(ctx);
     }
+    int rc;
     {
         ProfScope ps(ctx, st, "ransac.find_homography", 0.0);
         if ((rc = launch_find_homography(ctx, st, b.src, b.dst, b.q_off, b.n_pairs, frames, thr, b.H, b.mask, b.info))) return rc;
@@ -223,6 +214,26 @@ static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const Pipel
         DUNK_KERNEL_CHECK(ctx);
     }
     return DUNK_OK;
+}
+
+// all three stages for `frames` device-resident images against one shard; results (device) in b.results
+static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const PipelinePlan& p, const PipelineBuffers& b,
+                        const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
+                        float ratio, float thr, int max_points, int* h_total_q /*unused*/) {
+    int total_q = 0;
+    int rc = pipeline_extract(ctx, st, p, b, images_dev, frame_stride, row_stride, channels, frames, max_points, &total_q);
+    if (rc) return rc;
+    if (total_q > 0 && db->size >= 2) {
+        const KnnPlan kp = plan_knn2(ctx, total_q, (uint32_t)db->size);
+        if ((size_t)kp.gx * total_q * 16 > p.partial_bytes) {
+            set_error("pipeline: matcher partial buffer too small");
+            return DUNK_ERR_NO_MEM;
+        }
+        if ((rc = launch_knn2(ctx, st, db->desc64, (uint32_t)db->size, b.q64, total_q, 0, b.partial, b.top2, kp))) return rc;
+    } else if (total_q > 0) {
+        DUNK_CUDA(cudaMemsetAsync(b.top2, 0xFF, (size_t)total_q * 16, st));
+    }
+    return pipeline_finish(ctx, st, p, b, b.top2, db->kps, 0, frames, ratio, thr);
 }
 
 }  // namespace dunk
@@ -301,6 +312,87 @@ int dunk_register_frames(dunk_db* db, const uint8_t* images, int n_frames, int r
     }
     return DUNK_OK;
 }
+
+/* ---- sharded pipeline phases: extract on the frame owner, match on every shard,
+ * merge + RANSAC on the frame owner.  The exchange between the phases is the caller's (NCCL). ---- */
+size_t dunk_pipeline_workspace_bytes(dunk_ctx* ctx, int n_frames, int rows, int cols) {
+    if (!ctx || n_frames <= 0) return 0;
+    return plan_pipeline(ctx, rows, cols, n_frames, 1).total_bytes;
+}
+
+int dunk_pipeline_extract_dev(dunk_ctx* ctx, int slot, const void* images_dev, int n_frames, int rows, int cols, int channels,
+                              int row_stride_bytes, size_t frame_stride_bytes, int max_points, void* workspace_dev,
+                              size_t workspace_bytes, DunkPipelineView* view) {
+    DUNK_REQUIRE(ctx && images_dev && workspace_dev && view, DUNK_ERR_BAD_ARG, "dunk_pipeline_extract_dev: NULL argument");
+    DUNK_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), DUNK_ERR_BAD_ARG, "dunk_pipeline_extract_dev: bad slot");
+    int rc = check_frames("dunk_pipeline_extract_dev", n_frames, rows, cols, channels, row_stride_bytes);
+    if (rc) return rc;
+    DUNK_REQUIRE(n_frames > 0, DUNK_ERR_BAD_ARG, "dunk_pipeline_extract_dev: no frames");
+    if (frame_stride_bytes == 0) frame_stride_bytes = (size_t)rows * row_stride_bytes;
+    DUNK_CUDA(cudaSetDevice(ctx->device));
+    const PipelinePlan p = plan_pipeline(ctx, rows, cols, n_frames, 1);
+    DUNK_REQUIRE(workspace_bytes >= p.total_bytes, DUNK_ERR_NO_MEM, "dunk_pipeline_extract_dev: workspace %zu < %zu bytes",
+                 workspace_bytes, p.total_bytes);
+    PipelineBuffers b;
+    carve_pipeline(workspace_dev, p, &b);
+    int total_q = 0;
+    if ((rc = pipeline_extract(ctx, ctx->slots[slot].stream, p, b, (const unsigned char*)images_dev, frame_stride_bytes,
+                               row_stride_bytes, channels, n_frames, max_points <= 0 ? 0 : max_points, &total_q)))
+        return rc;
+    view->query64_dev = b.q64;
+    view->query_offsets_dev = b.q_off;
+    view->keypoints_dev = b.ws.kps;
+    view->keypoint_counts_dev = b.ws.kp_count;
+    view->top2_dev = b.top2;
+    view->total_queries = total_q;
+    view->keypoint_capacity = p.kp_cap;
+    view->query_capacity = (int64_t)n_frames * p.kp_cap;
+    return DUNK_OK;
+}
+
+int dunk_pipeline_finish_dev(dunk_ctx* ctx, int slot, int n_frames, int rows, int cols, const void* parts_dev, int n_parts,
+                             int64_t part_stride_records, int total_queries, const void* db_keypoints_dev,
+                             uint32_t index_base, float ratio, double thr, void* workspace_dev, size_t workspace_bytes,
+                             void* results_dev) {
+    DUNK_REQUIRE(ctx && parts_dev && db_keypoints_dev && workspace_dev && results_dev && n_parts >= 1, DUNK_ERR_BAD_ARG,
+                 "dunk_pipeline_finish_dev: bad argument");
+    DUNK_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), DUNK_ERR_BAD_ARG, "dunk_pipeline_finish_dev: bad slot");
+    DUNK_REQUIRE(n_frames > 0 && n_frames <= 1024 && total_queries >= 0, DUNK_ERR_BAD_ARG, "dunk_pipeline_finish_dev: bad sizes");
+    DUNK_CUDA(cudaSetDevice(ctx->device));
+    const PipelinePlan p = plan_pipeline(ctx, rows, cols, n_frames, 1);
+    DUNK_REQUIRE(workspace_bytes >= p.total_bytes, DUNK_ERR_NO_MEM, "dunk_pipeline_finish_dev: workspace too small");
+    PipelineBuffers b;
+    carve_pipeline(workspace_dev, p, &b);
+    cudaStream_t st = ctx->slots[slot].stream;
+    const uint4* top2 = (const uint4*)parts_dev;
+    int rc;
+    if (total_queries > 0 && (n_parts > 1 || part_stride_records != total_queries)) {
+        // lexicographic (distance, index) merge of the shards' top-2 records; parts are part-major with
+        // a stride, so merge each part row range through the strided view
+        {
+            ProfScope ps(ctx, st, "match.top2_merge", (double)total_queries * n_parts * 16);
+            if ((rc = launch_top2_merge_strided(ctx, st, (const uint4*)parts_dev, n_parts, part_stride_records, total_queries, b.top2)))
+                return rc;
+        }
+        top2 = b.top2;
+    }
+    if ((rc = pipeline_finish(ctx, st, p, b, top2, (const DunkKeyPoint*)db_keypoints_dev, index_base, n_frames, ratio, (float)thr)))
+        return rc;
+    DUNK_CUDA(cudaMemcpyAsync(results_dev, b.results, (size_t)n_frames * sizeof(DunkRegistration), cudaMemcpyDeviceToDevice, st));
+    return DUNK_OK;
+}
+
+int dunk_memcpy_dev(dunk_ctx* ctx, int slot, void* dst_dev, const void* src_dev, size_t nbytes) {
+    DUNK_REQUIRE(ctx && slot >= 0 && slot < (int)ctx->slots.size(), DUNK_ERR_BAD_ARG, "dunk_memcpy_dev: bad ctx / slot");
+    if (nbytes == 0) return DUNK_OK;
+    DUNK_REQUIRE(dst_dev && src_dev, DUNK_ERR_BAD_ARG, "dunk_memcpy_dev: NULL pointer");
+    DUNK_CUDA(cudaSetDevice(ctx->device));
+    DUNK_CUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDeviceToDevice, ctx->slots[slot].stream));
+    return DUNK_OK;
+}
+
+const void* dunk_db_keypoints_dev(dunk_db* db) { return db ? db->kps : nullptr; }
+const void* dunk_db_descriptors_dev(dunk_db* db) { return db ? db->desc64 : nullptr; }
 
 static __global__ void __launch_bounds__(256)
 k_append_rows(const uint4* __restrict__ desc64, const DunkKeyPoint* __restrict__ kps, int kp_cap, const int* __restrict__ counts,

@@ -155,3 +155,51 @@ def merge_top2(ctx: _lib.Context, parts: Sequence[np.ndarray]) -> np.ndarray:
     finally:
         ctx.release_slot(slot)
     return out.cpu().numpy().view(TOP2_DTYPE).copy()
+
+
+def register_frames_sharded_local(ctx: _lib.Context, shards: Sequence["DescriptorDatabase"], frames: np.ndarray,
+                                  ratio: float = 0.8, reproj_threshold: float = 3.0,
+                                  max_points: int = _lib.MAX_POINTS) -> np.ndarray:
+    """The sharded pipeline's three phases with every shard on THIS GPU: phase 1 extract,
+    phase 2 local top-2 against each shard (global row indices = shard bases), phase 3 merge + ratio +
+    RANSAC.  bench.py runs the same phases with one shard per rank and NCCL between them; this
+    single-process form is what the parity test compares with the unsharded `register_frames`."""
+    import torch  # device memory plumbing only
+    lib = _lib.load()
+    a = np.asarray(frames)
+    if a.ndim == 3:
+        a = a[..., None]
+    a = np.ascontiguousarray(a)
+    B, rows, cols, ch = a.shape
+    dev = torch.device("cuda", ctx.device)
+    f_dev = torch.from_numpy(a.reshape(-1)).to(dev)
+    ws_bytes = int(lib.dunk_pipeline_workspace_bytes(ctx.handle, B, rows, cols))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    res = torch.zeros(B * _lib.REGISTRATION_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    # replicated keypoint column of all shards (global row index -> keypoint)
+    sizes = [len(s) for s in shards]
+    bases = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    kps_all = torch.empty(int(bases[-1]) * 28, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize(dev)
+    slot = ctx.reserve_slot()
+    for s, b0, n in zip(shards, bases, sizes):
+        if n:
+            check(lib.dunk_memcpy_dev(ctx.handle, slot, kps_all.data_ptr() + int(b0) * 28,
+                                      lib.dunk_db_keypoints_dev(s.handle), n * 28))
+    try:
+        view = _lib.PipelineView()
+        check(lib.dunk_pipeline_extract_dev(ctx.handle, slot, f_dev.data_ptr(), B, rows, cols, ch, cols * ch,
+                                            rows * cols * ch, int(max_points), ws.data_ptr(), ws_bytes, C.byref(view)))
+        nq = view.total_queries
+        parts = torch.empty(len(shards) * max(nq, 1) * 16, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        for i, s in enumerate(shards):
+            check(lib.dunk_db_knn2_dev(s.handle, slot, view.query64_dev, nq, int(bases[i]),
+                                       parts.data_ptr() + i * max(nq, 1) * 16))
+        check(lib.dunk_pipeline_finish_dev(ctx.handle, slot, B, rows, cols, parts.data_ptr(), len(shards), max(nq, 1), nq,
+                                           kps_all.data_ptr(), 0, float(ratio), float(reproj_threshold), ws.data_ptr(),
+                                           ws_bytes, res.data_ptr()))
+        ctx.sync(slot)
+    finally:
+        ctx.release_slot(slot)
+    return res.cpu().numpy().view(_lib.REGISTRATION_DTYPE).copy()

@@ -213,6 +213,38 @@ int dunk_register_frames_dev(dunk_db* db, int slot, const void* images_dev, int 
                              int cols, int channels, int row_stride_bytes, size_t frame_stride_bytes,
                              float ratio, double thr, int max_points, void* workspace_dev,
                              size_t workspace_bytes, void* results_dev);
+/* ---- the same path with the DB sharded over GPUs (one process per GPU) ----------
+ * phase 1 (frame owner): extract + pack the batch's descriptors as 64-B query rows;
+ * phase 2 (every shard): dunk_db_knn2_dev of all ranks' query rows against the local shard;
+ * phase 3 (frame owner): (distance, index)-merge of the shards' top-2, ratio, RANSAC.
+ * The two exchanges between the phases (queries out, top-2 back) are the caller's collectives. */
+typedef struct DunkPipelineView {
+    void* query64_dev;          /* total_queries x 64-B rows (capacity: query_capacity rows) */
+    void* query_offsets_dev;    /* n_frames + 1 int32: first query of every frame */
+    void* keypoints_dev;        /* n_frames x keypoint_capacity DunkKeyPoint */
+    void* keypoint_counts_dev;  /* n_frames int32 */
+    void* top2_dev;             /* scratch: query_capacity DunkTop2 records */
+    int32_t total_queries;
+    int32_t keypoint_capacity;
+    int64_t query_capacity;
+} DunkPipelineView;
+size_t dunk_pipeline_workspace_bytes(dunk_ctx* ctx, int n_frames, int rows, int cols);
+int dunk_pipeline_extract_dev(dunk_ctx* ctx, int slot, const void* images_dev, int n_frames, int rows,
+                              int cols, int channels, int row_stride_bytes, size_t frame_stride_bytes,
+                              int max_points, void* workspace_dev, size_t workspace_bytes,
+                              DunkPipelineView* view);
+/* parts_dev: n_parts arrays of DunkTop2 (part p at parts_dev + p*part_stride_records), global row
+ * indices; db_keypoints_dev: keypoints of ALL shards addressed by (index - index_base) */
+int dunk_pipeline_finish_dev(dunk_ctx* ctx, int slot, int n_frames, int rows, int cols,
+                             const void* parts_dev, int n_parts, int64_t part_stride_records,
+                             int total_queries, const void* db_keypoints_dev, uint32_t index_base,
+                             float ratio, double thr, void* workspace_dev, size_t workspace_bytes,
+                             void* results_dev);
+const void* dunk_db_keypoints_dev(dunk_db* db);   /* shard columns, for replication / exchange */
+const void* dunk_db_descriptors_dev(dunk_db* db);
+/* device-to-device copy, async on the slot's stream (keeps exchanges ordered with the kernels) */
+int dunk_memcpy_dev(dunk_ctx* ctx, int slot, void* dst_dev, const void* src_dev, size_t nbytes);
+
 /* reference-DB build (preprocessor/src/main.rs:248-327 minus GDAL/Postgres): extract a tile
  * batch and append rows to the shard; keypoint coordinates become x*scale[t] + x_off[t]
  * (main.rs:296-304); image_ids[t] -> image_id column.  counts (may be NULL): rows per tile. */

@@ -303,10 +303,12 @@ def local_maxima(e, thr=DTHRESHOLD):
 
 
 def _find_neighbor(mask, x, y, r):
-    """first keypoint (row-major scan of the (2r+1)^2 window) within L2 distance r."""
+    """first keypoint in a row-major scan of the HALF-OPEN window [y-r, y+r) x [x-r, x+r) that lies
+    within L2 distance r (<=).  The half-open bounds matter: a neighbour at exactly +r along an axis
+    is not seen (established differentially against cv2 4.13.0 on dense images)."""
     h, w = mask.shape
-    for cy in range(max(0, y - r), min(h, y + r + 1)):
-        for cx in range(max(0, x - r), min(w, x + r + 1)):
+    for cy in range(max(0, y - r), min(h, y + r)):
+        for cx in range(max(0, x - r), min(w, x + r)):
             if mask[cy, cx] and (cx - x) ** 2 + (cy - y) ** 2 <= r * r:
                 return cx, cy
     return None

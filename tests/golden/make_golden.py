@@ -114,6 +114,11 @@ def make_akaze():
     g = synth(200, 22, 260)
     col = np.clip(g[..., None].astype(np.int32) + rng.integers(-40, 40, (200, 260, 3)), 0, 255).astype(np.uint8)
     imgs["c"] = col                            # BGR input (cvtColor path), 2 octaves
+    # dense keypoints (contrast-stretched, decimated scene): exercises the suppression corner cases
+    # (neighbours at exactly distance r, multi-partner windows) that sparse images never hit
+    big = synth(1024, 23).astype(np.float32)
+    big = np.clip((big - big.mean()) * 2.2 + 128, 0, 255).astype(np.uint8)
+    imgs["d"] = cv2.resize(big, (448, 448), interpolation=cv2.INTER_AREA)
     for name, img in imgs.items():
         k, d = akaze_cv(img)
         out[f"{name}_img"], out[f"{name}_kps"], out[f"{name}_desc"] = img, k, d

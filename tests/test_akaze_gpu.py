@@ -31,7 +31,7 @@ def test_scale_space_planes_vs_oracle(dunk, ctx):
             assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-7, (i, "Ldet")
 
 
-@pytest.mark.parametrize("name", ["a", "b", "c"])
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
 def test_extract_vs_cv2_golden(dunk, ctx, name):
     r = dunk.feature_extraction.akaze_keypoint_descriptor_extraction_def(G[f"{name}_img"], None, ctx)
     rep = compare(G[f"{name}_kps"], G[f"{name}_desc"], r.keypoints, r.descriptors)

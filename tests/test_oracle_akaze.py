@@ -11,7 +11,7 @@ from tests.akaze_compare import assert_parity, compare
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "akaze_golden.npz"))
 
 
-@pytest.mark.parametrize("name", ["a", "c"])
+@pytest.mark.parametrize("name", ["a", "c", "d"])
 def test_detect_and_compute_vs_cv2_golden(name):
     kps, desc = ao.detect_and_compute(G[f"{name}_img"])
     rep = compare(G[f"{name}_kps"], G[f"{name}_desc"], kps, desc)

@@ -77,3 +77,35 @@ def test_batch_registration_and_tile_offsets(dunk, ctx):
     r = db.register_frames(noise)[0]
     assert r["found"] in (0, 1) and r["inliers"] < 12
     db.close()
+
+
+def test_sharded_phases_equal_unsharded(dunk, ctx):
+    """SURVEY 8e on one GPU: DB rows split into 3 shards, per-shard top-2 with global indices, merged
+    by (distance, index) in the finish phase == the unsharded pipeline, record for record."""
+    import synthdata as synth
+    fdb = dunk.feature_database
+    scene = synth.synth_image(512, 768, seed=5)
+    tiles = np.stack([scene[:, :384], scene[:, 384:]])
+    whole = fdb.DescriptorDatabase(ctx, capacity=60000)
+    whole.append_tiles(tiles, x_off=[0.0, 384.0], y_off=[0.0, 0.0], scale=1.0, image_ids=[1, 2])
+    d, k, ids = whole.read_rows(0, len(whole))
+    cuts = [0, len(whole) // 5, len(whole) // 2 + 3, len(whole)]
+    shards = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s = fdb.DescriptorDatabase(ctx, capacity=b - a)
+        s.append(d[a:b], k[a:b], ids[a:b])
+        shards.append(s)
+    frames = []
+    for x0, y0 in [(30, 20), (250, 90)]:
+        H = np.array([[1.0, 0.02, -x0], [-0.02, 1.0, -y0], [0, 1e-5, 1.0]])
+        frames.append(synth.warp_perspective(scene, H, 384, 384))
+    frames = np.stack(frames)
+    ref = whole.register_frames(frames, ratio=0.8, reproj_threshold=3.0)
+    got = fdb.register_frames_sharded_local(ctx, shards, frames, ratio=0.8, reproj_threshold=3.0)
+    assert (ref["found"] == 1).all() and (ref["inliers"] > 30).all()
+    for name in ("found", "inliers", "matches", "keypoints", "ransac_iters", "hypotheses"):
+        assert np.array_equal(ref[name], got[name]), name
+    assert np.array_equal(ref["H"], got["H"])
+    for s in shards:
+        s.close()
+    whole.close()
