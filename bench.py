@@ -322,26 +322,41 @@ def run_ours_sharded(args):
     tiles, xo, yo, sc = scene_tiles(scene)
     T = len(tiles)
     t_lo, t_hi = sharding.shard_ranges(T, world)[rank]
-    db = dunk.feature_database.DescriptorDatabase(ctx, capacity=max(1, (t_hi - t_lo)) * 12000)
+    # every rank extracts its share of the tiles, then the rows are re-cut into equal contiguous
+    # row ranges (tiles of coarser LoDs carry more keypoints; equal ROW counts balance the matcher)
+    tmp = dunk.feature_database.DescriptorDatabase(ctx, capacity=max(1, (t_hi - t_lo)) * 12000)
     t0 = time.perf_counter()
     if t_hi > t_lo:
-        db.append_tiles(tiles[t_lo:t_hi], xo[t_lo:t_hi], yo[t_lo:t_hi], sc[t_lo:t_hi], np.arange(t_lo, t_hi, dtype=np.int32))
+        tmp.append_tiles(tiles[t_lo:t_hi], xo[t_lo:t_hi], yo[t_lo:t_hi], sc[t_lo:t_hi], np.arange(t_lo, t_hi, dtype=np.int32))
     db_build_s = time.perf_counter() - t0
-    # shard sizes -> global index bases; replicate the (small) keypoint column on every rank
-    n_local = torch.tensor([len(db)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, n_local)
-    sizes = [int(x[0]) for x in sizes]
-    bases = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    max_rows = max(sizes)
-    kp_local = torch.zeros(max_rows * 28, dtype=torch.uint8, device=dev)
-    check(lib.dunk_memcpy_dev(ctx.handle, slot, kp_local.data_ptr(), lib.dunk_db_keypoints_dev(db.handle), len(db) * 28))
-    ctx.sync(slot)
-    kp_pad = torch.empty(world * max_rows * 28, dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(kp_pad, kp_local)
-    kps_all = torch.empty(int(bases[-1]) * 28, dtype=torch.uint8, device=dev)
-    for r in range(world):
-        kps_all[int(bases[r]) * 28:int(bases[r + 1]) * 28] = kp_pad[r * max_rows * 28:r * max_rows * 28 + sizes[r] * 28]
+    n_local = torch.tensor([len(tmp)], dtype=torch.int64, device=dev)
+    got = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(got, n_local)
+    ext_sizes = [int(x[0]) for x in got]
+    ext_bases = np.concatenate([[0], np.cumsum(ext_sizes)]).astype(np.int64)
+    total_rows, max_rows = int(ext_bases[-1]), max(ext_sizes)
+
+    def gather_column(ptr, width):
+        loc = torch.zeros(max_rows * width, dtype=torch.uint8, device=dev)
+        check(lib.dunk_memcpy_dev(ctx.handle, slot, loc.data_ptr(), ptr, len(tmp) * width))
+        ctx.sync(slot)
+        pad = torch.empty(world * max_rows * width, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(pad, loc)
+        full = torch.empty(total_rows * width, dtype=torch.uint8, device=dev)
+        for r in range(world):
+            full[int(ext_bases[r]) * width:int(ext_bases[r + 1]) * width] = pad[r * max_rows * width:(r * max_rows + ext_sizes[r]) * width]
+        return full
+    desc_all = gather_column(lib.dunk_db_descriptors_dev(tmp.handle), 64)
+    kps_all = gather_column(lib.dunk_db_keypoints_dev(tmp.handle), 28)       # replicated: global row -> keypoint
+    torch.cuda.synchronize(dev)
+    tmp.close()
+    ranges = sharding.shard_ranges(total_rows, world)
+    sizes = [b - a for a, b in ranges]
+    bases = np.array([a for a, _ in ranges] + [total_rows], dtype=np.int64)
+    r_lo, r_hi = ranges[rank]
+    db = dunk.feature_database.DescriptorDatabase(ctx, capacity=max(1, r_hi - r_lo))
+    check(lib.dunk_db_append_dev(db.handle, slot, desc_all.data_ptr() + r_lo * 64, kps_all.data_ptr() + r_lo * 28, None, r_hi - r_lo))
+    del desc_all
     torch.cuda.synchronize(dev)
 
     frames, Hs = make_frames(scene, B, seed0=1000 + 7919 * rank)

@@ -108,6 +108,7 @@ SIGNATURES = {
     "dunk_pipeline_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
     "dunk_pipeline_extract_dev": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, C.c_size_t, _i, _vp, C.c_size_t, _vp]),
     "dunk_pipeline_finish_dev": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i64, _i, _vp, _u32, _f, _d, _vp, C.c_size_t, _vp]),
+    "dunk_db_append_dev": (_i, [_vp, _i, _vp, _vp, _vp, _i64]),
     "dunk_memcpy_dev": (_i, [_vp, _i, _vp, _vp, C.c_size_t]),
     "dunk_db_keypoints_dev": (_vp, [_vp]),
     "dunk_db_descriptors_dev": (_vp, [_vp]),

@@ -391,6 +391,28 @@ int dunk_memcpy_dev(dunk_ctx* ctx, int slot, void* dst_dev, const void* src_dev,
     return DUNK_OK;
 }
 
+int dunk_db_append_dev(dunk_db* db, int slot, const void* desc64_dev, const void* kps_dev, const void* image_ids_dev,
+                       int64_t n) {
+    DUNK_REQUIRE(db && n >= 0, DUNK_ERR_BAD_ARG, "dunk_db_append_dev: bad argument");
+    if (n == 0) return DUNK_OK;
+    DUNK_REQUIRE(desc64_dev, DUNK_ERR_BAD_ARG, "dunk_db_append_dev: NULL descriptors");
+    dunk_ctx* ctx = db->ctx;
+    DUNK_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), DUNK_ERR_BAD_ARG, "dunk_db_append_dev: bad slot");
+    std::lock_guard<std::mutex> lk(db->mu);
+    DUNK_REQUIRE(db->size + n <= db->capacity, DUNK_ERR_NO_MEM, "dunk_db_append_dev: exceeds capacity %lld",
+                 (long long)db->capacity);
+    DUNK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[slot].stream;
+    DUNK_CUDA(cudaMemcpyAsync(db->desc64 + db->size * 4, desc64_dev, (size_t)n * 64, cudaMemcpyDeviceToDevice, st));
+    if (kps_dev) DUNK_CUDA(cudaMemcpyAsync(db->kps + db->size, kps_dev, (size_t)n * sizeof(DunkKeyPoint), cudaMemcpyDeviceToDevice, st));
+    else DUNK_CUDA(cudaMemsetAsync(db->kps + db->size, 0, (size_t)n * sizeof(DunkKeyPoint), st));
+    if (image_ids_dev) DUNK_CUDA(cudaMemcpyAsync(db->image_id + db->size, image_ids_dev, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    else DUNK_CUDA(cudaMemsetAsync(db->image_id + db->size, 0, (size_t)n * 4, st));
+    DUNK_CUDA(cudaStreamSynchronize(st));
+    db->size += n;
+    return DUNK_OK;
+}
+
 const void* dunk_db_keypoints_dev(dunk_db* db) { return db ? db->kps : nullptr; }
 const void* dunk_db_descriptors_dev(dunk_db* db) { return db ? db->desc64 : nullptr; }
 

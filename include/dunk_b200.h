@@ -240,6 +240,10 @@ int dunk_pipeline_finish_dev(dunk_ctx* ctx, int slot, int n_frames, int rows, in
                              int total_queries, const void* db_keypoints_dev, uint32_t index_base,
                              float ratio, double thr, void* workspace_dev, size_t workspace_bytes,
                              void* results_dev);
+/* append n rows whose columns already live on the device (64-B descriptor rows, DunkKeyPoint,
+ * int32 image ids; the last two may be NULL) — used to re-cut shards into equal row ranges */
+int dunk_db_append_dev(dunk_db* db, int slot, const void* desc64_dev, const void* kps_dev,
+                       const void* image_ids_dev, int64_t n);
 const void* dunk_db_keypoints_dev(dunk_db* db);   /* shard columns, for replication / exchange */
 const void* dunk_db_descriptors_dev(dunk_db* db);
 /* device-to-device copy, async on the slot's stream (keeps exchanges ordered with the kernels) */
