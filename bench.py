@@ -373,6 +373,7 @@ def run_ours_sharded(args):
     q_all = torch.empty(world * QCAP * 64, dtype=torch.uint8, device=dev)
     nq_t = torch.zeros(1, dtype=torch.int32, device=dev)
     nq_all = torch.zeros(world, dtype=torch.int32, device=dev)
+    nq_pin = torch.zeros(world, dtype=torch.int32).pin_memory()
     top2_out = torch.empty(world * QCAP * 16, dtype=torch.uint8, device=dev)     # [source rank][query]
     parts = torch.empty(world * QCAP * 16, dtype=torch.uint8, device=dev)        # [shard][my query]
     torch.cuda.synchronize(dev)
@@ -388,7 +389,9 @@ def run_ours_sharded(args):
             nq_t.fill_(nq)
             dist.all_gather_into_tensor(nq_all, nq_t)
             dist.all_gather_into_tensor(q_all, q_pad)
-        counts = nq_all.cpu().tolist()                      # host sync: the matcher grids depend on the counts
+            nq_pin.copy_(nq_all, non_blocking=True)          # D2H on the pipeline stream, after the all-gather
+        ctx.sync(slot)                                      # host sync: the matcher grids depend on the counts
+        counts = nq_pin.tolist()
         for r in range(world):
             check(lib.dunk_db_knn2_dev(db.handle, slot, q_all.data_ptr() + r * QCAP * 64, counts[r], int(bases[rank]),
                                        top2_out.data_ptr() + r * QCAP * 16))

@@ -1,0 +1,365 @@
+"""Oracle for stage 3b (PnP-RANSAC pose) — TEST INFRASTRUCTURE ONLY.
+
+Restates `cv::solvePnPRansac(obj, img, K, dist=0, rvec, tvec, false, iters, thr, conf, inliers,
+SOLVEPNP_EPNP)` as the reference calls it (homographier/src/homographier/mod.rs:320-369; zero
+distortion is forced at :344, EPNP is the default method at :359).  The arithmetic lives in
+OpenCV's calib3d (`solvepnp.cpp`, `epnp.cpp`, `ptsetreg.cpp`) and core (`lapack.cpp` JacobiSVD,
+`calibration_base.cpp` Rodrigues / projectPoints); not vendored in the reference (opencv crate
+0.88.8 over the system libopencv 4.x).  Pinned against cv2 4.13.0 outputs in
+tests/golden/pnp_golden.npz (tests/golden/make_golden.py).
+
+What the restatement follows (all established differentially against cv2 4.13.0):
+  * f64 inputs are converted to f32 before the RANSAC loop (solvepnp.cpp: `convertTo(CV_32F)`),
+    the final solve on the inliers runs on those f32 values widened back to f64;
+  * minimal sample = 5 points (EPnP kernel), same MWC sample stream as findHomography, no
+    checkSubset; a model is accepted when good > max(best, 4);
+  * EPnP (Lepetit/Moreno-Noguer/Fua) with OpenCV's conventions: control points from the one-sided
+    Jacobi SVD of PW0^T PW0 (the SIGNS of its singular vectors change the answer under noise, so
+    the Jacobi sweep order is reproduced), betas from approximations 1..3 + 5 Gauss-Newton steps,
+    Procrustes R,t, candidate with the smallest mean reprojection error wins;
+  * error = squared f32 distance between the f32 image point and the f64 projection rounded to
+    f32; inlier iff err <= (float)(thr^2).
+For 5-point samples M^T M has a 2-dimensional null space whose basis OpenCV derives from rounding
+noise, so per-hypothesis poses are only reproducible to ~1e-6; the final pose (>= 6 inliers) is
+reproducible to ~1e-9 whenever the winning inlier set agrees.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .ransac_oracle import CvRNG, ransac_update_num_iters
+
+DBL_EPSILON = float(np.finfo(np.float64).eps)
+DBL_MIN = float(np.finfo(np.float64).tiny)
+
+
+# ----------------------------------------------------------------------------- cv::SVD (Jacobi)
+def jacobi_svd(A):
+    """cv::SVD::compute for an m x n f64 matrix with m >= n < 25 (core/src/lapack.cpp
+    JacobiSVDImpl_: one-sided Hestenes rotations on the rows of A^T, cyclic (i, j) order,
+    eps = 10 DBL_EPSILON, <= max(m, 30) sweeps, then a selection sort by decreasing singular
+    value).  Returns (w[n], U[m x n], Vt[n x n]) with OpenCV's signs."""
+    A = np.array(A, dtype=np.float64)
+    m, n = A.shape
+    assert m >= n
+    At = A.T.copy()                      # n rows of length m
+    Vt = np.eye(n)
+    W = (At * At).sum(1)
+    eps = DBL_EPSILON * 10
+    for _ in range(max(m, 30)):
+        changed = False
+        for i in range(n - 1):
+            for j in range(i + 1, n):
+                a, b = W[i], W[j]
+                p = float(At[i] @ At[j])
+                if abs(p) <= eps * math.sqrt(a * b):
+                    continue
+                p *= 2.0
+                beta = a - b
+                gamma = math.hypot(p, beta)
+                if beta < 0:
+                    delta = (gamma - beta) * 0.5
+                    s = math.sqrt(delta / gamma)
+                    c = p / (gamma * s * 2)
+                else:
+                    c = math.sqrt((gamma + beta) / (gamma * 2))
+                    s = p / (gamma * c * 2)
+                t0 = c * At[i] + s * At[j]
+                t1 = -s * At[i] + c * At[j]
+                At[i], At[j] = t0, t1
+                W[i], W[j] = float(t0 @ t0), float(t1 @ t1)
+                changed = True
+                v0 = c * Vt[i] + s * Vt[j]
+                v1 = -s * Vt[i] + c * Vt[j]
+                Vt[i], Vt[j] = v0, v1
+        if not changed:
+            break
+    W = np.sqrt((At * At).sum(1))
+    for i in range(n - 1):
+        j = i
+        for k in range(i + 1, n):
+            if W[j] < W[k]:
+                j = k
+        if i != j:
+            W[[i, j]] = W[[j, i]]
+            At[[i, j]] = At[[j, i]]
+            Vt[[i, j]] = Vt[[j, i]]
+    U = np.zeros((m, n))
+    for i in range(n):
+        sd = W[i]
+        U[:, i] = At[i] * (1.0 / sd if sd > DBL_MIN else 0.0)   # (zero singular values: OpenCV fills a random vector)
+    return W, U, Vt
+
+
+def _svd_solve(A, b):
+    """cv::solve(A, b, x, DECOMP_SVD): least squares through the SVD (SVBkSb threshold)."""
+    w, U, Vt = jacobi_svd(A)
+    thr = DBL_EPSILON * 2 * w.sum()
+    y = U.T @ b
+    y = np.where(w > thr, y / np.where(w > thr, w, 1.0), 0.0)
+    return Vt.T @ y
+
+
+def _svd_inv3(A):
+    w, U, Vt = jacobi_svd(A)
+    thr = DBL_EPSILON * 2 * w.sum()
+    wi = np.where(w > thr, 1.0 / np.where(w > thr, w, 1.0), 0.0)
+    return (Vt.T * wi) @ U.T
+
+
+def _qr_solve(A, b):
+    """epnp::qr_solve — Householder least squares of the 6 x 4 Gauss-Newton system."""
+    return np.linalg.lstsq(A, b, rcond=None)[0]
+
+
+# ----------------------------------------------------------------------------- cv::Rodrigues
+def rodrigues_to_matrix(r):
+    r = np.asarray(r, dtype=np.float64).ravel()
+    theta = math.sqrt(float(r @ r))
+    if theta < DBL_EPSILON:
+        return np.eye(3)
+    c, s = math.cos(theta), math.sin(theta)
+    c1 = 1.0 - c
+    k = r / theta
+    rrt = np.outer(k, k)
+    rx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return c * np.eye(3) + c1 * rrt + s * rx
+
+
+def rodrigues_to_vector(R):
+    w, U, Vt = jacobi_svd(np.asarray(R, dtype=np.float64))
+    R = U @ Vt
+    r = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    s = math.sqrt(float(r @ r) * 0.25)
+    c = (R[0, 0] + R[1, 1] + R[2, 2] - 1) * 0.5
+    c = 1.0 if c > 1.0 else (-1.0 if c < -1.0 else c)
+    theta = math.acos(c)
+    if s < 1e-5:
+        if c > 0:
+            return np.zeros(3)
+        t = (R[0, 0] + 1) * 0.5
+        r[0] = math.sqrt(max(t, 0.0))
+        t = (R[1, 1] + 1) * 0.5
+        r[1] = math.sqrt(max(t, 0.0)) * (-1.0 if R[0, 1] < 0 else 1.0)
+        t = (R[2, 2] + 1) * 0.5
+        r[2] = math.sqrt(max(t, 0.0)) * (-1.0 if R[0, 2] < 0 else 1.0)
+        if abs(r[0]) < abs(r[1]) and abs(r[0]) < abs(r[2]) and ((R[1, 2] > 0) != (r[1] * r[2] > 0)):
+            r[2] = -r[2]
+        return r * (theta / math.sqrt(float(r @ r)))
+    return r * (theta / (2 * s))
+
+
+# ----------------------------------------------------------------------------- EPnP
+_PAIRS = ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))
+
+
+def epnp(obj, img, K, f32_normalised=False):
+    """epnp::compute_pose (calib3d/src/epnp.cpp).  obj n x 3, img n x 2 (pixels), K 3 x 3; all f64.
+    f32_normalised: the image points reached solvePnP as CV_32F, so undistortPoints returned f32
+    normalised coordinates (every call made from inside solvePnPRansac's loop).
+    Returns (R 3x3, t 3, mean reprojection error)."""
+    pws = np.asarray(obj, dtype=np.float64).reshape(-1, 3)
+    img = np.asarray(img, dtype=np.float64).reshape(-1, 2)
+    n = pws.shape[0]
+    fu, fv, uc, vc = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    # solvePnPGeneric: undistortPoints (zero distortion -> (u - cx)/fx), then epnp::init_points maps back
+    xn, yn = (img[:, 0] - uc) / fu, (img[:, 1] - vc) / fv
+    if f32_normalised:
+        xn, yn = xn.astype(np.float32).astype(np.float64), yn.astype(np.float32).astype(np.float64)
+    us = np.stack([xn * fu + uc, yn * fv + vc], 1)
+
+    # choose_control_points
+    cws = np.zeros((4, 3))
+    cws[0] = pws.sum(0) / n
+    PW0 = pws - cws[0]
+    dc, U, _ = jacobi_svd(PW0.T @ PW0)
+    for i in range(1, 4):
+        cws[i] = cws[0] + math.sqrt(dc[i - 1] / n) * U[:, i - 1]
+    # compute_barycentric_coordinates
+    CC = (cws[1:] - cws[0]).T
+    CCi = _svd_inv3(CC)
+    al = np.zeros((n, 4))
+    al[:, 1:] = (pws - cws[0]) @ CCi.T
+    al[:, 0] = 1.0 - al[:, 1] - al[:, 2] - al[:, 3]
+    # fill_M, M^T M, its 4 smallest left singular vectors
+    M = np.zeros((2 * n, 12))
+    for j in range(4):
+        M[0::2, 3 * j] = al[:, j] * fu
+        M[0::2, 3 * j + 2] = al[:, j] * (uc - us[:, 0])
+        M[1::2, 3 * j + 1] = al[:, j] * fv
+        M[1::2, 3 * j + 2] = al[:, j] * (vc - us[:, 1])
+    _, U12, _ = jacobi_svd(M.T @ M)
+    v = [U12[:, 11], U12[:, 10], U12[:, 9], U12[:, 8]]
+    # compute_L_6x10, compute_rho
+    dv = np.zeros((4, 6, 3))
+    for i in range(4):
+        for p, (a, b) in enumerate(_PAIRS):
+            dv[i, p] = v[i][3 * a:3 * a + 3] - v[i][3 * b:3 * b + 3]
+    L = np.zeros((6, 10))
+    for p in range(6):
+        d0, d1, d2, d3 = dv[0, p], dv[1, p], dv[2, p], dv[3, p]
+        L[p] = [d0 @ d0, 2 * (d0 @ d1), d1 @ d1, 2 * (d0 @ d2), 2 * (d1 @ d2), d2 @ d2,
+                2 * (d0 @ d3), 2 * (d1 @ d3), 2 * (d2 @ d3), d3 @ d3]
+    rho = np.array([((cws[a] - cws[b]) ** 2).sum() for a, b in _PAIRS])
+
+    def approx_1():
+        b4 = _svd_solve(L[:, [0, 1, 3, 6]], rho)
+        if b4[0] < 0:
+            b0 = math.sqrt(-b4[0])
+            return np.array([b0, -b4[1] / b0, -b4[2] / b0, -b4[3] / b0])
+        b0 = math.sqrt(b4[0])
+        return np.array([b0, b4[1] / b0, b4[2] / b0, b4[3] / b0])
+
+    def _two(b):
+        be = np.zeros(4)
+        if b[0] < 0:
+            be[0] = math.sqrt(-b[0])
+            be[1] = math.sqrt(-b[2]) if b[2] < 0 else 0.0
+        else:
+            be[0] = math.sqrt(b[0])
+            be[1] = math.sqrt(b[2]) if b[2] > 0 else 0.0
+        if b[1] < 0:
+            be[0] = -be[0]
+        return be
+
+    def approx_2():
+        return _two(_svd_solve(L[:, [0, 1, 2]], rho))
+
+    def approx_3():
+        b5 = _svd_solve(L[:, [0, 1, 2, 3, 4]], rho)
+        be = _two(b5)
+        be[2] = b5[3] / be[0]
+        return be
+
+    def gauss_newton(be):
+        be = be.copy()
+        for _ in range(5):
+            A = np.stack([2 * L[:, 0] * be[0] + L[:, 1] * be[1] + L[:, 3] * be[2] + L[:, 6] * be[3],
+                          L[:, 1] * be[0] + 2 * L[:, 2] * be[1] + L[:, 4] * be[2] + L[:, 7] * be[3],
+                          L[:, 3] * be[0] + L[:, 4] * be[1] + 2 * L[:, 5] * be[2] + L[:, 8] * be[3],
+                          L[:, 6] * be[0] + L[:, 7] * be[1] + L[:, 8] * be[2] + 2 * L[:, 9] * be[3]], 1)
+            b = rho - (L[:, 0] * be[0] * be[0] + L[:, 1] * be[0] * be[1] + L[:, 2] * be[1] * be[1] + L[:, 3] * be[0] * be[2]
+                       + L[:, 4] * be[1] * be[2] + L[:, 5] * be[2] * be[2] + L[:, 6] * be[0] * be[3] + L[:, 7] * be[1] * be[3]
+                       + L[:, 8] * be[2] * be[3] + L[:, 9] * be[3] * be[3])
+            be = be + _qr_solve(A, b)
+        return be
+
+    def compute_R_and_t(be):
+        ccs = np.zeros((4, 3))
+        for i in range(4):
+            for j in range(4):
+                ccs[j] += be[i] * v[i][3 * j:3 * j + 3]
+        pcs = al @ ccs
+        if pcs[0, 2] < 0.0:                      # solve_for_sign
+            ccs, pcs = -ccs, -pcs
+        pc0, pw0 = pcs.sum(0) / n, pws.sum(0) / n
+        ABt = (pcs - pc0).T @ (pws - pw0)
+        _, Ua, Vta = jacobi_svd(ABt)
+        R = Ua @ Vta
+        if np.linalg.det(R) < 0:
+            R[2] = -R[2]
+        t = pc0 - R @ pw0
+        P = pws @ R.T + t
+        ue, ve = uc + fu * P[:, 0] / P[:, 2], vc + fv * P[:, 1] / P[:, 2]
+        err = float(np.sqrt((us[:, 0] - ue) ** 2 + (us[:, 1] - ve) ** 2).sum() / n)
+        return R, t, err
+
+    best = None
+    for f in (approx_1, approx_2, approx_3):
+        with np.errstate(all="ignore"):
+            cand = compute_R_and_t(gauss_newton(f()))
+        if best is None or cand[2] < best[2]:
+            best = cand
+    return best
+
+
+def solve_pnp_epnp(obj, img, K, f32_normalised=False):
+    """cv::solvePnP(..., SOLVEPNP_EPNP): (rvec, tvec) or None when the pose is not finite."""
+    R, t, _ = epnp(obj, img, K, f32_normalised)
+    if not (np.isfinite(R).all() and np.isfinite(t).all()):
+        return None
+    return rodrigues_to_vector(R), t
+
+
+# ----------------------------------------------------------------------------- RANSAC
+def project_points(obj, rvec, tvec, K):
+    """cv::projectPoints with zero distortion, f64 arithmetic."""
+    R = rodrigues_to_matrix(rvec)
+    P = np.asarray(obj, dtype=np.float64) @ R.T + np.asarray(tvec, dtype=np.float64)
+    z = 1.0 / P[:, 2]
+    x, y = P[:, 0] * z, P[:, 1] * z
+    return np.stack([x * K[0, 0] + K[0, 2], y * K[1, 1] + K[1, 2]], 1)
+
+
+def reproj_err_f32(obj32, img32, rvec, tvec, K):
+    """PnPRansacCallback::computeError: f32 projected points, f32 squared distance (no FMA)."""
+    with np.errstate(all="ignore"):
+        pp = project_points(obj32, rvec, tvec, K).astype(np.float32)
+        d = img32 - pp
+        return d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
+
+
+def sample_stream(n, count, model_points=5):
+    """the first `count` minimal index sets of the registrator's fixed-seed stream (no checkSubset)."""
+    rng = CvRNG()
+    out = []
+    for _ in range(count):
+        idx = []
+        for _i in range(model_points):
+            v = rng.uniform(0, n)
+            while v in idx:
+                v = rng.uniform(0, n)
+            idx.append(v)
+        out.append(idx)
+    return np.array(out, dtype=np.int32).reshape(-1, model_points)
+
+
+def solve_pnp_ransac(obj, img, K, iters=100, thr=8.0, confidence=0.99):
+    """cv::solvePnPRansac(obj, img, K, zeros, iters, thr, confidence, flags=EPNP).
+    Returns (found, rvec[3], tvec[3], inlier indices int32)."""
+    obj32 = np.ascontiguousarray(obj, dtype=np.float64).reshape(-1, 3).astype(np.float32)
+    img32 = np.ascontiguousarray(img, dtype=np.float64).reshape(-1, 2).astype(np.float32)
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    n = obj32.shape[0]
+    if n < 4:
+        raise ValueError("-215: solvePnPRansac needs at least 4 correspondences")
+    if n == 4:
+        raise NotImplementedError("npoints == 4 switches the kernel to P3P (not on the reference's default path)")
+    mp = 5
+    objd, imgd = obj32.astype(np.float64), img32.astype(np.float64)
+    if n == mp:
+        sol = solve_pnp_epnp(objd, imgd, K, True)
+        if sol is None:
+            return False, np.zeros(3), np.zeros(3), np.zeros(0, np.int32)
+        return True, sol[0], sol[1], np.arange(n, dtype=np.int32)
+    thr2 = np.float32(float(thr) * float(thr))
+    rng = CvRNG()
+    niters = iters
+    best = None
+    best_count = 0
+    it = 0
+    while it < niters:
+        idx = []
+        for _ in range(mp):
+            v = rng.uniform(0, n)
+            while v in idx:
+                v = rng.uniform(0, n)
+            idx.append(v)
+        sol = solve_pnp_epnp(objd[idx], imgd[idx], K, True)
+        if sol is not None:
+            err = reproj_err_f32(obj32, img32, sol[0], sol[1], K)
+            mask = err <= thr2
+            good = int(mask.sum())
+            if good > max(best_count, mp - 1):
+                best, best_count = (sol, mask), good
+                niters = ransac_update_num_iters(confidence, (n - good) / n, mp, niters)
+        it += 1
+    if best is None:
+        return False, np.zeros(3), np.zeros(3), np.zeros(0, np.int32)
+    (rv, tv), mask = best
+    sol = solve_pnp_epnp(objd[mask], imgd[mask], K)
+    if sol is None:
+        return False, rv, tv, np.zeros(0, np.int32)
+    return True, sol[0], sol[1], np.nonzero(mask)[0].astype(np.int32)

@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ by running the reference's OpenCV entry
 points (through cv2, the same C++ library the `opencv` crate binds) with the reference's exact
-arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|akaze|all]
+arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|akaze|pnp|all]
 The OpenCV version is recorded in every file (parity is defined against that version)."""
 import os
 import sys
@@ -128,6 +128,74 @@ def make_akaze():
     print("akaze_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
+PNP_K = np.array([[800., 0, 512], [0, 820., 500], [0, 0, 1]])
+# (n, outlier fraction, pixel noise sigma, iterations, reprojection threshold, confidence, relief)
+PNP_CASES = [(100, 0.3, 0.5, 100, 8.0, 0.99, "cube"), (1000, 0.4, 0.5, 1000, 2.0, 0.99, "cube"),
+             (50, 0.0, 0.0, 100, 8.0, 0.99, "cube"), (300, 0.5, 1.0, 500, 3.0, 0.999, "cube"),
+             (6, 0.0, 0.1, 100, 8.0, 0.99, "cube"), (2000, 0.2, 0.3, 1000, 2.0, 0.99, "cube"),
+             (500, 0.6, 0.5, 1000, 2.0, 0.99, "cube"), (5, 0.0, 0.1, 100, 8.0, 0.99, "cube"),
+             (400, 0.3, 0.5, 300, 3.0, 0.99, "terrain"), (64, 0.9, 0.5, 50, 1.0, 0.99, "cube")]
+
+
+def pnp_case(seed, n, out_frac, noise, relief):
+    """n object points seen by a camera 8 units away; `terrain` = mild relief over a plane (DEM-like)."""
+    rng = np.random.default_rng(seed)
+    rv = rng.normal(0, 0.4, 3)
+    tv = np.array([0.3, -0.2, 8.0]) + rng.normal(0, 0.5, 3)
+    obj = rng.uniform(-2, 2, (n, 3))
+    if relief == "terrain":
+        obj[:, 2] = 0.15 * np.sin(obj[:, 0] * 2.0) * np.cos(obj[:, 1] * 1.5) + rng.normal(0, 0.02, n)
+    R, _ = cv2.Rodrigues(rv)
+    P = obj @ R.T + tv
+    img = np.stack([PNP_K[0, 0] * P[:, 0] / P[:, 2] + PNP_K[0, 2], PNP_K[1, 1] * P[:, 1] / P[:, 2] + PNP_K[1, 2]], 1)
+    img += rng.normal(0, noise, (n, 2))
+    no = int(out_frac * n)
+    o = rng.choice(n, no, replace=False)
+    img[o] = rng.uniform(0, 1024, (no, 2))
+    return obj, img
+
+
+def make_pnp():
+    """cv2.solvePnPRansac(obj, img, K, zeros(4,1), ..., flags=EPNP) — mod.rs:347-361 — plus
+    cv2.solvePnP(EPNP) on f64 and f32 point sets, cv2.Rodrigues and cv2.SVDecomp probes."""
+    out = {"opencv_version": np.array(cv2.__version__), "n_cases": np.array(len(PNP_CASES)), "K": PNP_K}
+    for i, (n, of, noise, iters, thr, conf, relief) in enumerate(PNP_CASES):
+        obj, img = pnp_case(i, n, of, noise, relief)
+        ok, r, t, inl = cv2.solvePnPRansac(obj, img, PNP_K, np.zeros((4, 1)), None, None, False, iters, thr, conf, None,
+                                           cv2.SOLVEPNP_EPNP)
+        out[f"c{i}_obj"], out[f"c{i}_img"] = obj, img
+        out[f"c{i}_params"] = np.array([iters, thr, conf])
+        out[f"c{i}_found"] = np.array(bool(ok))
+        out[f"c{i}_rvec"], out[f"c{i}_tvec"] = r.ravel(), t.ravel()
+        out[f"c{i}_inliers"] = np.zeros(0, np.int32) if inl is None else inl.ravel().astype(np.int32)
+        print(f"pnp case {i}: n={n} found={ok} inliers={len(out[f'c{i}_inliers'])}")
+    # plain EPnP solves (f64 points and f32 points take different undistortPoints precisions)
+    rng = np.random.default_rng(99)
+    for j, n in enumerate((6, 7, 12, 40, 300)):
+        obj, img = pnp_case(100 + j, n, 0.0, 0.5, "cube")
+        ok, r, t = cv2.solvePnP(obj, img, PNP_K, np.zeros((4, 1)), flags=cv2.SOLVEPNP_EPNP)
+        o32, i32 = obj.astype(np.float32), img.astype(np.float32)
+        ok2, r2, t2 = cv2.solvePnP(o32, i32, PNP_K, np.zeros((4, 1)), flags=cv2.SOLVEPNP_EPNP)
+        out[f"e{j}_obj"], out[f"e{j}_img"] = obj, img
+        out[f"e{j}_rt64"] = np.r_[r.ravel(), t.ravel()]
+        out[f"e{j}_rt32"] = np.r_[r2.ravel(), t2.ravel()]
+    out["n_epnp"] = np.array(5)
+    # Rodrigues both ways, Jacobi SVD signs on small symmetric matrices
+    rv = rng.normal(0, 1.0, (8, 3))
+    out["rod_rvec"] = rv
+    out["rod_R"] = np.stack([cv2.Rodrigues(v)[0] for v in rv])
+    out["rod_back"] = np.stack([cv2.Rodrigues(R)[0].ravel() for R in out["rod_R"]])
+    A = rng.normal(size=(6, 7, 3))
+    B = np.einsum("kij,kil->kjl", A, A)
+    out["svd_in"] = B
+    sv = [cv2.SVDecomp(b) for b in B]
+    out["svd_w"] = np.stack([s[0].ravel() for s in sv])
+    out["svd_u"] = np.stack([s[1] for s in sv])
+    out["svd_vt"] = np.stack([s[2] for s in sv])
+    np.savez_compressed(os.path.join(HERE, "pnp_golden.npz"), **out)
+    print("pnp_golden.npz written")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("match", "all"):
@@ -136,3 +204,5 @@ if __name__ == "__main__":
         make_ransac()
     if what in ("akaze", "all") and "make_akaze" in globals():
         make_akaze()
+    if what in ("pnp", "all") and "make_pnp" in globals():
+        make_pnp()

@@ -1,0 +1,60 @@
+"""CPU: the PnP oracle reproduces cv2 4.13.0 `solvePnPRansac(..., EPNP)` (the call made at
+homographier/src/homographier/mod.rs:347-361) on the committed golden vectors: inlier index lists
+identical, rvec/tvec within 1e-9; plain EPnP solves within 1e-9 for f64 and f32 point sets;
+cv::Rodrigues and the Jacobi SVD sign conventions within 1e-12."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pnp_oracle as po
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pnp_golden.npz"))
+N = int(G["n_cases"])
+K = G["K"]
+POSE_ATOL = 1e-9
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_solve_pnp_ransac_matches_cv2(i):
+    iters, thr, conf = G[f"c{i}_params"]
+    found, r, t, inl = po.solve_pnp_ransac(G[f"c{i}_obj"], G[f"c{i}_img"], K, int(iters), float(thr), float(conf))
+    assert found == bool(G[f"c{i}_found"])
+    assert np.array_equal(inl, G[f"c{i}_inliers"])
+    if found:
+        assert np.abs(r - G[f"c{i}_rvec"]).max() < POSE_ATOL
+        assert np.abs(t - G[f"c{i}_tvec"]).max() < POSE_ATOL
+
+
+@pytest.mark.parametrize("j", range(int(G["n_epnp"])))
+def test_epnp_matches_cv2(j):
+    obj, img = G[f"e{j}_obj"], G[f"e{j}_img"]
+    r, t = po.solve_pnp_epnp(obj, img, K)
+    assert np.abs(np.r_[r, t] - G[f"e{j}_rt64"]).max() < POSE_ATOL
+    o32, i32 = obj.astype(np.float32).astype(np.float64), img.astype(np.float32).astype(np.float64)
+    r, t = po.solve_pnp_epnp(o32, i32, K, f32_normalised=True)
+    assert np.abs(np.r_[r, t] - G[f"e{j}_rt32"]).max() < POSE_ATOL
+
+
+def test_rodrigues_both_ways():
+    for rv, R, back in zip(G["rod_rvec"], G["rod_R"], G["rod_back"]):
+        assert np.abs(po.rodrigues_to_matrix(rv) - R).max() < 1e-12
+        assert np.abs(po.rodrigues_to_vector(R) - back).max() < 1e-12
+
+
+def test_jacobi_svd_signs():
+    for B, w, u, vt in zip(G["svd_in"], G["svd_w"], G["svd_u"], G["svd_vt"]):
+        W, U, Vt = po.jacobi_svd(B)
+        assert np.abs(W - w).max() < 1e-12 * w.max()
+        assert np.abs(U - u).max() < 1e-12 and np.abs(Vt - vt).max() < 1e-12
+
+
+def test_too_few_points():
+    """reference test pnp_solver_ransac_no_work_lthan_3_points (mod.rs:627-638): error, not None"""
+    with pytest.raises(ValueError):
+        po.solve_pnp_ransac(np.array([[1., 2, 3], [4, 5, 6]]), np.array([[1., 2], [4, 5]]), np.zeros((3, 3)), 50, 2.0, 0.99)
+
+
+def test_sample_stream_is_the_homography_stream_with_5_points():
+    s = po.sample_stream(100, 4)
+    assert s.shape == (4, 5) and all(len(set(r)) == 5 for r in s.tolist())
