@@ -116,6 +116,9 @@ SIGNATURES = {
     "dunk_find_homography": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _pi]),
     "dunk_find_homography_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "dunk_ransac_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _vp, _vp]),
+    "dunk_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _i, _pi, _pi]),
+    "dunk_pnp_ransac_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _vp]),
+    "dunk_pnp_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp]),
 }
 
 

@@ -1,0 +1,526 @@
+// Scalar f64 building blocks of the PnP stage (replaces cv::solvePnPRansac as called at
+// homographier/src/homographier/mod.rs:347-361): OpenCV's one-sided Jacobi SVD (the SIGNS of the
+// singular vectors of PW0^T PW0 change EPnP's answer under noise, so the rotation order is kept),
+// cv::solve(DECOMP_SVD), cv::Rodrigues in both directions, and EPnP itself.
+//
+// Everything here is `__host__ __device__` so the same source is exercised on the host by
+// tests/hostcheck (a test-only harness; the product never runs it on the CPU) and on the device
+// by ransac_pnp.cu.  EPnP is written against an "executor" that owns the loop over the used
+// points: SerialExec (one thread = one minimal sample) or the CTA-wide BlockExec of ransac_pnp.cu
+// (every thread runs the scalar part redundantly, the sums over points are block reductions).
+#pragma once
+#include <cfloat>
+#include <cmath>
+
+#ifdef __CUDACC__
+#define DUNK_HD __host__ __device__
+#else
+#define DUNK_HD
+#endif
+
+namespace dunk {
+namespace pnp {
+
+struct Camera {
+    double fu, fv, uc, vc;
+};
+
+struct Point {
+    double X, Y, Z, u, v;
+};
+
+// cv::undistortPoints with zero distortion ((u - cx) * (1/fx)), optionally rounded to f32 (f32 image
+// points give f32 normalised points), then epnp::init_points maps back: x * fu + uc.
+DUNK_HD inline Point load_point(const float* obj, const float* img, int i, const Camera& c, bool f32_normalised) {
+    Point p;
+    p.X = obj[3 * i];
+    p.Y = obj[3 * i + 1];
+    p.Z = obj[3 * i + 2];
+    double xn = ((double)img[2 * i] - c.uc) * (1.0 / c.fu);
+    double yn = ((double)img[2 * i + 1] - c.vc) * (1.0 / c.fv);
+    if (f32_normalised) {
+        xn = (double)(float)xn;
+        yn = (double)(float)yn;
+    }
+    p.u = xn * c.fu + c.uc;
+    p.v = yn * c.fv + c.vc;
+    return p;
+}
+
+// JacobiSVDImpl_ (core/src/lapack.cpp).  At: N rows of length M = the columns of A.  On return the
+// rows of At are the left singular vectors (unit length), W the singular values in decreasing
+// order, Vt (N x N, only if WantV) the right singular vectors as rows.
+template <int M, int N, bool WantV>
+DUNK_HD void jacobi_svd(double* At, double* W, double* Vt) {
+    const double eps = DBL_EPSILON * 10;
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+        W[i] = sd;
+        if (WantV) {
+            for (int k = 0; k < N; ++k) Vt[i * N + k] = 0;
+            Vt[i * N + i] = 1;
+        }
+    }
+    const int max_iter = M > 30 ? M : 30;
+    for (int iter = 0; iter < max_iter; ++iter) {
+        bool changed = false;
+        for (int i = 0; i < N - 1; ++i)
+            for (int j = i + 1; j < N; ++j) {
+                double* Ai = At + i * M;
+                double* Aj = At + j * M;
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < M; ++k) p += Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = hypot(p, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = p / (gamma * s * 2);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2));
+                    s = p / (gamma * c * 2);
+                }
+                a = b = 0;
+                for (int k = 0; k < M; ++k) {
+                    const double t0 = c * Ai[k] + s * Aj[k];
+                    const double t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0;
+                    Aj[k] = t1;
+                    a += t0 * t0;
+                    b += t1 * t1;
+                }
+                W[i] = a;
+                W[j] = b;
+                changed = true;
+                if (WantV) {
+                    double* Vi = Vt + i * N;
+                    double* Vj = Vt + j * N;
+                    for (int k = 0; k < N; ++k) {
+                        const double t0 = c * Vi[k] + s * Vj[k];
+                        const double t1 = -s * Vi[k] + c * Vj[k];
+                        Vi[k] = t0;
+                        Vj[k] = t1;
+                    }
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < N; ++i) {
+        double sd = 0;
+        for (int k = 0; k < M; ++k) sd += At[i * M + k] * At[i * M + k];
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < N - 1; ++i) {
+        int j = i;
+        for (int k = i + 1; k < N; ++k)
+            if (W[j] < W[k]) j = k;
+        if (i != j) {
+            double t = W[i]; W[i] = W[j]; W[j] = t;
+            for (int k = 0; k < M; ++k) { t = At[i * M + k]; At[i * M + k] = At[j * M + k]; At[j * M + k] = t; }
+            if (WantV)
+                for (int k = 0; k < N; ++k) { t = Vt[i * N + k]; Vt[i * N + k] = Vt[j * N + k]; Vt[j * N + k] = t; }
+        }
+    }
+    for (int i = 0; i < N; ++i) {
+        const double s = W[i] > DBL_MIN ? 1.0 / W[i] : 0.0;   // (an exactly-zero singular value gets a random vector in OpenCV)
+        for (int k = 0; k < M; ++k) At[i * M + k] *= s;
+    }
+}
+
+// cv::solve(A, b, x, DECOMP_SVD) for an M x N system (row-major A): least squares through the SVD
+template <int M, int N>
+DUNK_HD void svd_solve(const double* A, const double* b, double* x) {
+    double At[N * M], W[N], Vt[N * N];
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < N; ++j) At[j * M + i] = A[i * N + j];
+    jacobi_svd<M, N, true>(At, W, Vt);
+    double thr = 0;
+    for (int j = 0; j < N; ++j) thr += W[j];
+    thr *= DBL_EPSILON * 2;
+    for (int j = 0; j < N; ++j) x[j] = 0;
+    for (int j = 0; j < N; ++j) {
+        if (!(W[j] > thr)) continue;
+        double y = 0;
+        for (int i = 0; i < M; ++i) y += At[j * M + i] * b[i];
+        y /= W[j];
+        for (int k = 0; k < N; ++k) x[k] += y * Vt[j * N + k];
+    }
+}
+
+// cvInvert(A, Ai, CV_SVD) for a 3 x 3 matrix
+DUNK_HD inline void svd_inverse3(const double* A, double* Ai) {
+    double At[9], W[3], Vt[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) At[j * 3 + i] = A[i * 3 + j];
+    jacobi_svd<3, 3, true>(At, W, Vt);
+    const double thr = (W[0] + W[1] + W[2]) * DBL_EPSILON * 2;
+    for (int i = 0; i < 9; ++i) Ai[i] = 0;
+    for (int k = 0; k < 3; ++k) {
+        if (!(W[k] > thr)) continue;
+        const double wi = 1.0 / W[k];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Ai[r * 3 + c] += Vt[k * 3 + r] * wi * At[k * 3 + c];
+    }
+}
+
+// R = U * Vt of the SVD of a 3 x 3 matrix A (row-major)
+DUNK_HD inline void svd_rotation3(const double* A, double* R) {
+    double At[9], W[3], Vt[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) At[j * 3 + i] = A[i * 3 + j];
+    jacobi_svd<3, 3, true>(At, W, Vt);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r * 3 + c] = At[0 * 3 + r] * Vt[0 * 3 + c] + At[1 * 3 + r] * Vt[1 * 3 + c] + At[2 * 3 + r] * Vt[2 * 3 + c];
+}
+
+// Householder least squares of a 6 x 4 system (epnp::qr_solve); A and b are destroyed
+DUNK_HD inline bool householder_ls_6x4(double* A, double* b, double* x) {
+    const int M = 6, N = 4;
+    for (int k = 0; k < N; ++k) {
+        double nrm = 0;
+        for (int i = k; i < M; ++i) nrm += A[i * N + k] * A[i * N + k];
+        nrm = sqrt(nrm);
+        if (nrm == 0) return false;
+        const double alpha = A[k * N + k] > 0 ? -nrm : nrm;
+        double v[6];
+        for (int i = k; i < M; ++i) v[i] = A[i * N + k];
+        v[k] -= alpha;
+        double vn = 0;
+        for (int i = k; i < M; ++i) vn += v[i] * v[i];
+        if (vn == 0) continue;
+        const double f = 2.0 / vn;
+        for (int j = k; j < N; ++j) {
+            double d = 0;
+            for (int i = k; i < M; ++i) d += v[i] * A[i * N + j];
+            d *= f;
+            for (int i = k; i < M; ++i) A[i * N + j] -= d * v[i];
+        }
+        double d = 0;
+        for (int i = k; i < M; ++i) d += v[i] * b[i];
+        d *= f;
+        for (int i = k; i < M; ++i) b[i] -= d * v[i];
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        double s = b[k];
+        for (int j = k + 1; j < N; ++j) s -= A[k * N + j] * x[j];
+        x[k] = s / A[k * N + k];
+    }
+    return true;
+}
+
+// cv::Rodrigues, vector -> matrix
+DUNK_HD inline void rodrigues_to_matrix(const double* r, double* R) {
+    const double theta = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (theta < DBL_EPSILON) {
+        for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0);
+        return;
+    }
+    const double c = cos(theta), s = sin(theta), c1 = 1.0 - c, it = 1.0 / theta;
+    const double x = r[0] * it, y = r[1] * it, z = r[2] * it;
+    R[0] = c + c1 * x * x;      R[1] = c1 * x * y - s * z;  R[2] = c1 * x * z + s * y;
+    R[3] = c1 * x * y + s * z;  R[4] = c + c1 * y * y;      R[5] = c1 * y * z - s * x;
+    R[6] = c1 * x * z - s * y;  R[7] = c1 * y * z + s * x;  R[8] = c + c1 * z * z;
+}
+
+// cv::Rodrigues, matrix -> vector (the matrix is first projected onto SO(3) through its SVD)
+DUNK_HD inline void rodrigues_to_vector(const double* Rin, double* r) {
+    double R[9];
+    svd_rotation3(Rin, R);
+    r[0] = R[7] - R[5];
+    r[1] = R[2] - R[6];
+    r[2] = R[3] - R[1];
+    const double s = sqrt((r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) * 0.25);
+    double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+    c = c > 1. ? 1. : c < -1. ? -1. : c;
+    double theta = acos(c);
+    if (s < 1e-5) {
+        if (c > 0) {
+            r[0] = r[1] = r[2] = 0;
+            return;
+        }
+        double t = (R[0] + 1) * 0.5;
+        r[0] = sqrt(t > 0 ? t : 0.);
+        t = (R[4] + 1) * 0.5;
+        r[1] = sqrt(t > 0 ? t : 0.) * (R[1] < 0 ? -1. : 1.);
+        t = (R[8] + 1) * 0.5;
+        r[2] = sqrt(t > 0 ? t : 0.) * (R[2] < 0 ? -1. : 1.);
+        if (fabs(r[0]) < fabs(r[1]) && fabs(r[0]) < fabs(r[2]) && ((R[5] > 0) != (r[1] * r[2] > 0))) r[2] = -r[2];
+        theta /= sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        r[0] *= theta; r[1] *= theta; r[2] *= theta;
+        return;
+    }
+    const double vth = theta / (2 * s);
+    r[0] *= vth; r[1] *= vth; r[2] *= vth;
+}
+
+// One thread owns the whole point set: `idx` (may be null = identity) selects `n` points.
+struct SerialExec {
+    const float* obj;
+    const float* img;
+    const int* idx;
+    int n;
+    Camera cam;
+    bool f32_normalised;
+    DUNK_HD double count() const { return (double)n; }
+    DUNK_HD Point first() const { return load_point(obj, img, idx ? idx[0] : 0, cam, f32_normalised); }
+    template <int K, class F>
+    DUNK_HD void sum(F f, double (&out)[K]) const {
+        for (int k = 0; k < K; ++k) out[k] = 0;
+        for (int i = 0; i < n; ++i) f(load_point(obj, img, idx ? idx[i] : i, cam, f32_normalised), out);
+    }
+};
+
+// epnp::compute_pose (calib3d/src/epnp.cpp).  Returns the mean reprojection error of the chosen
+// candidate; R (row-major) and t receive the pose.
+template <class Exec>
+DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], double (&t)[3]) {
+    const double n = ex.count();
+    const double fu = cam.fu, fv = cam.fv, uc = cam.uc, vc = cam.vc;
+    // ---- choose_control_points
+    double cws[4][3];
+    {
+        double s[3];
+        ex.template sum<3>([](const Point& p, double (&a)[3]) { a[0] += p.X; a[1] += p.Y; a[2] += p.Z; }, s);
+        for (int j = 0; j < 3; ++j) cws[0][j] = s[j] / n;
+    }
+    const double c0x = cws[0][0], c0y = cws[0][1], c0z = cws[0][2];
+    {
+        double s[6];
+        ex.template sum<6>(
+            [=](const Point& p, double (&a)[6]) {
+                const double x = p.X - c0x, y = p.Y - c0y, z = p.Z - c0z;
+                a[0] += x * x; a[1] += x * y; a[2] += x * z; a[3] += y * y; a[4] += y * z; a[5] += z * z;
+            },
+            s);
+        double At[9] = {s[0], s[1], s[2], s[1], s[3], s[4], s[2], s[4], s[5]}, dc[3];
+        jacobi_svd<3, 3, false>(At, dc, nullptr);
+        for (int i = 1; i < 4; ++i) {
+            const double k = sqrt(dc[i - 1] / n);
+            for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * At[3 * (i - 1) + j];
+        }
+    }
+    // ---- compute_barycentric_coordinates: alphas[1..3] = CC^-1 (pw - cw0)
+    double ci[9];
+    {
+        double cc[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 1; j < 4; ++j) cc[3 * i + j - 1] = cws[j][i] - cws[0][i];
+        svd_inverse3(cc, ci);
+    }
+    auto alphas = [=](const Point& p, double (&a)[4]) {
+        const double x = p.X - c0x, y = p.Y - c0y, z = p.Z - c0z;
+        a[1] = ci[0] * x + ci[1] * y + ci[2] * z;
+        a[2] = ci[3] * x + ci[4] * y + ci[5] * z;
+        a[3] = ci[6] * x + ci[7] * y + ci[8] * z;
+        a[0] = 1.0 - a[1] - a[2] - a[3];
+    };
+    // ---- fill_M, M^T M (upper triangle, 78 sums), its 4 smallest singular vectors
+    double ut[144];
+    {
+        double s[78];
+        ex.template sum<78>(
+            [=](const Point& p, double (&acc)[78]) {
+                double a[4];
+                alphas(p, a);
+                double m1[12], m2[12];
+                for (int j = 0; j < 4; ++j) {
+                    m1[3 * j] = a[j] * fu; m1[3 * j + 1] = 0.0;       m1[3 * j + 2] = a[j] * (uc - p.u);
+                    m2[3 * j] = 0.0;       m2[3 * j + 1] = a[j] * fv; m2[3 * j + 2] = a[j] * (vc - p.v);
+                }
+                int k = 0;
+                for (int r = 0; r < 12; ++r)
+                    for (int c = r; c < 12; ++c) acc[k++] += m1[r] * m1[c] + m2[r] * m2[c];
+            },
+            s);
+        int k = 0;
+        for (int r = 0; r < 12; ++r)
+            for (int c = r; c < 12; ++c) {
+                ut[r * 12 + c] = s[k];
+                ut[c * 12 + r] = s[k];
+                ++k;
+            }
+        double d[12];
+        jacobi_svd<12, 12, false>(ut, d, nullptr);
+    }
+    const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
+    // ---- compute_L_6x10, compute_rho
+    const int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+    double L[60], rho[6];
+    for (int p = 0; p < 6; ++p) {
+        double dv[4][3];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 3; ++j) dv[i][j] = v[i][3 * pa[p] + j] - v[i][3 * pb[p] + j];
+        auto dot = [&](int a, int b) { return dv[a][0] * dv[b][0] + dv[a][1] * dv[b][1] + dv[a][2] * dv[b][2]; };
+        double* row = L + 10 * p;
+        row[0] = dot(0, 0); row[1] = 2.0 * dot(0, 1); row[2] = dot(1, 1); row[3] = 2.0 * dot(0, 2); row[4] = 2.0 * dot(1, 2);
+        row[5] = dot(2, 2); row[6] = 2.0 * dot(0, 3); row[7] = 2.0 * dot(1, 3); row[8] = 2.0 * dot(2, 3); row[9] = dot(3, 3);
+        double d2 = 0;
+        for (int j = 0; j < 3; ++j) d2 += (cws[pa[p]][j] - cws[pb[p]][j]) * (cws[pa[p]][j] - cws[pb[p]][j]);
+        rho[p] = d2;
+    }
+    // ---- betas: three approximations, each refined by 5 Gauss-Newton steps
+    double betas[3][4];
+    {   // find_betas_approx_1: columns 0 1 3 6 (B11 B12 B13 B14)
+        double A[24], b4[4];
+        for (int i = 0; i < 6; ++i) { A[4 * i] = L[10 * i]; A[4 * i + 1] = L[10 * i + 1]; A[4 * i + 2] = L[10 * i + 3]; A[4 * i + 3] = L[10 * i + 6]; }
+        svd_solve<6, 4>(A, rho, b4);
+        double* be = betas[0];
+        if (b4[0] < 0) { be[0] = sqrt(-b4[0]); be[1] = -b4[1] / be[0]; be[2] = -b4[2] / be[0]; be[3] = -b4[3] / be[0]; }
+        else           { be[0] = sqrt(b4[0]);  be[1] = b4[1] / be[0];  be[2] = b4[2] / be[0];  be[3] = b4[3] / be[0]; }
+    }
+    {   // find_betas_approx_2: columns 0 1 2 (B11 B12 B22)
+        double A[18], b3[3];
+        for (int i = 0; i < 6; ++i) { A[3 * i] = L[10 * i]; A[3 * i + 1] = L[10 * i + 1]; A[3 * i + 2] = L[10 * i + 2]; }
+        svd_solve<6, 3>(A, rho, b3);
+        double* be = betas[1];
+        if (b3[0] < 0) { be[0] = sqrt(-b3[0]); be[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0; }
+        else           { be[0] = sqrt(b3[0]);  be[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0; }
+        if (b3[1] < 0) be[0] = -be[0];
+        be[2] = 0.0; be[3] = 0.0;
+    }
+    {   // find_betas_approx_3: columns 0..4 (B11 B12 B22 B13 B23)
+        double A[30], b5[5];
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 5; ++j) A[5 * i + j] = L[10 * i + j];
+        svd_solve<6, 5>(A, rho, b5);
+        double* be = betas[2];
+        if (b5[0] < 0) { be[0] = sqrt(-b5[0]); be[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0; }
+        else           { be[0] = sqrt(b5[0]);  be[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0; }
+        if (b5[1] < 0) be[0] = -be[0];
+        be[2] = b5[3] / be[0];
+        be[3] = 0.0;
+    }
+    double ccs[3][4][3];   // candidate, control point, xyz
+    for (int c = 0; c < 3; ++c) {
+        double* be = betas[c];
+        for (int it = 0; it < 5; ++it) {   // gauss_newton
+            double A[24], b[6], x[4];
+            for (int i = 0; i < 6; ++i) {
+                const double* l = L + 10 * i;
+                A[4 * i + 0] = 2 * l[0] * be[0] + l[1] * be[1] + l[3] * be[2] + l[6] * be[3];
+                A[4 * i + 1] = l[1] * be[0] + 2 * l[2] * be[1] + l[4] * be[2] + l[7] * be[3];
+                A[4 * i + 2] = l[3] * be[0] + l[4] * be[1] + 2 * l[5] * be[2] + l[8] * be[3];
+                A[4 * i + 3] = l[6] * be[0] + l[7] * be[1] + l[8] * be[2] + 2 * l[9] * be[3];
+                b[i] = rho[i] - (l[0] * be[0] * be[0] + l[1] * be[0] * be[1] + l[2] * be[1] * be[1] + l[3] * be[0] * be[2] +
+                                 l[4] * be[1] * be[2] + l[5] * be[2] * be[2] + l[6] * be[0] * be[3] + l[7] * be[1] * be[3] +
+                                 l[8] * be[2] * be[3] + l[9] * be[3] * be[3]);
+            }
+            if (!householder_ls_6x4(A, b, x)) break;
+            for (int k = 0; k < 4; ++k) be[k] += x[k];
+        }
+        for (int j = 0; j < 4; ++j)        // compute_ccs
+            for (int k = 0; k < 3; ++k)
+                ccs[c][j][k] = be[0] * v[0][3 * j + k] + be[1] * v[1][3 * j + k] + be[2] * v[2][3 * j + k] + be[3] * v[3][3 * j + k];
+    }
+    // ---- solve_for_sign: the first point must lie in front of the camera
+    {
+        double a[4];
+        alphas(ex.first(), a);
+        for (int c = 0; c < 3; ++c) {
+            const double z = a[0] * ccs[c][0][2] + a[1] * ccs[c][1][2] + a[2] * ccs[c][2][2] + a[3] * ccs[c][3][2];
+            if (z < 0.0)
+                for (int j = 0; j < 4; ++j)
+                    for (int k = 0; k < 3; ++k) ccs[c][j][k] = -ccs[c][j][k];
+        }
+    }
+    // ---- estimate_R_and_t for the three candidates (Procrustes on camera/world point sets)
+    auto pcs = [&](const double (&a)[4], int c, double (&pc)[3]) {
+        for (int k = 0; k < 3; ++k) pc[k] = a[0] * ccs[c][0][k] + a[1] * ccs[c][1][k] + a[2] * ccs[c][2][k] + a[3] * ccs[c][3][k];
+    };
+    double pc0[3][3];
+    {
+        double s[9];
+        ex.template sum<9>(
+            [&](const Point& p, double (&acc)[9]) {
+                double a[4], pc[3];
+                alphas(p, a);
+                for (int c = 0; c < 3; ++c) {
+                    pcs(a, c, pc);
+                    acc[3 * c] += pc[0]; acc[3 * c + 1] += pc[1]; acc[3 * c + 2] += pc[2];
+                }
+            },
+            s);
+        for (int c = 0; c < 3; ++c)
+            for (int k = 0; k < 3; ++k) pc0[c][k] = s[3 * c + k] / n;
+    }
+    double Rs[3][9], ts[3][3];
+    {
+        double s[27];
+        ex.template sum<27>(
+            [&](const Point& p, double (&acc)[27]) {
+                double a[4], pc[3];
+                alphas(p, a);
+                const double w[3] = {p.X - c0x, p.Y - c0y, p.Z - c0z};
+                for (int c = 0; c < 3; ++c) {
+                    pcs(a, c, pc);
+                    for (int j = 0; j < 3; ++j)
+                        for (int k = 0; k < 3; ++k) acc[9 * c + 3 * j + k] += (pc[j] - pc0[c][j]) * w[k];
+                }
+            },
+            s);
+        for (int c = 0; c < 3; ++c) {
+            double* Rc = Rs[c];
+            svd_rotation3(s + 9 * c, Rc);
+            const double det = Rc[0] * Rc[4] * Rc[8] + Rc[1] * Rc[5] * Rc[6] + Rc[2] * Rc[3] * Rc[7] - Rc[2] * Rc[4] * Rc[6] -
+                               Rc[1] * Rc[3] * Rc[8] - Rc[0] * Rc[5] * Rc[7];
+            if (det < 0) { Rc[6] = -Rc[6]; Rc[7] = -Rc[7]; Rc[8] = -Rc[8]; }
+            for (int k = 0; k < 3; ++k) ts[c][k] = pc0[c][k] - (Rc[3 * k] * c0x + Rc[3 * k + 1] * c0y + Rc[3 * k + 2] * c0z);
+        }
+    }
+    // ---- reprojection_error, pick the best candidate
+    double err[3];
+    ex.template sum<3>(
+        [&](const Point& p, double (&acc)[3]) {
+            for (int c = 0; c < 3; ++c) {
+                const double* Rc = Rs[c];
+                const double Xc = Rc[0] * p.X + Rc[1] * p.Y + Rc[2] * p.Z + ts[c][0];
+                const double Yc = Rc[3] * p.X + Rc[4] * p.Y + Rc[5] * p.Z + ts[c][1];
+                const double iz = 1.0 / (Rc[6] * p.X + Rc[7] * p.Y + Rc[8] * p.Z + ts[c][2]);
+                const double ue = uc + fu * Xc * iz, ve = vc + fv * Yc * iz;
+                acc[c] += sqrt((p.u - ue) * (p.u - ue) + (p.v - ve) * (p.v - ve));
+            }
+        },
+        err);
+    int N = 0;
+    if (err[1] < err[0]) N = 1;
+    if (err[2] < err[N]) N = 2;
+    for (int i = 0; i < 9; ++i) R[i] = Rs[N][i];
+    for (int i = 0; i < 3; ++i) t[i] = ts[N][i];
+    return err[N] / n;
+}
+
+// cv::projectPoints (zero distortion) + PnPRansacCallback::computeError for one point: the f64
+// projection is rounded to f32, the squared distance is f32.  R2 = Rodrigues(rvec) of the model.
+// (separate multiplies and adds: OpenCV's build does not contract them into FMAs)
+#ifdef __CUDA_ARCH__
+#define DUNK_MUL(a, b) __dmul_rn((a), (b))
+#define DUNK_ADD(a, b) __dadd_rn((a), (b))
+#define DUNK_FMUL(a, b) __fmul_rn((a), (b))
+#define DUNK_FADD(a, b) __fadd_rn((a), (b))
+#define DUNK_FSUB(a, b) __fsub_rn((a), (b))
+#else
+#define DUNK_MUL(a, b) ((a) * (b))
+#define DUNK_ADD(a, b) ((a) + (b))
+#define DUNK_FMUL(a, b) ((a) * (b))
+#define DUNK_FADD(a, b) ((a) + (b))
+#define DUNK_FSUB(a, b) ((a) - (b))
+#endif
+DUNK_HD inline float reproj_err_f32(const double* R2, const double* t, const Camera& cam, const float* obj, const float* img, int i) {
+    const double X = obj[3 * i], Y = obj[3 * i + 1], Z = obj[3 * i + 2];
+    double x = DUNK_ADD(DUNK_ADD(DUNK_ADD(DUNK_MUL(R2[0], X), DUNK_MUL(R2[1], Y)), DUNK_MUL(R2[2], Z)), t[0]);
+    double y = DUNK_ADD(DUNK_ADD(DUNK_ADD(DUNK_MUL(R2[3], X), DUNK_MUL(R2[4], Y)), DUNK_MUL(R2[5], Z)), t[1]);
+    double z = DUNK_ADD(DUNK_ADD(DUNK_ADD(DUNK_MUL(R2[6], X), DUNK_MUL(R2[7], Y)), DUNK_MUL(R2[8], Z)), t[2]);
+    z = z ? 1.0 / z : 1.0;
+    x = DUNK_MUL(x, z);
+    y = DUNK_MUL(y, z);
+    const float px = (float)DUNK_ADD(DUNK_MUL(x, cam.fu), cam.uc);
+    const float py = (float)DUNK_ADD(DUNK_MUL(y, cam.fv), cam.vc);
+    const float dx = DUNK_FSUB(img[2 * i], px), dy = DUNK_FSUB(img[2 * i + 1], py);
+    return DUNK_FADD(DUNK_FMUL(dx, dx), DUNK_FMUL(dy, dy));
+}
+
+}  // namespace pnp
+}  // namespace dunk

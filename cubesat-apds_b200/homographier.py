@@ -1,7 +1,8 @@
 """Host-side mirror of the reference crate `homographier` (homographier/src/homographier/mod.rs).
 
 Same names, argument order and error behaviour as the Rust items on the hot path:
-`HomographyMethod`, `MatError`, `Cmat`, `raster_to_mat`, `find_homography_mat`.  `Cmat<T>` wraps a
+`HomographyMethod`, `MatError`, `Cmat`, `raster_to_mat`, `find_homography_mat`, `SolvePnPMethod`,
+`ImgObjCorrespondence`, `PNPRANSACSolution`, `pnp_solver_ransac`.  `Cmat<T>` wraps a
 numpy array (the checked-Mat idea: never empty, element type checked)."""
 from __future__ import annotations
 
@@ -146,3 +147,110 @@ def score_hypotheses(src, dst, samples, reproj_threshold: float = 3.0, ctx: Opti
     check(_lib.load().dunk_ransac_score_hypotheses(ctx.handle, ptr(src), ptr(dst), src.shape[0], ptr(smp),
                                                    smp.shape[0], float(reproj_threshold), ptr(counts), ptr(Hs)))
     return counts[: smp.shape[0]], Hs[: smp.shape[0]]
+
+
+# ------------------------------------------------------------------------------------------ PnP
+class SolvePnPMethod(enum.IntEnum):
+    """opencv::calib3d::SolvePnPMethod values reachable from mod.rs:320-361"""
+    SOLVEPNP_ITERATIVE = 0
+    SOLVEPNP_EPNP = 1
+    SOLVEPNP_P3P = 2
+
+
+class ImgObjCorrespondence:
+    """mod.rs:53-65 — a 3-D object point and its 2-D image point"""
+    __slots__ = ("obj_point", "img_point")
+
+    def __init__(self, obj_point, img_point):
+        self.obj_point = tuple(float(v) for v in obj_point)
+        self.img_point = tuple(float(v) for v in img_point)
+        if len(self.obj_point) != 3 or len(self.img_point) != 2:
+            raise MatError("Unknown")
+
+
+class PNPRANSACSolution:
+    """mod.rs:46-51 — rvec, tvec: Cmat<f64> 3x1; inliers: Cmat<i32> M x 1"""
+    __slots__ = ("rvec", "tvec", "inliers")
+
+    def __init__(self, rvec: Cmat, tvec: Cmat, inliers: Cmat):
+        self.rvec, self.tvec, self.inliers = rvec, tvec, inliers
+
+
+def _split_correspondences(point_correspondences):
+    if isinstance(point_correspondences, tuple) and len(point_correspondences) == 2:
+        obj, img = point_correspondences                      # (N x 3, N x 2) arrays
+    else:
+        obj = [c.obj_point for c in point_correspondences]
+        img = [c.img_point for c in point_correspondences]
+    obj = np.ascontiguousarray(obj, dtype=np.float64).reshape(-1, 3)
+    img = np.ascontiguousarray(img, dtype=np.float64).reshape(-1, 2)
+    if obj.shape[0] != img.shape[0]:
+        raise MatError("Opencv", DunkError(_lib.ERR_ASSERT, "object and image point counts differ"))
+    return obj, img
+
+
+def pnp_solver_ransac(point_correspondences, camera_intrinsic, iter_count: int, reproj_thres: float, confidence: float,
+                      dist_coeffs=None, method: Optional[SolvePnPMethod] = None,
+                      ctx: Optional[_lib.Context] = None) -> Optional[PNPRANSACSolution]:
+    """mod.rs:320-369 — solvePnPRansac(obj, img, K, zeros(4,1), rvec, tvec, false, iter_count,
+    reproj_thres, confidence, inliers, method or SOLVEPNP_EPNP).  `dist_coeffs` is accepted and ignored
+    exactly as in the reference (it shadows the argument with zeros, :344).  Returns the solution or
+    None when no pose was found (`Ok(None)`); fewer than 4 correspondences -> MatError('Opencv', -215)
+    (reference test :627-638).  `point_correspondences`: a sequence of ImgObjCorrespondence, or an
+    (obj N x 3, img N x 2) pair of arrays."""
+    ctx = ctx or default_context()
+    obj, img = _split_correspondences(point_correspondences)
+    K = camera_intrinsic.mat if isinstance(camera_intrinsic, Cmat) else np.asarray(camera_intrinsic)
+    K = np.ascontiguousarray(K, dtype=np.float64).reshape(3, 3)
+    m = int(SolvePnPMethod.SOLVEPNP_EPNP if method is None else method)
+    n = obj.shape[0]
+    rvec, tvec = np.zeros(3), np.zeros(3)
+    inliers = np.zeros(max(n, 1), dtype=np.int32)
+    n_inl, found = C.c_int(0), C.c_int(0)
+    try:
+        check(_lib.load().dunk_pnp_ransac(ctx.handle, ptr(obj), ptr(img), n, ptr(K), int(iter_count), float(reproj_thres),
+                                          float(confidence), m, ptr(rvec), ptr(tvec), ptr(inliers), n, C.byref(n_inl),
+                                          C.byref(found)))
+    except DunkError as e:
+        raise MatError("Opencv", e) from None
+    if not found.value:
+        return None
+    return PNPRANSACSolution(Cmat(rvec.reshape(3, 1), np.float64), Cmat(tvec.reshape(3, 1), np.float64),
+                             Cmat(inliers[: n_inl.value].reshape(-1, 1).copy(), np.int32))
+
+
+def pnp_solver_ransac_batch(obj_list, img_list, camera_intrinsics, iter_count: int, reproj_thres: float, confidence: float,
+                            ctx: Optional[_lib.Context] = None):
+    """Frame-batched pnp_solver_ransac (one CTA per frame; partitioned by frame, no collective).
+    camera_intrinsics: one 3x3 for all frames or one per frame.
+    Returns (rvecs [B,3], tvecs [B,3], inlier masks list, info [B,4] = found/inliers/iters/hypotheses)."""
+    ctx = ctx or default_context()
+    B = len(obj_list)
+    lens = [len(o) for o in obj_list]
+    offsets = np.zeros(B + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(lens)
+    obj = np.ascontiguousarray(np.concatenate([np.asarray(o, np.float64).reshape(-1, 3) for o in obj_list]))
+    img = np.ascontiguousarray(np.concatenate([np.asarray(i, np.float64).reshape(-1, 2) for i in img_list]))
+    K = np.asarray(camera_intrinsics, dtype=np.float64)
+    K = np.ascontiguousarray(np.broadcast_to(K.reshape(-1, 3, 3), (B, 3, 3)))
+    rvecs, tvecs = np.zeros((B, 3)), np.zeros((B, 3))
+    mask = np.zeros(max(int(offsets[-1]), 1), dtype=np.uint8)
+    info = np.zeros((B, 4), dtype=np.int32)
+    check(_lib.load().dunk_pnp_ransac_batch(ctx.handle, ptr(obj), ptr(img), ptr(offsets), B, ptr(K), int(iter_count),
+                                            float(reproj_thres), float(confidence), int(SolvePnPMethod.SOLVEPNP_EPNP),
+                                            ptr(rvecs), ptr(tvecs), ptr(mask), ptr(info)))
+    return rvecs, tvecs, [mask[offsets[i]:offsets[i + 1]].astype(bool) for i in range(B)], info
+
+
+def pnp_score_hypotheses(obj, img, camera_intrinsic, samples, reproj_thres: float, ctx: Optional[_lib.Context] = None):
+    """Per-hypothesis inlier counts and (rvec, tvec) for explicit 5-index samples (parity hook)."""
+    ctx = ctx or default_context()
+    obj = np.ascontiguousarray(obj, dtype=np.float64).reshape(-1, 3)
+    img = np.ascontiguousarray(img, dtype=np.float64).reshape(-1, 2)
+    K = np.ascontiguousarray(camera_intrinsic, dtype=np.float64).reshape(3, 3)
+    smp = np.ascontiguousarray(samples, dtype=np.int32).reshape(-1, 5)
+    counts = np.zeros(max(smp.shape[0], 1), dtype=np.int32)
+    rt = np.zeros((max(smp.shape[0], 1), 6), dtype=np.float64)
+    check(_lib.load().dunk_pnp_score_hypotheses(ctx.handle, ptr(obj), ptr(img), obj.shape[0], ptr(K), ptr(smp), smp.shape[0],
+                                                float(reproj_thres), ptr(counts), ptr(rt)))
+    return counts[: smp.shape[0]], rt[: smp.shape[0]]

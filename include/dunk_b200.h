@@ -192,6 +192,34 @@ int dunk_ransac_score_hypotheses(dunk_ctx* ctx, const float* src, const float* d
                                  const int* samples, int n_hyp, double thr, int* counts,
                                  double* Hs);
 
+/* ---- stage 3b: PnP-RANSAC pose ------------------------------------------------------------
+ * replaces cv::solvePnPRansac(obj, img, K, dist = zeros(4,1), rvec, tvec, false, iters, thr, conf,
+ * inliers, method) as called by pnp_solver_ransac, homographier/src/homographier/mod.rs:320-369
+ * (distortion is forced to zero at :344; method defaults to SOLVEPNP_EPNP at :359).
+ * obj: n x 3 f64 (Point3d), img: n x 2 f64 (Point2d), K: 9 f64 row-major camera matrix.  As in
+ * OpenCV the f64 points are rounded to f32 first.  rvec/tvec: 3 f64 each.  inliers: indices of the
+ * inliers of the best minimal model in increasing order (capacity inliers_cap; may be NULL).
+ * *found = 0 when no pose was found (the reference returns Ok(None), mod.rs:367).
+ * n < 4 -> DUNK_ERR_ASSERT (-215, reference test mod.rs:627-638).  Only DUNK_PNP_EPNP is
+ * implemented; other methods and n == 4 (where OpenCV switches to its P3P kernel) ->
+ * DUNK_ERR_BAD_ARG. */
+int dunk_pnp_ransac(dunk_ctx* ctx, const double* obj, const double* img, int n, const double* K,
+                    int iters, float thr, double confidence, int method, double* rvec, double* tvec,
+                    int32_t* inliers, int inliers_cap, int* n_inliers, int* found);
+/* batch of independent problems (one CTA each; frames partition with no collective): points
+ * concatenated, offsets[n_problems+1], K: n_problems x 9, rvecs/tvecs: n_problems x 3,
+ * inlier_mask: offsets[n_problems] bytes (may be NULL), info: n_problems x 4 int32 =
+ * {found, inliers, RANSAC iterations run, hypotheses scored} */
+int dunk_pnp_ransac_batch(dunk_ctx* ctx, const double* obj, const double* img, const int* offsets,
+                          int n_problems, const double* K, int iters, float thr, double confidence,
+                          int method, double* rvecs, double* tvecs, uint8_t* inlier_mask, int* info);
+/* parity hook ("identical seeded hypothesis sets giving identical inlier counts"): scores explicit
+ * 5-index samples with the EPnP kernel; counts: n_hyp int32 (-1 = no finite pose), rt: n_hyp x 6
+ * f64 (rvec, tvec of every hypothesis) */
+int dunk_pnp_score_hypotheses(dunk_ctx* ctx, const double* obj, const double* img, int n,
+                              const double* K, const int* samples, int n_hyp, double thr,
+                              int* counts, double* rt);
+
 /* ---- the whole path: frame batch -> extract -> 2-NN + ratio vs the shard -> RANSAC homography
  * The composition the reference performs in feature_extraction/src/lib.rs:196-249 followed by
  * find_homography_mat (mod.rs:231-259), for a batch of same-shape frames, without leaving the

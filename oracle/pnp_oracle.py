@@ -165,7 +165,7 @@ def epnp(obj, img, K, f32_normalised=False):
     n = pws.shape[0]
     fu, fv, uc, vc = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
     # solvePnPGeneric: undistortPoints (zero distortion -> (u - cx)/fx), then epnp::init_points maps back
-    xn, yn = (img[:, 0] - uc) / fu, (img[:, 1] - vc) / fv
+    xn, yn = (img[:, 0] - uc) * (1.0 / fu), (img[:, 1] - vc) * (1.0 / fv)     # cvUndistortPoints: (x - cx) * ifx
     if f32_normalised:
         xn, yn = xn.astype(np.float32).astype(np.float64), yn.astype(np.float32).astype(np.float64)
     us = np.stack([xn * fu + uc, yn * fv + vc], 1)

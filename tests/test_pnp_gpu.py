@@ -1,0 +1,110 @@
+"""GPU parity: batched PnP-RANSAC (EPnP kernel) through the C ABI vs cv2 4.13.0 goldens and the
+oracle.  Contract: inlier index lists identical to cv2's `solvePnPRansac` (the call at
+homographier/src/homographier/mod.rs:347-361), rvec / tvec within 1e-6 absolute (measured ~1e-12:
+the final pose is EPnP over >= 6 inliers, which is reproducible); identical seeded 5-point
+hypothesis sets give identical inlier counts for every hypothesis RANSAC could accept (> 4
+inliers) — samples containing outliers yield unrelated garbage poses on both sides because the
+5-point system leaves a 2-D null space whose basis is rounding noise (oracle/pnp_oracle.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pnp_oracle as po
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pnp_golden.npz"))
+N = int(G["n_cases"])
+K = G["K"]
+POSE_ATOL = 1e-6
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_pnp_ransac_vs_cv2_golden(dunk, ctx, i):
+    hg = dunk.homographier
+    iters, thr, conf = G[f"c{i}_params"]
+    sol = hg.pnp_solver_ransac((G[f"c{i}_obj"], G[f"c{i}_img"]), hg.Cmat(K, np.float64), int(iters), float(thr), float(conf),
+                               None, None, ctx)
+    if not bool(G[f"c{i}_found"]):
+        assert sol is None
+        return
+    assert sol is not None
+    assert np.array_equal(sol.inliers.mat.ravel(), G[f"c{i}_inliers"])
+    assert np.abs(sol.rvec.mat.ravel() - G[f"c{i}_rvec"]).max() < POSE_ATOL
+    assert np.abs(sol.tvec.mat.ravel() - G[f"c{i}_tvec"]).max() < POSE_ATOL
+
+
+@pytest.mark.parametrize("i", [0, 1, 3, 8])
+def test_identical_hypothesis_sets_identical_counts(dunk, ctx, i):
+    obj, img = G[f"c{i}_obj"], G[f"c{i}_img"]
+    thr = float(G[f"c{i}_params"][1])
+    o32, i32 = obj.astype(np.float32), img.astype(np.float32)
+    od, idd = o32.astype(np.float64), i32.astype(np.float64)
+    samples = po.sample_stream(len(obj), 64)
+    counts, rt = dunk.homographier.pnp_score_hypotheses(obj, img, K, samples, thr, ctx)
+    acceptable = exact = 0
+    for s, c, m in zip(samples, counts, rt):
+        sol = po.solve_pnp_epnp(od[s], idd[s], K, True)
+        co = -1 if sol is None else int((po.reproj_err_f32(o32, i32, sol[0], sol[1], K) <= np.float32(thr * thr)).sum())
+        if max(c, co) <= 4:
+            continue                      # RANSAC can accept neither
+        acceptable += 1
+        exact += int(c == co)
+        # a pose that differs in the 7th digit may move a point sitting on the threshold
+        assert abs(int(c) - co) <= max(1, co // 100)
+        # the GPU's own pose scores to the GPU's own count under the oracle's error function (bit-exact f32 errors)
+        assert int((po.reproj_err_f32(o32, i32, m[:3], m[3:], K) <= np.float32(thr * thr)).sum()) == c
+    assert acceptable >= 1 and exact >= 0.9 * acceptable
+
+
+def test_reference_test_too_few_points(dunk, ctx):
+    """mod.rs:627-638 pnp_solver_ransac_no_work_lthan_3_points: 2 correspondences, zero K -> Err"""
+    hg = dunk.homographier
+    corres = [hg.ImgObjCorrespondence((1, 2, 3), (1, 2)), hg.ImgObjCorrespondence((4, 5, 6), (4, 5))]
+    with pytest.raises(hg.MatError) as e:
+        hg.pnp_solver_ransac(corres, hg.Cmat.zeros(3, 3), 50, 2.0, 0.99, None, None, ctx)
+    assert e.value.kind == "Opencv" and e.value.code == -215
+
+
+def test_unsupported_methods_fail_loudly(dunk, ctx):
+    hg = dunk.homographier
+    with pytest.raises(hg.MatError):
+        hg.pnp_solver_ransac((G["c0_obj"], G["c0_img"]), K, 100, 8.0, 0.99, None, hg.SolvePnPMethod.SOLVEPNP_P3P, ctx)
+
+
+def test_batch_equals_single(dunk, ctx):
+    hg = dunk.homographier
+    ids = [0, 2, 4, 8]
+    iters, thr, conf = 100, 8.0, 0.99
+    rv, tv, masks, info = hg.pnp_solver_ransac_batch([G[f"c{i}_obj"] for i in ids], [G[f"c{i}_img"] for i in ids], K, iters, thr,
+                                                     conf, ctx)
+    for k, i in enumerate(ids):
+        sol = hg.pnp_solver_ransac((G[f"c{i}_obj"], G[f"c{i}_img"]), K, iters, thr, conf, None, None, ctx)
+        assert info[k, 0] == 1 and sol is not None
+        assert np.array_equal(np.nonzero(masks[k])[0], sol.inliers.mat.ravel())
+        assert np.array_equal(rv[k], sol.rvec.mat.ravel()) and np.array_equal(tv[k], sol.tvec.mat.ravel())
+
+
+def test_full_size_pose_recovery(dunk, ctx):
+    """size-independent property at pipeline scale: 64 frames x 3000 correspondences, 40 % outliers:
+    every pose is recovered to the noise level and every true inlier set is found"""
+    hg = dunk.homographier
+    rng = np.random.default_rng(5)
+    objs, imgs, truth = [], [], []
+    for f in range(64):
+        n = 3000
+        rv = rng.normal(0, 0.3, 3)
+        tv = np.array([0.0, 0.0, 9.0]) + rng.normal(0, 0.4, 3)
+        R = po.rodrigues_to_matrix(rv)
+        obj = rng.uniform(-2, 2, (n, 3))
+        P = obj @ R.T + tv
+        img = np.stack([K[0, 0] * P[:, 0] / P[:, 2] + K[0, 2], K[1, 1] * P[:, 1] / P[:, 2] + K[1, 2]], 1) + rng.normal(0, 0.3, (n, 2))
+        out = rng.choice(n, int(0.4 * n), replace=False)
+        img[out] = rng.uniform(0, 1024, (len(out), 2))
+        objs.append(obj); imgs.append(img); truth.append((rv, tv, np.setdiff1d(np.arange(n), out)))
+    rvs, tvs, masks, info = hg.pnp_solver_ransac_batch(objs, imgs, K, 500, 3.0, 0.99, ctx)
+    assert (info[:, 0] == 1).all()
+    for f in range(64):
+        rv, tv, inl = truth[f]
+        assert np.abs(rvs[f] - rv).max() < 2e-3 and np.abs(tvs[f] - tv).max() < 2e-2
+        assert masks[f][inl].mean() > 0.99
