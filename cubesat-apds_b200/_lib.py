@@ -39,6 +39,16 @@ REGISTRATION_DTYPE = np.dtype(
     [("H", "<f8", (9,)), ("found", "<i4"), ("inliers", "<i4"), ("matches", "<i4"), ("keypoints", "<i4"),
      ("ransac_iters", "<i4"), ("hypotheses", "<i4")]
 )
+IMAGE_DTYPE = np.dtype([("id", "<i4"), ("x_start", "<i4"), ("y_start", "<i4"), ("x_end", "<i4"), ("y_end", "<i4"),
+                        ("level_of_detail", "<i4")])
+
+
+class RowFilter(C.Structure):
+    """DunkRowFilter (include/dunk_b200.h)"""
+    _fields_ = [("image_id", C.c_int32), ("level_of_detail", C.c_int32), ("use_box", C.c_int32), ("x_start", C.c_float),
+                ("y_start", C.c_float), ("x_end", C.c_float), ("y_end", C.c_float)]
+
+
 TOP2_DTYPE = np.dtype([("d1", "<u4"), ("i1", "<u4"), ("d2", "<u4"), ("i2", "<u4")])
 assert REGISTRATION_DTYPE.itemsize == 96 and KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16
 
@@ -90,6 +100,14 @@ SIGNATURES = {
     "dunk_db_append_random": (_i, [_vp, _i64, _u64]),
     "dunk_db_size": (_i64, [_vp]),
     "dunk_db_read": (_i, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "dunk_db_create_image": (_i, [_vp, _i, _i, _i, _i, _i, _pi]),
+    "dunk_db_read_image": (_i, [_vp, _i, _vp]),
+    "dunk_db_find_images": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _pi]),
+    "dunk_db_image_count": (_i, [_vp]),
+    "dunk_db_select": (_i, [_vp, _vp, _i64, C.POINTER(_vp)]),
+    "dunk_db_read_ids": (_i, [_vp, _i64, _i64, _vp]),
+    "dunk_db_save": (_i, [_vp, C.c_char_p]),
+    "dunk_db_load": (_i, [_vp, C.c_char_p, _i64, C.POINTER(_vp)]),
     "dunk_db_match": (_i, [_vp, _vp, _i, _f, _vp, _i, _pi]),
     "dunk_db_knn2": (_i, [_vp, _vp, _i, _u32, _vp]),
     "dunk_db_knn2_dev": (_i, [_vp, _i, _vp, _i, _u32, _vp]),
@@ -116,6 +134,8 @@ SIGNATURES = {
     "dunk_find_homography": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _pi]),
     "dunk_find_homography_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "dunk_ransac_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _vp, _vp]),
+    "dunk_warp_perspective": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "dunk_warp_perspective_batch_dev": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "dunk_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _i, _pi, _pi]),
     "dunk_pnp_ransac_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _vp]),
     "dunk_pnp_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp]),

@@ -15,7 +15,6 @@ namespace {
 
 constexpr int kBX = 32, kBY = 8;           // thread block 32 x 8
 constexpr int kTW = 64, kTH = 32;          // generic stencil tile
-constexpr int kFedT = 64;                  // FED tile (square)
 constexpr int kFedMaxK = 8;                // FED steps fused per launch
 constexpr int kNBins = 300;
 
@@ -280,66 +279,159 @@ k_prep_level(const float* __restrict__ Lt, size_t lt_stride, int W, int H, Gauss
         }
 }
 
-// ---- FED: K explicit diffusion steps per launch, temporally blocked in shared memory ------------
+// ---- FED: K explicit diffusion steps per launch, temporally blocked, register-resident patches ----
+// The smem tile is always kFedS x kFedS cells; a launch of K steps produces the inner
+// (kFedS - 2K)^2 cells.  Each of the 16 x 16 threads owns a 5 x 5 patch in registers together
+// with the conductivity sums on its 60 cell boundaries (constant over the K steps), so a step only
+// exchanges patch perimeters through shared memory (ping-pong, one barrier per step).
+// Arithmetic is OpenCV's nld_step_scalar, f32 without FMA contraction:
+//   Lstep = 0.5 tau (((xpos + xneg) + ypos) + yneg),  xpos = (c + c_E)(L_E - L), ...
+// Every boundary flux f = (c_a + c_b)(L_b - L_a) is computed once and used by both cells:
+// xneg of the right-hand cell is exactly -f (IEEE negation is exact), so the result is bit-identical
+// to the per-pixel formula while doing half the multiplies.
 struct FedSteps {
     int k;
     float step[kFedMaxK];   // tau * 0.5
 };
 
-__global__ void __launch_bounds__(kBX* kBY)
+constexpr int kFedS = 80;     // smem tile edge = 16 threads x 5 cells
+constexpr int kFedP = 5;      // patch edge
+
+__global__ void __launch_bounds__(256, 2)
 k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout, size_t out_stride,
       const float* __restrict__ Lflow, size_t flow_stride, int W, int H, FedSteps fs) {
     extern __shared__ float smem[];
+    float* bufA = smem;
+    float* bufB = smem + kFedS * kFedS;
     const int K = fs.k;
-    const int S = kFedT + 2 * K;          // smem tile edge
-    float* A = smem;
-    float* B = smem + S * S;
-    float* C = smem + 2 * S * S;
+    const int T = kFedS - 2 * K;
     const int f = blockIdx.z;
     const float* lin = Lin + (size_t)f * in_stride;
     const float* lfl = Lflow + (size_t)f * flow_stride;
-    const int x0 = blockIdx.x * kFedT - K, y0 = blockIdx.y * kFedT - K;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int ly = ty; ly < S; ly += kBY)
-        for (int lx = tx; lx < S; lx += kBX) {
-            const int gx = x0 + lx, gy = y0 + ly;
-            float a = 0.f, c = 0.f;
-            if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-                a = lin[(size_t)gy * W + gx];
-                c = lfl[(size_t)gy * W + gx];
-            }
-            A[ly * S + lx] = a;
-            C[ly * S + lx] = c;
-        }
+    const int x0 = blockIdx.x * T - K, y0 = blockIdx.y * T - K;
+    const int tid = threadIdx.y * 16 + threadIdx.x;
+    // 50 independent 4-byte async copies per thread (zero-filled outside the image): the whole
+    // 51 KB tile is in flight at once, no registers are staged
+#pragma unroll
+    for (int it = 0; it < kFedS * kFedS / 256; ++it) {
+        const int i = tid + it * 256;
+        const int r = i / kFedS, c = i - r * kFedS;
+        const int gx = x0 + c, gy = y0 + r;
+        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+        const size_t o = in ? (size_t)gy * W + gx : 0;
+        const unsigned nbytes = in ? 4u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(bufA + i)),
+                     "l"(lin + o), "r"(nbytes) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(bufB + i)),
+                     "l"(lfl + o), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
+    const int px = threadIdx.x * kFedP, py = threadIdx.y * kFedP;
+    auto in_img = [&](int lx, int ly) {
+        const int gx = x0 + lx, gy = y0 + ly;
+        return lx >= 0 && lx < kFedS && ly >= 0 && ly < kFedS && gx >= 0 && gx < W && gy >= 0 && gy < H;
+    };
+    float L[kFedP][kFedP];
+    float CE[kFedP][kFedP + 1];   // CE[r][j]: boundary between columns px+j-1 | px+j of row py+r
+    float CS[kFedP + 1][kFedP];   // CS[i][c]: boundary between rows py+i-1 | py+i of column px+c
+    unsigned corner = 0;          // cells of this patch that are image corners (Lstep forced to 0)
+#pragma unroll
+    for (int r = 0; r < kFedP; ++r)
+#pragma unroll
+        for (int c = 0; c < kFedP; ++c) {
+            L[r][c] = bufA[(py + r) * kFedS + px + c];
+            const int gx = x0 + px + c, gy = y0 + py + r;
+            if ((gy == 0 || gy == H - 1) && (gx == 0 || gx == W - 1)) corner |= 1u << (r * kFedP + c);
+        }
+#pragma unroll
+    for (int r = 0; r < kFedP; ++r)
+#pragma unroll
+        for (int j = 0; j <= kFedP; ++j) {
+            const int cl = px + j - 1, cr = px + j, ly = py + r;
+            float v = 0.f;
+            if (in_img(cl, ly) && in_img(cr, ly)) v = __fadd_rn(bufB[ly * kFedS + cl], bufB[ly * kFedS + cr]);
+            CE[r][j] = v;
+        }
+#pragma unroll
+    for (int i = 0; i <= kFedP; ++i)
+#pragma unroll
+        for (int c = 0; c < kFedP; ++c) {
+            const int lu = py + i - 1, ld = py + i, lx = px + c;
+            float v = 0.f;
+            if (in_img(lx, lu) && in_img(lx, ld)) v = __fadd_rn(bufB[lu * kFedS + lx], bufB[ld * kFedS + lx]);
+            CS[i][c] = v;
+        }
+    __syncthreads();   // bufB (conductivities) becomes the second ping-pong buffer
+    float* cur = bufA;
+    float* nxt = bufB;
+    // halo indices clamped into the tile: an out-of-tile neighbour always meets a zero conductivity sum
+    const int xl = px > 0 ? px - 1 : 0, xr = px + kFedP < kFedS ? px + kFedP : kFedS - 1;
+    const int yu = py > 0 ? py - 1 : 0, yd = py + kFedP < kFedS ? py + kFedP : kFedS - 1;
     for (int s = 0; s < K; ++s) {
         const float step = fs.step[s];
-        const int lo = s + 1, hi = S - 2 - s;   // cells whose 4 neighbours are still valid
-        for (int ly = lo + ty; ly <= hi; ly += kBY)
-            for (int lx = lo + tx; lx <= hi; lx += kBX) {
-                const int gx = x0 + lx, gy = y0 + ly;
-                if (gx < 0 || gx >= W || gy < 0 || gy >= H) continue;
-                const int i = ly * S + lx;
-                const float L = A[i], c = C[i];
-                // nld_step_scalar: ((xpos + xneg) + ypos) + yneg, border terms dropped, f32, no FMA
-                const float xpos = gx + 1 < W ? __fmul_rn(__fadd_rn(c, C[i + 1]), __fsub_rn(A[i + 1], L)) : 0.f;
-                const float xneg = gx > 0 ? __fmul_rn(__fadd_rn(c, C[i - 1]), __fsub_rn(A[i - 1], L)) : 0.f;
-                const float ypos = gy + 1 < H ? __fmul_rn(__fadd_rn(c, C[i + S]), __fsub_rn(A[i + S], L)) : 0.f;
-                const float yneg = gy > 0 ? __fmul_rn(__fadd_rn(c, C[i - S]), __fsub_rn(A[i - S], L)) : 0.f;
-                float r = __fadd_rn(__fadd_rn(__fadd_rn(xpos, xneg), ypos), yneg);
-                r = __fmul_rn(r, step);
-                if ((gy == 0 || gy == H - 1) && (gx == 0 || gx == W - 1)) r = 0.f;   // corners are written 0
-                B[i] = __fadd_rn(L, r);
-            }
-        __syncthreads();
-        float* t = A; A = B; B = t;
-    }
-    float* lout = Lout + (size_t)f * out_stride;
-    for (int ly = ty; ly < kFedT; ly += kBY)
-        for (int lx = tx; lx < kFedT; lx += kBX) {
-            const int gx = x0 + K + lx, gy = y0 + K + ly;
-            if (gx < W && gy < H) lout[(size_t)gy * W + gx] = A[(ly + K) * S + (lx + K)];
+        float fE[kFedP][kFedP + 1], fS[kFedP + 1][kFedP];
+#pragma unroll
+        for (int r = 0; r < kFedP; ++r) {
+            const float hl = cur[(py + r) * kFedS + xl], hr = cur[(py + r) * kFedS + xr];
+            fE[r][0] = __fmul_rn(CE[r][0], __fsub_rn(L[r][0], hl));
+#pragma unroll
+            for (int j = 1; j < kFedP; ++j) fE[r][j] = __fmul_rn(CE[r][j], __fsub_rn(L[r][j], L[r][j - 1]));
+            fE[r][kFedP] = __fmul_rn(CE[r][kFedP], __fsub_rn(hr, L[r][kFedP - 1]));
         }
+#pragma unroll
+        for (int c = 0; c < kFedP; ++c) {
+            const float hu = cur[yu * kFedS + px + c], hd = cur[yd * kFedS + px + c];
+            fS[0][c] = __fmul_rn(CS[0][c], __fsub_rn(L[0][c], hu));
+#pragma unroll
+            for (int i = 1; i < kFedP; ++i) fS[i][c] = __fmul_rn(CS[i][c], __fsub_rn(L[i][c], L[i - 1][c]));
+            fS[kFedP][c] = __fmul_rn(CS[kFedP][c], __fsub_rn(hd, L[kFedP - 1][c]));
+        }
+        if (corner == 0) {
+#pragma unroll
+            for (int r = 0; r < kFedP; ++r)
+#pragma unroll
+                for (int c = 0; c < kFedP; ++c) {
+                    const float sum = __fsub_rn(__fadd_rn(__fsub_rn(fE[r][c + 1], fE[r][c]), fS[r + 1][c]), fS[r][c]);
+                    L[r][c] = __fadd_rn(L[r][c], __fmul_rn(sum, step));
+                }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kFedP; ++r)
+#pragma unroll
+                for (int c = 0; c < kFedP; ++c) {
+                    float sum = __fsub_rn(__fadd_rn(__fsub_rn(fE[r][c + 1], fE[r][c]), fS[r + 1][c]), fS[r][c]);
+                    sum = __fmul_rn(sum, step);
+                    if (corner >> (r * kFedP + c) & 1u) sum = 0.f;   // the four image corners are written 0
+                    L[r][c] = __fadd_rn(L[r][c], sum);
+                }
+        }
+        // publish the patch perimeter for the neighbours' next step
+#pragma unroll
+        for (int c = 0; c < kFedP; ++c) {
+            nxt[py * kFedS + px + c] = L[0][c];
+            nxt[(py + kFedP - 1) * kFedS + px + c] = L[kFedP - 1][c];
+        }
+#pragma unroll
+        for (int r = 1; r < kFedP - 1; ++r) {
+            nxt[(py + r) * kFedS + px] = L[r][0];
+            nxt[(py + r) * kFedS + px + kFedP - 1] = L[r][kFedP - 1];
+        }
+        __syncthreads();
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    // full patch -> smem -> coalesced store of the valid inner window
+#pragma unroll
+    for (int r = 0; r < kFedP; ++r)
+#pragma unroll
+        for (int c = 0; c < kFedP; ++c) nxt[(py + r) * kFedS + px + c] = L[r][c];
+    __syncthreads();
+    float* lout = Lout + (size_t)f * out_stride;
+    for (int i = tid; i < T * T; i += 256) {
+        const int r = i / T, c = i - r * T;
+        const int gx = x0 + K + c, gy = y0 + K + r;
+        if (gx < W && gy < H) lout[(size_t)gy * W + gx] = nxt[(r + K) * kFedS + c + K];
+    }
 }
 
 // ---- fused Hessian: Lsmooth -> Lx, Ly (kept for orientation/descriptor) and Ldet ------------------
@@ -497,8 +589,7 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
     gaussian_kernel(5, 1.0, g5.k);
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             3 * (kFedT + 2 * kFedMaxK) * (kFedT + 2 * kFedMaxK) * 4);
+        cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFedS * kFedS * 4);
         cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr = true;
     }
@@ -562,7 +653,7 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
         const LevelInfo& e = lt.lv[i];
         const LevelInfo& p = lt.lv[i - 1];
         const int n = e.n_tau;
-        const int m = div_up(n, kFedMaxK);
+        const int m = div_up(n, kFedMaxK);   // launches; the n steps are split as evenly as possible
         float* P = ws.Lt + e.plane_off;   // final home of this level's Lt (stride pyr)
         float* Q = ws.Ltmp;               // ping-pong partner (stride plane)
         const float* init;
@@ -594,18 +685,21 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
         if ((rc = hessian(i, ws.Lsmooth, plane))) return rc;
         const float* in = init;
         size_t in_stride = init_stride;
+        int done = 0;
         for (int j = 0; j < m; ++j) {
             FedSteps fs{};
-            fs.k = std::min(kFedMaxK, n - j * kFedMaxK);
-            for (int k = 0; k < fs.k; ++k) fs.step[k] = e.tau[j * kFedMaxK + k] * 0.5f;
+            fs.k = n / m + (j < n % m ? 1 : 0);
+            for (int k = 0; k < fs.k; ++k) fs.step[k] = e.tau[done + k] * 0.5f;
+            done += fs.k;
             const bool out_is_P = ((m - 1 - j) % 2 == 0);
             float* out = out_is_P ? P : Q;
             const size_t out_stride = out_is_P ? pyr : plane;
-            const int S = kFedT + 2 * fs.k;
-            const dim3 fgrid(div_up(e.w, kFedT), div_up(e.h, kFedT), frames);
+            const int T = kFedS - 2 * fs.k;
+            const dim3 fgrid(div_up(e.w, T), div_up(e.h, T), frames);
             {
                 ProfScope ps(ctx, st, "scale.fed", (double)frames * e.w * e.h * 12);
-                k_fed<<<fgrid, blk, (size_t)3 * S * S * 4, st>>>(in, in_stride, out, out_stride, ws.Lflow, plane, e.w, e.h, fs);
+                k_fed<<<fgrid, dim3(16, 16), (size_t)2 * kFedS * kFedS * 4, st>>>(in, in_stride, out, out_stride, ws.Lflow, plane,
+                                                                                 e.w, e.h, fs);
                 DUNK_KERNEL_CHECK(ctx);
             }
             in = out;

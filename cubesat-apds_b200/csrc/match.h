@@ -1,5 +1,6 @@
 // Internal declarations for the Hamming matcher (not part of the ABI).
 #pragma once
+#include <vector>
 #include "ctx.h"
 
 // One HBM-resident shard of the reference descriptor database: SoA columns of the reference's
@@ -12,6 +13,14 @@ struct dunk_db {
     uint4* desc64 = nullptr;        // capacity x 64 B descriptor rows
     DunkKeyPoint* kps = nullptr;    // capacity x 28 B (x, y, size, angle, response, octave, class_id)
     int32_t* image_id = nullptr;    // capacity
+    int32_t* row_id = nullptr;      // capacity; only in DBs produced by dunk_db_select (the `id` column,
+                                    // = 1 + row index in the source DB); a base DB's id is 1 + row index
+    // `ref_image` table (feature_database/src/models.rs:5-15): tiny, host-resident; ids are 1-based
+    // like a Postgres SERIAL.  image_lod_dev mirrors level_of_detail for the select kernel.
+    std::vector<DunkImage> images;
+    int32_t* image_lod_dev = nullptr;
+    int64_t image_lod_cap = 0;
+    bool image_lod_dirty = true;
     std::mutex mu;
 };
 

@@ -210,6 +210,8 @@ void dunk_db_destroy(dunk_db* db) {
     if (db->desc64) cudaFree(db->desc64);
     if (db->kps) cudaFree(db->kps);
     if (db->image_id) cudaFree(db->image_id);
+    if (db->row_id) cudaFree(db->row_id);
+    if (db->image_lod_dev) cudaFree(db->image_lod_dev);
     delete db;
 }
 

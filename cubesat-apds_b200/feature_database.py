@@ -20,17 +20,131 @@ from ._lib import DMATCH_DTYPE, KEYPOINT_DTYPE, TOP2_DTYPE, DunkError, check, pt
 # keypointdb.rs:12
 OPENCV_KEYPOINT_LIMIT = 2 ** 18 - 1
 
+# models::Keypoint (models.rs:30-41) as a record array: what the read_keypoints_* calls return
+DB_KEYPOINT_DTYPE = np.dtype([("id", "<i4"), ("x_coord", "<f4"), ("y_coord", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                              ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4"), ("descriptor", "u1", (_lib.DESC_BYTES,)),
+                              ("image_id", "<i4")])
+
+
+class NotFound(KeyError):
+    """diesel::result::Error::NotFound"""
+
 
 class DescriptorDatabase:
     """One HBM-resident shard of the `keypoint` table (schema.rs:27-40)."""
 
     def __init__(self, ctx: Optional[_lib.Context] = None, capacity: int = 1 << 20,
-                 desc_bytes: int = _lib.DESC_BYTES):
+                 desc_bytes: int = _lib.DESC_BYTES, _handle=None):
         self.ctx = ctx or _lib.default_context()
         self.desc_bytes = desc_bytes
+        if _handle is not None:
+            self._h = _handle
+            return
         h = C.c_void_p()
         check(_lib.load().dunk_db_create(self.ctx.handle, int(capacity), int(desc_bytes), C.byref(h)))
         self._h = h
+
+    # -- ImageDatabase (feature_database/src/imagedb.rs:14-77): the ref_image table
+    def create_image(self, x_start: int, y_start: int, x_end: int, y_end: int, level_of_detail: int) -> int:
+        """ImageDatabase::create_image with Image::One(InsertImage{..}) -> new id (1-based)"""
+        out = C.c_int(0)
+        check(_lib.load().dunk_db_create_image(self.handle, int(x_start), int(y_start), int(x_end), int(y_end),
+                                               int(level_of_detail), C.byref(out)))
+        return out.value
+
+    def read_image_from_id(self, id: int) -> np.void:
+        out = np.zeros(1, dtype=_lib.IMAGE_DTYPE)
+        try:
+            check(_lib.load().dunk_db_read_image(self.handle, int(id), ptr(out)))
+        except DunkError as e:
+            if e.code == _lib.ERR_OUT_OF_RANGE:
+                raise NotFound(id) from None
+            raise
+        return out[0]
+
+    def _find_images(self, use_box, x_start, y_start, x_end, y_end, lod) -> List[int]:
+        cap = max(1, int(_lib.load().dunk_db_image_count(self.handle)))
+        ids = np.zeros(cap, dtype=np.int32)
+        n = C.c_int(0)
+        check(_lib.load().dunk_db_find_images(self.handle, int(use_box), int(x_start), int(y_start), int(x_end), int(y_end),
+                                              int(lod), ptr(ids), cap, C.byref(n)))
+        return ids[: n.value].tolist()
+
+    def find_images_from_dimensions(self, x_start: int, y_start: int, x_end: int, y_end: int, level_of_detail: int) -> List[int]:
+        """imagedb.rs:39-56"""
+        return self._find_images(1, x_start, y_start, x_end, y_end, level_of_detail)
+
+    def find_images_from_lod(self, level_of_detail: int) -> List[int]:
+        """imagedb.rs:58-66"""
+        return self._find_images(0, 0, 0, 0, 0, level_of_detail)
+
+    # -- KeypointDatabase keyed reads (keypointdb.rs:38-90): filter, ORDER BY response DESC, LIMIT 2^18-1
+    def select(self, image_id: int = -1, level_of_detail: int = -1, box=None,
+               limit: int = OPENCV_KEYPOINT_LIMIT) -> "DescriptorDatabase":
+        """The rows of a keyed read as a new HBM-resident shard (to match against, or to read back)."""
+        f = _lib.RowFilter(int(image_id), int(level_of_detail), 0 if box is None else 1, *(box or (0.0, 0.0, 0.0, 0.0)))
+        h = C.c_void_p()
+        check(_lib.load().dunk_db_select(self.handle, C.byref(f), int(limit), C.byref(h)))
+        return DescriptorDatabase(self.ctx, desc_bytes=self.desc_bytes, _handle=h)
+
+    def rows(self) -> np.ndarray:
+        """every row as models::Keypoint records"""
+        n = len(self)
+        out = np.zeros(n, dtype=DB_KEYPOINT_DTYPE)
+        if n == 0:
+            return out
+        d, k, im = self.read_rows(0, n)
+        ids = np.zeros(n, dtype=np.int32)
+        check(_lib.load().dunk_db_read_ids(self.handle, 0, n, ptr(ids)))
+        out["id"], out["descriptor"], out["image_id"] = ids, d, im
+        out["x_coord"], out["y_coord"] = k["x"], k["y"]
+        for name in ("size", "angle", "response", "octave", "class_id"):
+            out[name] = k[name]
+        return out
+
+    def _read(self, **kw) -> np.ndarray:
+        sub = self.select(**kw)
+        try:
+            return sub.rows()
+        finally:
+            sub.close()
+
+    def read_keypoints_from_image_id(self, image_id: int) -> np.ndarray:
+        """keypointdb.rs:38-49"""
+        return self._read(image_id=image_id)
+
+    def read_keypoints_from_lod(self, level_of_detail: int) -> np.ndarray:
+        """keypointdb.rs:51-66"""
+        return self._read(level_of_detail=level_of_detail)
+
+    def read_keypoints_from_coordinates(self, x_start: float, y_start: float, x_end: float, y_end: float,
+                                        level_of_detail: int) -> np.ndarray:
+        """keypointdb.rs:68-90 (bounds are floor()/ceil()-ed, inclusive)"""
+        return self._read(level_of_detail=level_of_detail, box=(float(x_start), float(y_start), float(x_end), float(y_end)))
+
+    def read_keypoint_from_id(self, id: int) -> np.void:
+        """keypointdb.rs:28-36 — ids are 1 + row index"""
+        if not 1 <= id <= len(self):
+            raise NotFound(id)
+        d, k, im = self.read_rows(id - 1, 1)
+        out = np.zeros(1, dtype=DB_KEYPOINT_DTYPE)
+        out["id"], out["descriptor"], out["image_id"] = id, d, im
+        out["x_coord"], out["y_coord"] = k["x"], k["y"]
+        for name in ("size", "angle", "response", "octave", "class_id"):
+            out[name] = k[name]
+        return out[0]
+
+    # -- flat dump / load
+    def save(self, path: str):
+        check(_lib.load().dunk_db_save(self.handle, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, ctx: Optional[_lib.Context] = None, min_capacity: int = 0) -> "DescriptorDatabase":
+        ctx = ctx or _lib.default_context()
+        h = C.c_void_p()
+        check(_lib.load().dunk_db_load(ctx.handle, str(path).encode(), int(min_capacity), C.byref(h)))
+        db = cls(ctx, _handle=h)
+        return db
 
     @property
     def handle(self):

@@ -2,7 +2,7 @@
 
 Same names, argument order and error behaviour as the Rust items on the hot path:
 `HomographyMethod`, `MatError`, `Cmat`, `raster_to_mat`, `find_homography_mat`, `SolvePnPMethod`,
-`ImgObjCorrespondence`, `PNPRANSACSolution`, `pnp_solver_ransac`.  `Cmat<T>` wraps a
+`ImgObjCorrespondence`, `PNPRANSACSolution`, `pnp_solver_ransac`, `warp_image_perspective`.  `Cmat<T>` wraps a
 numpy array (the checked-Mat idea: never empty, element type checked)."""
 from __future__ import annotations
 
@@ -113,6 +113,30 @@ def find_homography_mat(input: np.ndarray, reference: np.ndarray,
     if method in (HomographyMethod.RANSAC, HomographyMethod.LMEDS):
         out_mask = Cmat(mask[: src.shape[0]].reshape(-1, 1), np.uint8)
     return Cmat(H.reshape(3, 3), np.float64), out_mask
+
+
+def warp_image_perspective(src: Cmat, m, size: Optional[Tuple[int, int]] = None, ctx: Optional[_lib.Context] = None) -> Cmat:
+    """mod.rs:271-300 — warpPerspective(src, M, size or src.size(), INTER_LINEAR, BORDER_CONSTANT,
+    Scalar(1,1,1,1)).  `size` is (width, height) like Size2i.  8-bit images with 1..4 channels.
+    m must be 3x3 (anything else is an OpenCV assertion, -215)."""
+    ctx = ctx or default_context()
+    a = src.mat if isinstance(src, Cmat) else np.asarray(src)
+    M = m.mat if isinstance(m, Cmat) else np.asarray(m)
+    if M.shape != (3, 3):
+        raise MatError("Opencv", DunkError(_lib.ERR_ASSERT, "warpPerspective: M must be 3x3"))
+    if a.dtype != np.uint8 or a.ndim not in (2, 3):
+        raise MatError("Opencv", DunkError(_lib.ERR_ASSERT, f"warp_image_perspective: {a.dtype} / {a.ndim}-d images unsupported"))
+    a = np.ascontiguousarray(a)
+    rows, cols = a.shape[:2]
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    w, h = (cols, rows) if size is None else (int(size[0]), int(size[1]))
+    out = np.empty((h, w) if a.ndim == 2 else (h, w, ch), dtype=np.uint8)
+    Md = np.ascontiguousarray(M, dtype=np.float64)
+    try:
+        check(_lib.load().dunk_warp_perspective(ctx.handle, ptr(a), rows, cols, ch, cols * ch, ptr(Md), h, w, None, ptr(out)))
+    except DunkError as e:
+        raise MatError("Opencv", e) from None
+    return Cmat(out, np.uint8)
 
 
 def find_homography_batch(src_list, dst_list, reproj_threshold: float = 3.0,

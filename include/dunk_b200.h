@@ -133,6 +133,45 @@ int dunk_db_match(dunk_db* db, const uint8_t* query, int nq, float ratio, DunkDM
 /* local top-2 of host queries against the shard (for an external merge), out: nq records */
 int dunk_db_knn2(dunk_db* db, const uint8_t* query, int nq, uint32_t index_base, DunkTop2* out);
 
+/* ---- feature_database: ref_image table, keyed reads, flat dump / load ------
+ * models::Image (feature_database/src/models.rs:5-15): the tile a keypoint row belongs to. */
+typedef struct DunkImage {
+    int32_t id;                 /* 1-based, assigned by dunk_db_create_image (Postgres SERIAL) */
+    int32_t x_start, y_start, x_end, y_end;
+    int32_t level_of_detail;
+} DunkImage;
+/* ImageDatabase::create_image (imagedb.rs:14-30): returns the new id through *id_out */
+int dunk_db_create_image(dunk_db* db, int32_t x_start, int32_t y_start, int32_t x_end, int32_t y_end,
+                         int32_t level_of_detail, int32_t* id_out);
+/* ImageDatabase::read_image_from_id (imagedb.rs:32-37); unknown id -> DUNK_ERR_OUT_OF_RANGE */
+int dunk_db_read_image(dunk_db* db, int32_t id, DunkImage* out);
+/* ImageDatabase::find_images_from_dimensions / find_images_from_lod (imagedb.rs:39-66): ids of the
+ * images of `level_of_detail` whose extent intersects the box (use_box = 0: every image of the LoD) */
+int dunk_db_find_images(dunk_db* db, int use_box, int32_t x_start, int32_t y_start, int32_t x_end,
+                        int32_t y_end, int32_t level_of_detail, int32_t* ids, int cap, int* n_out);
+int dunk_db_image_count(dunk_db* db);
+/* KeypointDatabase::read_keypoints_from_{image_id, lod, coordinates} (keypointdb.rs:38-90):
+ * SELECT rows WHERE [image_id = f.image_id] [AND ref_image.level_of_detail = f.level_of_detail]
+ * [AND x_coord >= floor(x_start) AND x_coord <= ceil(x_end) AND y likewise]
+ * ORDER BY response DESC LIMIT `limit` (the reference passes 2^18 - 1).  Runs on the device
+ * (predicate, stable descending radix sort on the response, gather) and returns the result as a new
+ * HBM-resident dunk_db (read it with dunk_db_read / dunk_db_read_ids, or match against it).
+ * A negative image_id / level_of_detail disables that predicate. */
+typedef struct DunkRowFilter {
+    int32_t image_id;
+    int32_t level_of_detail;
+    int32_t use_box;
+    float x_start, y_start, x_end, y_end;
+} DunkRowFilter;
+int dunk_db_select(dunk_db* db, const DunkRowFilter* filter, int64_t limit, dunk_db** out);
+/* the `id` column of rows [first, first+n): 1 + row index in the DB the rows were inserted into */
+int dunk_db_read_ids(dunk_db* db, int64_t first, int64_t n, int32_t* ids);
+/* flat binary dump / load of a shard (header, ref_image table, SoA columns as they lie in HBM), so a
+ * multi-GB reference DB is built once (dunk_db_append_tiles) and re-loaded at H2D speed.
+ * load: capacity = max(rows in file, min_capacity_rows). */
+int dunk_db_save(dunk_db* db, const char* path);
+int dunk_db_load(dunk_ctx* ctx, const char* path, int64_t min_capacity_rows, dunk_db** out);
+
 /* ---- device-pointer variants (async on slot's stream; no sync, no host copies) ---- */
 /* queries: nq x 64-B padded rows in device memory; top2_dev: nq DunkTop2 records */
 int dunk_db_knn2_dev(dunk_db* db, int slot, const void* query64_dev, int nq, uint32_t index_base,
@@ -219,6 +258,22 @@ int dunk_pnp_ransac_batch(dunk_ctx* ctx, const double* obj, const double* img, c
 int dunk_pnp_score_hypotheses(dunk_ctx* ctx, const double* obj, const double* img, int n,
                               const double* K, const int* samples, int n_hyp, double thr,
                               int* counts, double* rt);
+
+/* ---- warp_image_perspective -----------------------------------------------
+ * replaces cv::warpPerspective(src, dst, M, size, INTER_LINEAR, BORDER_CONSTANT, Scalar(1,1,1,1)) as
+ * called by warp_image_perspective, homographier/src/homographier/mod.rs:271-300, for 8-bit images
+ * with 1..4 interleaved channels; bit-exact with OpenCV 4.13 (1/32-pixel grid, 15-bit weights).
+ * M: 9 f64 row-major, src -> dst (inverted internally like OpenCV without WARP_INVERSE_MAP).
+ * border_value: 4 f64 (NULL = the reference's 1,1,1,1).  dst: out_rows x out_cols x channels. */
+int dunk_warp_perspective(dunk_ctx* ctx, const uint8_t* src, int rows, int cols, int channels,
+                          int row_stride_bytes, const double* M, int out_rows, int out_cols,
+                          const double* border_value, uint8_t* dst);
+/* device-resident batch: n outputs of the same source, one matrix each (M: n x 9, host), written
+ * back to back at dst_dev; async on the slot's stream */
+int dunk_warp_perspective_batch_dev(dunk_ctx* ctx, int slot, const void* src_dev, int rows, int cols,
+                                    int channels, int row_stride_bytes, const double* M, int n,
+                                    int out_rows, int out_cols, const double* border_value,
+                                    void* dst_dev);
 
 /* ---- the whole path: frame batch -> extract -> 2-NN + ratio vs the shard -> RANSAC homography
  * The composition the reference performs in feature_extraction/src/lib.rs:196-249 followed by

@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ by running the reference's OpenCV entry
 points (through cv2, the same C++ library the `opencv` crate binds) with the reference's exact
-arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|akaze|pnp|all]
+arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|akaze|pnp|warp|all]
 The OpenCV version is recorded in every file (parity is defined against that version)."""
 import os
 import sys
@@ -196,6 +196,28 @@ def make_pnp():
     print("pnp_golden.npz written")
 
 
+def make_warp():
+    """cv2.warpPerspective(src, M, size, INTER_LINEAR, BORDER_CONSTANT, (1,1,1,1)) — mod.rs:286-294"""
+    import synthdata
+    out = {"opencv_version": np.array(cv2.__version__)}
+    gray = synthdata.synth_image(200, 264, 3)
+    bgra = np.stack([gray, gray[::-1], gray[:, ::-1], np.full_like(gray, 255)], -1).copy()
+    Hs = [np.eye(3), H_TRUE, np.array([[1.2, 0.3, -50], [-0.2, 0.9, 80], [3e-4, -2e-4, 1.0]]),
+          np.array([[0.5, 0, 10.25], [0, 0.5, 3.5], [0, 0, 1.0]]), np.array([[0.9, -0.4, 200.], [0.4, 0.9, -100], [1e-5, 1e-5, 1]]),
+          np.array([[1.0, 0, 0.5], [0, 1.0, 0.5], [0, 0, 1.0]])]
+    out["gray"], out["bgra"], out["H"] = gray, bgra, np.stack(Hs)
+    sizes = [(264, 200), (300, 170), (97, 333)]
+    out["sizes"] = np.array(sizes)
+    for i, H in enumerate(Hs):
+        for j, (w, h) in enumerate(sizes):
+            out[f"g{i}_{j}"] = cv2.warpPerspective(gray, H, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
+                                                   borderValue=(1, 1, 1, 1))
+        out[f"c{i}"] = cv2.warpPerspective(bgra, H, (264, 200), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT,
+                                           borderValue=(1, 1, 1, 1))
+    np.savez_compressed(os.path.join(HERE, "warp_golden.npz"), **out)
+    print("warp_golden.npz written")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("match", "all"):
@@ -206,3 +228,5 @@ if __name__ == "__main__":
         make_akaze()
     if what in ("pnp", "all") and "make_pnp" in globals():
         make_pnp()
+    if what in ("warp", "all") and "make_warp" in globals():
+        make_warp()
