@@ -136,6 +136,12 @@ SIGNATURES = {
     "dunk_ransac_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _vp, _vp]),
     "dunk_warp_perspective": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "dunk_warp_perspective_batch_dev": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "dunk_band_merger": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp]),
+    "dunk_band_merger_dev": (_i, [_vp, _i, _vp, _vp, _vp, _i64, _vp, _i, _vp]),
+    "dunk_raster_to_mat": (_i, [_vp, _vp, _i, _i, _vp]),
+    "dunk_elevation_create": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
+    "dunk_elevation_destroy": (None, [_vp]),
+    "dunk_world_coordinates": (_i, [_vp, _vp, _vp, _i64, _vp, _pi]),
     "dunk_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _i, _pi, _pi]),
     "dunk_pnp_ransac_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _vp]),
     "dunk_pnp_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp]),

@@ -252,6 +252,52 @@ class DescriptorDatabase:
         return out
 
 
+class Geotransform:
+    """`feature_database::elevationdb::geotransform` + `elevation` (elevationdb.rs:12-104, 182-244): the
+    "dataset" and "elevation" GDAL geotransforms and the elevation raster, resident in HBM, so that
+    `get_world_coordinates` (pixel -> ECEF object point for pnp_solver_ransac) runs batched on the GPU."""
+
+    def __init__(self, dataset_transform, elevation_transform=None, heights: Optional[np.ndarray] = None,
+                 ctx: Optional[_lib.Context] = None):
+        self.ctx = ctx or _lib.default_context()
+        gd = np.ascontiguousarray(dataset_transform, dtype=np.float64).reshape(6)
+        ge = None if elevation_transform is None else np.ascontiguousarray(elevation_transform, dtype=np.float64).reshape(6)
+        hh, xs, ys = None, 0, 0
+        if heights is not None:
+            hh = np.ascontiguousarray(heights, dtype=np.float64)
+            ys, xs = hh.shape
+        h = C.c_void_p()
+        check(_lib.load().dunk_elevation_create(self.ctx.handle, ptr(gd), ptr(ge), ptr(hh), xs, ys, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.load().dunk_elevation_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def world_coordinates(self, x, y):
+        """batched get_world_coordinates: returns (xyz [n, 3] f64, number of points without an elevation sample)"""
+        px = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        py = np.ascontiguousarray(y, dtype=np.float64).ravel()
+        out = np.empty((px.shape[0], 3), dtype=np.float64)
+        miss = C.c_int(0)
+        check(_lib.load().dunk_world_coordinates(self._h, ptr(px), ptr(py), px.shape[0], ptr(out), C.byref(miss)))
+        return out, miss.value
+
+    def get_world_coordinates(self, x: float, y: float):
+        """elevationdb.rs:64-90 — one point; a missing elevation sample is the reference's diesel NotFound"""
+        xyz, miss = self.world_coordinates([x], [y])
+        if miss:
+            raise NotFound((x, y))
+        return tuple(float(v) for v in xyz[0])
+
+
 def merge_top2(ctx: _lib.Context, parts: Sequence[np.ndarray]) -> np.ndarray:
     """(distance, index)-lexicographic merge of per-shard top-2 records on the GPU — the step
     that follows the allgather in the sharded matcher.  Host arrays in/out."""

@@ -275,6 +275,35 @@ int dunk_warp_perspective_batch_dev(dunk_ctx* ctx, int slot, const void* src_dev
                                     int out_rows, int out_cols, const double* border_value,
                                     void* dst_dev);
 
+/* ---- the steps either side of the path ------------------------------------
+ * band_merger + f32_to_u8 + gamma_correction, geotiff_extractor/src/image_extractor/mod.rs:346-378,
+ * 402-422: three f32 bands (n samples each) -> n RGBA8 pixels.  Per channel: NaN -> 0;
+ * f = (v - min) / (max - min) in f32; f outside 0..=1 -> 0; else round(powf(f, 1/2.2) * 255).
+ * Alpha = 0 where all three bands are NaN, else 255.  min_max: {red_min, red_max, green_min,
+ * green_max, blue_min, blue_max} (f64, cast to f32 as the reference does).  bgra != 0 writes the
+ * channels in the BGRA order raster_to_mat produces (homographier mod.rs:183-220), so the output
+ * feeds dunk_akaze_extract (channels = 4) directly. */
+int dunk_band_merger(dunk_ctx* ctx, const float* red, const float* green, const float* blue, int64_t n,
+                     const double* min_max, int bgra, uint8_t* out_rgba);
+int dunk_band_merger_dev(dunk_ctx* ctx, int slot, const void* red_dev, const void* green_dev,
+                         const void* blue_dev, int64_t n, const double* min_max, int bgra, void* out_dev);
+/* raster_to_mat, homographier/src/homographier/mod.rs:183-220: w*h RGBA8 -> BGRA8 (Cmat<Vec4b>) */
+int dunk_raster_to_mat(dunk_ctx* ctx, const uint8_t* rgba, int w, int h, uint8_t* bgra);
+/* geotransform::get_world_coordinates, feature_database/src/elevationdb.rs:64-104: reference-image
+ * pixel (x, y) -> GDAL geotransform "dataset" -> (lon, lat) -> nearest sample of the elevation raster
+ * through the inverted "elevation" geotransform (row id = round(y) * x_size + round(x) + 1) ->
+ * EPSG:4326 -> EPSG:4978 (WGS-84 geodetic -> ECEF metres): the object points of pnp_solver_ransac.
+ * gt_elevation / heights may be NULL: height 0, as the reference falls back to (:76-79).
+ * heights: y_size x x_size f64 (the `elevation` table in row-id order), kept in HBM by the handle. */
+typedef struct dunk_elevation dunk_elevation;
+int dunk_elevation_create(dunk_ctx* ctx, const double* gt_dataset, const double* gt_elevation,
+                          const double* heights, int x_size, int y_size, dunk_elevation** out);
+void dunk_elevation_destroy(dunk_elevation* e);
+/* xyz: n x 3 f64.  Points whose elevation sample does not exist (diesel NotFound in the reference)
+ * get NaN coordinates and are counted in *n_missing (may be NULL). */
+int dunk_world_coordinates(dunk_elevation* e, const double* px, const double* py, int64_t n,
+                           double* xyz, int* n_missing);
+
 /* ---- the whole path: frame batch -> extract -> 2-NN + ratio vs the shard -> RANSAC homography
  * The composition the reference performs in feature_extraction/src/lib.rs:196-249 followed by
  * find_homography_mat (mod.rs:231-259), for a batch of same-shape frames, without leaving the
