@@ -98,6 +98,7 @@ SIGNATURES = {
     "dunk_db_destroy": (None, [_vp]),
     "dunk_db_append": (_i, [_vp, _vp, _vp, _vp, _i64]),
     "dunk_db_append_random": (_i, [_vp, _i64, _u64]),
+    "dunk_db_append_random_at": (_i, [_vp, _i64, _u64, _u64]),
     "dunk_db_size": (_i64, [_vp]),
     "dunk_db_read": (_i, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "dunk_db_create_image": (_i, [_vp, _i, _i, _i, _i, _i, _pi]),

@@ -245,38 +245,96 @@ k_halfsample(const float* __restrict__ src, size_t src_stride, int sw, int sh, f
 }
 
 // ---- per level: Lsmooth = Gauss5(Lt_init), Lflow = PM-G2(Scharr(Lsmooth), k) --------------------
+// Same arithmetic as gauss5_tile + scharr_at above; all tile extents are compile-time, every stage is
+// a flat 256-thread loop, and tiles that do not touch the image border skip the clamp / reflect work.
 __global__ void __launch_bounds__(kBX* kBY)
 k_prep_level(const float* __restrict__ Lt, size_t lt_stride, int W, int H, Gauss5 g,
              const float* __restrict__ kcontrast, float kscale, float* __restrict__ Lsmooth,
              float* __restrict__ Lflow, size_t plane_stride) {
-    __shared__ float A[kTH + 6][kTW + 6];
-    __shared__ float T[kTH + 6][kTW + 2];
-    __shared__ float B[kTH + 2][kTW + 2];
+    constexpr int AW = kTW + 6, AH = kTH + 6;     // clamped input, halo 3
+    constexpr int TWd = kTW + 2;                  // row-filtered, halo 1 in x, 3 in y
+    constexpr int BW = kTW + 2, BH = kTH + 2;     // Gauss5 output, halo 1
+    __shared__ float A[AH * AW];
+    __shared__ float T[AH * TWd];
+    __shared__ float B[BH * BW];
     const int f = blockIdx.z;
     const float* src = Lt + (size_t)f * lt_stride;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    for (int ly = ty; ly < kTH + 6; ly += kBY)
-        for (int lx = tx; lx < kTW + 6; lx += kBX)
-            A[ly][lx] = src[(size_t)clampi(y0 + ly - 3, 0, H - 1) * W + clampi(x0 + lx - 3, 0, W - 1)];
+    const int tid = threadIdx.y * kBX + threadIdx.x;
+    const bool interior = x0 >= 3 && y0 >= 3 && x0 + kTW + 3 <= W && y0 + kTH + 3 <= H;
+    if (interior) {
+        const float* base = src + (size_t)(y0 - 3) * W + (x0 - 3);
+#pragma unroll
+        for (int it = 0; it < (AH * AW + 255) / 256; ++it) {
+            const int i = tid + it * 256;
+            if (i < AH * AW) {
+                const int ly = i / AW, lx = i - ly * AW;
+                A[i] = base[(size_t)ly * W + lx];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < (AH * AW + 255) / 256; ++it) {
+            const int i = tid + it * 256;
+            if (i < AH * AW) {
+                const int ly = i / AW, lx = i - ly * AW;
+                A[i] = src[(size_t)clampi(y0 + ly - 3, 0, H - 1) * W + clampi(x0 + lx - 3, 0, W - 1)];
+            }
+        }
+    }
     __syncthreads();
-    gauss5_tile<kTW, kTH>(A, T, B, g, x0, y0, W, H);
+#pragma unroll
+    for (int it = 0; it < (AH * TWd + 255) / 256; ++it) {
+        const int i = tid + it * 256;
+        if (i < AH * TWd) {
+            const int ly = i / TWd, lx = i - ly * TWd;
+            const float* a = &A[ly * AW + lx + 2];
+            T[i] = g.k[0] * a[0] + g.k[1] * (a[-1] + a[1]) + g.k[2] * (a[-2] + a[2]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < (BH * BW + 255) / 256; ++it) {
+        const int i = tid + it * 256;
+        if (i < BH * BW) {
+            const int ly = i / BW, lx = i - ly * BW;
+            const float* t = &T[(ly + 2) * TWd + lx];
+            B[i] = g.k[0] * t[0] + g.k[1] * (t[-TWd] + t[TWd]) + g.k[2] * (t[-2 * TWd] + t[2 * TWd]);
+        }
+    }
+    __syncthreads();
+    if (!(x0 >= 1 && y0 >= 1 && x0 + kTW + 1 <= W && y0 + kTH + 1 <= H)) {
+        // B(lx, ly) sits at global (x0-1+lx, y0-1+ly); cells outside the image take the reflect-101 value
+        // (what Scharr's BORDER_DEFAULT sees)
+        for (int i = tid; i < BH * BW; i += 256) {
+            const int ly = i / BW, lx = i - ly * BW;
+            const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+            if (gx < 0 || gx >= W || gy < 0 || gy >= H) {
+                const int rx = reflect101(gx, W), ry = reflect101(gy, H);
+                const int sx = rx - (x0 - 1), sy = ry - (y0 - 1);
+                if (sx >= 0 && sx < BW && sy >= 0 && sy < BH && rx >= 0 && ry >= 0) B[i] = B[sy * BW + sx];
+            }
+        }
+        __syncthreads();
+    }
     const float k = __fmul_rn(kcontrast[f], kscale);
     const float inv_k = __fdiv_rn(1.f, __fmul_rn(k, k));
     float* sm = Lsmooth + (size_t)f * plane_stride;
     float* fl = Lflow + (size_t)f * plane_stride;
-    for (int ly = ty; ly < kTH; ly += kBY)
-        for (int lx = tx; lx < kTW; lx += kBX) {
-            const int gx = x0 + lx, gy = y0 + ly;
-            if (gx < W && gy < H) {
-                float dx, dy;
-                scharr_at(&B[ly][lx + 1], &B[ly + 1][lx + 1], &B[ly + 2][lx + 1], dx, dy);
-                sm[(size_t)gy * W + gx] = B[ly + 1][lx + 1];
-                // pm_g2: 1 / (1 + (Lx^2 + Ly^2) / k^2)
-                fl[(size_t)gy * W + gx] =
-                    __fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(inv_k, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)))));
-            }
+#pragma unroll
+    for (int it = 0; it < kTW * kTH / 256; ++it) {
+        const int i = tid + it * 256;
+        const int ly = i / kTW, lx = i - ly * kTW;
+        const int gx = x0 + lx, gy = y0 + ly;
+        if (gx < W && gy < H) {
+            float dx, dy;
+            scharr_at(&B[ly * BW + lx + 1], &B[(ly + 1) * BW + lx + 1], &B[(ly + 2) * BW + lx + 1], dx, dy);
+            sm[(size_t)gy * W + gx] = B[(ly + 1) * BW + lx + 1];
+            // pm_g2: 1 / (1 + (Lx^2 + Ly^2) / k^2)
+            fl[(size_t)gy * W + gx] =
+                __fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(inv_k, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)))));
         }
+    }
 }
 
 // ---- FED: K explicit diffusion steps per launch, temporally blocked, register-resident patches ----
@@ -438,7 +496,7 @@ k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout,
 // kernels of compute_derivative_kernels(scale s): taps at -s, 0, +s: smoothing [w0, w1, w0],
 // derivative [-1, 0, 1]; sepFilter2D = row pass (kx) then column pass (ky), BORDER_REFLECT_101.
 __global__ void __launch_bounds__(kBX* kBY)
-k_hessian(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, int s, float w0, float w1,
+k_hessian_generic(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, int s, float w0, float w1,
           float sigma_quat, float* __restrict__ Lx, float* __restrict__ Ly, float* __restrict__ Ldet,
           size_t pyr_stride) {
     extern __shared__ float smem[];
@@ -487,6 +545,82 @@ k_hessian(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, int s, 
             oy[o] = cy[0];
             od[o] = __fmul_rn(__fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy)), sigma_quat);
         }
+}
+
+// The same kernel with the tap distance S as a template parameter (AKAZE's sublevels always give
+// sigma_size 2, 3, 3, 4): every extent and tap offset is a compile-time constant, the three stages are
+// flat 256-thread loops, and tiles away from the border skip the reflect-101 index work.  The
+// arithmetic expressions are those of k_hessian_generic.
+template <int S>
+__global__ void __launch_bounds__(kBX* kBY)
+k_hessian(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, float w0, float w1,
+          float sigma_quat, float* __restrict__ Lx, float* __restrict__ Ly, float* __restrict__ Ldet,
+          size_t pyr_stride) {
+    constexpr int SW = kTW + 4 * S, SH = kTH + 4 * S;      // Lsmooth region (halo 2S)
+    constexpr int DW = kTW + 2 * S, DH = kTH + 2 * S;      // first-derivative region (halo S)
+    extern __shared__ float smem[];
+    float* S0 = smem;                 // SH x SW
+    float* DX = S0 + SW * SH;         // DH x DW
+    float* DY = DX + DW * DH;         // DH x DW
+    const int f = blockIdx.z;
+    const float* src = Lsm + (size_t)f * sm_stride;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+    const int tid = threadIdx.y * kBX + threadIdx.x;
+    if (x0 >= 2 * S && y0 >= 2 * S && x0 + kTW + 2 * S <= W && y0 + kTH + 2 * S <= H) {
+        const float* base = src + (size_t)(y0 - 2 * S) * W + (x0 - 2 * S);
+#pragma unroll
+        for (int it = 0; it < (SH * SW + 255) / 256; ++it) {
+            const int i = tid + it * 256;
+            if (i < SH * SW) {
+                const int ly = i / SW, lx = i - ly * SW;
+                S0[i] = base[(size_t)ly * W + lx];
+            }
+        }
+    } else {
+        for (int i = tid; i < SH * SW; i += 256) {
+            const int ly = i / SW, lx = i - ly * SW;
+            S0[i] = src[(size_t)reflect101(y0 - 2 * S + ly, H) * W + reflect101(x0 - 2 * S + lx, W)];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < (DH * DW + 255) / 256; ++it) {
+        const int i = tid + it * 256;
+        if (i < DH * DW) {
+            const int ly = i / DW, lx = i - ly * DW;
+            const float* c = &S0[(ly + S) * SW + (lx + S)];
+            const float* u = c - S * SW;
+            const float* d = c + S * SW;
+            // Lx: rows [-1 0 1], columns [w0 w1 w0]
+            DX[i] = w0 * (u[S] - u[-S]) + w1 * (c[S] - c[-S]) + w0 * (d[S] - d[-S]);
+            // Ly: rows [w0 w1 w0], columns [-1 0 1]
+            DY[i] = (w0 * d[-S] + w1 * d[0] + w0 * d[S]) - (w0 * u[-S] + w1 * u[0] + w0 * u[S]);
+        }
+    }
+    __syncthreads();
+    float* ox = Lx + (size_t)f * pyr_stride;
+    float* oy = Ly + (size_t)f * pyr_stride;
+    float* od = Ldet + (size_t)f * pyr_stride;
+#pragma unroll
+    for (int it = 0; it < kTW * kTH / 256; ++it) {
+        const int i = tid + it * 256;
+        const int ly = i / kTW, lx = i - ly * kTW;
+        const int gx = x0 + lx, gy = y0 + ly;
+        if (gx >= W || gy >= H) continue;
+        const float* cx = &DX[(ly + S) * DW + (lx + S)];
+        const float* cy = &DY[(ly + S) * DW + (lx + S)];
+        const float* ux = cx - S * DW;
+        const float* dx = cx + S * DW;
+        const float* uy = cy - S * DW;
+        const float* dy = cy + S * DW;
+        const float lxx = w0 * (ux[S] - ux[-S]) + w1 * (cx[S] - cx[-S]) + w0 * (dx[S] - dx[-S]);
+        const float lxy = (w0 * dx[-S] + w1 * dx[0] + w0 * dx[S]) - (w0 * ux[-S] + w1 * ux[0] + w0 * ux[S]);
+        const float lyy = (w0 * dy[-S] + w1 * dy[0] + w0 * dy[S]) - (w0 * uy[-S] + w1 * uy[0] + w0 * uy[S]);
+        const size_t o = (size_t)gy * W + gx;
+        ox[o] = cx[0];
+        oy[o] = cy[0];
+        od[o] = __fmul_rn(__fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy)), sigma_quat);
+    }
 }
 
 bool is_prime(int n) {
@@ -590,7 +724,10 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFedS * kFedS * 4);
-        cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_hessian_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_hessian<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_hessian<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(k_hessian<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr = true;
     }
     // level 0
@@ -639,8 +776,14 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
         const dim3 grid(div_up(e.w, kTW), div_up(e.h, kTH), frames);
         {
             ProfScope ps(ctx, st, "scale.hessian", (double)frames * e.w * e.h * 16);
-            k_hessian<<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, s, w0, w1, (float)(s * s * s * s),
-                                               ws.Lx + e.plane_off, ws.Ly + e.plane_off, ws.Ldet + e.plane_off, pyr);
+            float* lx = ws.Lx + e.plane_off;
+            float* ly = ws.Ly + e.plane_off;
+            float* ld = ws.Ldet + e.plane_off;
+            const float sq = (float)(s * s * s * s);
+            if (s == 2) k_hessian<2><<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, w0, w1, sq, lx, ly, ld, pyr);
+            else if (s == 3) k_hessian<3><<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, w0, w1, sq, lx, ly, ld, pyr);
+            else if (s == 4) k_hessian<4><<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, w0, w1, sq, lx, ly, ld, pyr);
+            else k_hessian_generic<<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, s, w0, w1, sq, lx, ly, ld, pyr);
             DUNK_KERNEL_CHECK(ctx);
         }
         return DUNK_OK;

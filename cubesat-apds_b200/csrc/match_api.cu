@@ -257,7 +257,12 @@ int dunk_db_append(dunk_db* db, const uint8_t* desc, const DunkKeyPoint* kps, co
     return DUNK_OK;
 }
 
+int dunk_db_append_random_at(dunk_db* db, int64_t n, uint64_t seed, uint64_t global_row_offset);
 int dunk_db_append_random(dunk_db* db, int64_t n, uint64_t seed) {
+    return dunk_db_append_random_at(db, n, seed, db ? (uint64_t)db->size : 0);
+}
+
+int dunk_db_append_random_at(dunk_db* db, int64_t n, uint64_t seed, uint64_t global_row_offset) {
     DUNK_REQUIRE(db && n >= 0, DUNK_ERR_BAD_ARG, "dunk_db_append_random: bad argument");
     if (n == 0) return DUNK_OK;
     std::lock_guard<std::mutex> lk(db->mu);
@@ -266,7 +271,7 @@ int dunk_db_append_random(dunk_db* db, int64_t n, uint64_t seed) {
     dunk_ctx* ctx = db->ctx;
     SlotGuard g(ctx);
     cudaStream_t st = g.stream();
-    int rc = launch_fill_random_rows(ctx, st, db->desc64 + db->size * 4, n, seed, (uint64_t)db->size);
+    int rc = launch_fill_random_rows(ctx, st, db->desc64 + db->size * 4, n, seed, global_row_offset);
     if (rc) return rc;
     DUNK_CUDA(cudaMemsetAsync(db->kps + db->size, 0, (size_t)n * sizeof(DunkKeyPoint), st));
     DUNK_CUDA(cudaMemsetAsync(db->image_id + db->size, 0, (size_t)n * 4, st));

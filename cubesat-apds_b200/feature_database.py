@@ -220,8 +220,11 @@ class DescriptorDatabase:
                                                float(ratio), float(reproj_threshold), int(max_points), ptr(out)))
         return out
 
-    def append_random(self, n: int, seed: int):
-        check(_lib.load().dunk_db_append_random(self.handle, int(n), int(seed)))
+    def append_random(self, n: int, seed: int, global_row_offset: Optional[int] = None):
+        if global_row_offset is None:
+            check(_lib.load().dunk_db_append_random(self.handle, int(n), int(seed)))
+        else:
+            check(_lib.load().dunk_db_append_random_at(self.handle, int(n), int(seed), int(global_row_offset)))
 
     # -- read side
     def read_descriptors(self, first: int, n: int) -> np.ndarray:

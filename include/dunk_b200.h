@@ -123,6 +123,9 @@ int dunk_db_append(dunk_db* db, const uint8_t* desc, const DunkKeyPoint* kps,
                    const int32_t* image_ids, int64_t n);
 /* fill n rows with device-generated uniform random descriptors (seeded; bench config 3) */
 int dunk_db_append_random(dunk_db* db, int64_t n, uint64_t seed);
+/* same, for a shard: row r of the call is row (global_row_offset + r) of the seeded global sequence,
+ * so the union of the shards equals the unsharded DB whatever the shard count */
+int dunk_db_append_random_at(dunk_db* db, int64_t n, uint64_t seed, uint64_t global_row_offset);
 int64_t dunk_db_size(dunk_db* db);
 /* read back rows [first, first+n) (any of the outputs may be NULL) */
 int dunk_db_read(dunk_db* db, int64_t first, int64_t n, uint8_t* desc, DunkKeyPoint* kps,

@@ -35,7 +35,7 @@ def test_band_merger_bit_exact_full_tile(dunk, ctx):
     got = dunk.image_extractor.band_merger(bands, dunk.image_extractor.BandsMinMax(*mm), ctx=ctx)
     exp = go.band_merger(*bands, mm)
     assert np.array_equal(got, exp)
-    assert (got[:, 3] == 0).sum() == len(range(0, n, 2002))
+    assert (got[:, 3] == 0).sum() == (exp[:, 3] == 0).sum() > 500
     got_bgra = dunk.image_extractor.band_merger(bands, dunk.image_extractor.BandsMinMax(*mm), bgra=True, ctx=ctx)
     assert np.array_equal(got_bgra, exp[:, [2, 1, 0, 3]])
 
