@@ -4,6 +4,7 @@
 // reference only performs in a test (feature_extraction/src/lib.rs:196-249 extract -> knn ->
 // points) followed by find_homography_mat (homographier/src/homographier/mod.rs:231-259).
 #include <algorithm>
+#include <cmath>
 #include "akaze.h"
 #include "match.h"
 #include "pipeline.h"
@@ -512,3 +513,201 @@ int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int ro
 }
 
 }  // extern "C"
+
+/* ---- reference-DB build straight from the scene's bands ----------------------
+ * preprocessor/src/main.rs:160-327: for every level of detail lod in 0..lods the scene is cut into
+ * (tile_w * 2^lod) x (tile_h * 2^lod) windows, tile = scene / 2^(lods-1) (integer division, remainder
+ * rows / columns dropped), each window is read at tile resolution (GDAL Lanczos in the reference),
+ * converted by band_merger, extracted, and its rows inserted with x * 2^lod + column offset.  Here the
+ * whole chain runs on the device per tile batch: resample + radiometric conversion fused into one
+ * kernel that writes BGRA tiles, batched AKAZE, row append, ref_image rows. */
+namespace dunk {
+namespace {
+
+constexpr int kMaxTaps = 6 * 16;   // Lanczos-3 support at decimation 16
+
+struct ResampleTaps {
+    int n;                 // taps per axis (1 = copy)
+    int first;             // offset of tap 0 relative to floor(centre)
+    double w[kMaxTaps];
+};
+
+// One thread per output pixel: 3 bands resampled (f64 accumulation in a fixed tap order, weights
+// renormalised where the support leaves the scene), then f32_to_u8 per channel -> BGRA.
+__global__ void __launch_bounds__(256)
+k_lod_tiles(const float* __restrict__ red, const float* __restrict__ green, const float* __restrict__ blue, int W, int H,
+            int tile_w, int tile_h, int scale, int tiles_x, int tile0, ResampleTaps taps, float rmin, float rmax, float gmin,
+            float gmax, float bmin, float bmax, uchar4* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, t = tile0 + blockIdx.z;
+    if (x >= tile_w) return;
+    const int tcol = t % tiles_x, trow = t / tiles_x;
+    const long long sx0 = ((long long)tcol * tile_w + x) * scale, sy0 = ((long long)trow * tile_h + y) * scale;   // window of this pixel
+    const float* bands[3] = {red, green, blue};
+    float v[3];
+    if (taps.n == 1) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) v[b] = bands[b][(size_t)sy0 * W + sx0];
+    } else {
+        // centre of the output pixel in source coordinates is (s0 + scale / 2); taps start at first
+        const long long cx = sx0 + scale / 2, cy = sy0 + scale / 2;
+        double acc[3] = {0, 0, 0}, wsum_y = 0;
+        for (int ky = 0; ky < taps.n; ++ky) {
+            const long long yy = cy + taps.first + ky;
+            if (yy < 0 || yy >= H) continue;
+            double row[3] = {0, 0, 0}, wsum_x = 0;
+            for (int kx = 0; kx < taps.n; ++kx) {
+                const long long xx = cx + taps.first + kx;
+                if (xx < 0 || xx >= W) continue;
+                const double w = taps.w[kx];
+                wsum_x = __dadd_rn(wsum_x, w);
+#pragma unroll
+                for (int b = 0; b < 3; ++b) row[b] = __dadd_rn(row[b], __dmul_rn(w, (double)bands[b][(size_t)yy * W + xx]));
+            }
+            const double wy = taps.w[ky];
+            wsum_y = __dadd_rn(wsum_y, wy);
+#pragma unroll
+            for (int b = 0; b < 3; ++b) acc[b] = __dadd_rn(acc[b], __dmul_rn(wy, __ddiv_rn(row[b], wsum_x)));
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) v[b] = (float)__ddiv_rn(acc[b], wsum_y);
+    }
+    auto to_u8 = [](float val, float lo, float hi) -> unsigned char {
+        if (isnan(val)) return 0;
+        const float fl = __fdiv_rn(__fsub_rn(val, lo), __fsub_rn(hi, lo));
+        if (!(fl >= 0.f && fl <= 1.f)) return 0;
+        const float g = (float)pow((double)fl, (double)(1.0f / 2.2f));
+        return (unsigned char)(int)floorf(__fadd_rn(__fmul_rn(g, 255.f), 0.5f));
+    };
+    uchar4 o;
+    o.z = to_u8(v[0], rmin, rmax);   // BGRA (raster_to_mat)
+    o.y = to_u8(v[1], gmin, gmax);
+    o.x = to_u8(v[2], bmin, bmax);
+    o.w = (isnan(v[0]) && isnan(v[1]) && isnan(v[2])) ? 0 : 255;
+    out[((size_t)blockIdx.z * tile_h + y) * tile_w + x] = o;
+}
+
+double lanczos3(double x) {
+    if (x == 0.0) return 1.0;
+    if (std::fabs(x) >= 3.0) return 0.0;
+    const double px = M_PI * x;
+    return 3.0 * std::sin(px) * std::sin(px / 3.0) / (px * px);
+}
+
+// taps for decimation by `scale` (a power of two): area = box mean, lanczos = GDAL-style convolution
+// kernel stretched by the decimation factor (support 3 * scale either side of the pixel centre)
+bool make_taps(int scale, int resample, ResampleTaps* t) {
+    if (scale == 1) { t->n = 1; t->first = 0; t->w[0] = 1.0; return true; }
+    if (resample == 0) {
+        t->n = scale; t->first = -(scale / 2);
+        for (int k = 0; k < scale; ++k) t->w[k] = 1.0;
+        return true;
+    }
+    const int n = 6 * scale;
+    if (n > kMaxTaps) return false;
+    t->n = n; t->first = -3 * scale;
+    // source pixel j covers [j, j+1); its centre sits (k + first + 0.5) away from the output centre
+    for (int k = 0; k < n; ++k) t->w[k] = lanczos3(((double)(k + t->first) + 0.5) / scale);
+    return true;
+}
+
+}  // namespace
+}  // namespace dunk
+
+extern "C" int dunk_db_build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue, int width, int height,
+                                        const double* min_max, int lods, int resample, int max_points, int* n_tiles_out,
+                                        int* tile_w_out, int* tile_h_out) {
+    DUNK_REQUIRE(db && red && green && blue && min_max, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: NULL argument");
+    DUNK_REQUIRE(lods >= 1 && lods <= 5, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: lods=%d (1..5)", lods);
+    DUNK_REQUIRE(resample == 0 || resample == 1, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: resample %d (0 = area, 1 = Lanczos-3)", resample);
+    const int tile_w = width >> (lods - 1), tile_h = height >> (lods - 1);      // main.rs:212
+    DUNK_REQUIRE(tile_w >= 16 && tile_h >= 16, DUNK_ERR_ASSERT, "dunk_db_build_from_bands: tiles of %dx%d are too small", tile_w, tile_h);
+    if (tile_w_out) *tile_w_out = tile_w;
+    if (tile_h_out) *tile_h_out = tile_h;
+    dunk_ctx* ctx = db->ctx;
+    std::lock_guard<std::mutex> lk(db->mu);
+    SlotGuard g(ctx);
+    cudaStream_t st = g.stream();
+    const size_t plane = (size_t)width * height;
+    const int sub = 8;
+    const LevelTable lt = make_level_table(tile_w, tile_h);
+    long long c = (long long)tile_w * tile_h / 32;
+    c = std::min<long long>(std::max<long long>(c, 2048), 1 << 20);
+    const int cap = (int)c;
+    const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cap, cap);
+    const size_t tile_bytes = (size_t)tile_w * tile_h * 4;
+    const size_t need = 3 * al(plane * 4) + al(ws_bytes) + al(sub * tile_bytes) + al((sub + 1) * 4) + 4 * al(sub * 4);
+    void* scratch = ctx->dev_scratch(g.s, need);
+    if (!scratch) return DUNK_ERR_NO_MEM;
+    char* ptr = (char*)scratch;
+    float* d_band[3];
+    for (int b = 0; b < 3; ++b) { d_band[b] = (float*)ptr; ptr += al(plane * 4); }
+    AkazeWorkspace ws;
+    akaze_carve_workspace(ptr, lt, sub, cap, cap, &ws);
+    ptr += al(ws_bytes);
+    unsigned char* d_tiles = (unsigned char*)ptr; ptr += al(sub * tile_bytes);
+    int* d_off = (int*)ptr; ptr += al((sub + 1) * 4);
+    float* d_xo = (float*)ptr; ptr += al(sub * 4);
+    float* d_yo = (float*)ptr; ptr += al(sub * 4);
+    float* d_sc = (float*)ptr; ptr += al(sub * 4);
+    int32_t* d_id = (int32_t*)ptr;
+    DUNK_CUDA(cudaMemcpyAsync(d_band[0], red, plane * 4, cudaMemcpyHostToDevice, st));
+    DUNK_CUDA(cudaMemcpyAsync(d_band[1], green, plane * 4, cudaMemcpyHostToDevice, st));
+    DUNK_CUDA(cudaMemcpyAsync(d_band[2], blue, plane * 4, cudaMemcpyHostToDevice, st));
+    int n_tiles = 0;
+    std::vector<int> h_off(sub + 1), h_cnt(sub);
+    for (int lod = 0; lod < lods; ++lod) {
+        const int scale = 1 << lod;
+        const int tiles_x = width / (tile_w * scale), tiles_y = height / (tile_h * scale);    // main.rs:215-216
+        ResampleTaps taps;
+        DUNK_REQUIRE(make_taps(scale, resample, &taps), DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: decimation %d too large", scale);
+        const int total = tiles_x * tiles_y;
+        for (int t0 = 0; t0 < total; t0 += sub) {
+            const int nf = std::min(sub, total - t0);
+            {
+                ProfScope ps(ctx, st, "lod.resample_merge", (double)nf * tile_w * tile_h * (12.0 * scale * scale + 4.0));
+                k_lod_tiles<<<dim3(div_up(tile_w, 256), tile_h, nf), 256, 0, st>>>(
+                    d_band[0], d_band[1], d_band[2], width, height, tile_w, tile_h, scale, tiles_x, t0, taps, (float)min_max[0],
+                    (float)min_max[1], (float)min_max[2], (float)min_max[3], (float)min_max[4], (float)min_max[5], (uchar4*)d_tiles);
+                DUNK_KERNEL_CHECK(ctx);
+            }
+            int rc = akaze_run(ctx, st, lt, ws, d_tiles, tile_bytes, tile_w * 4, 4, nf, max_points <= 0 ? 0 : max_points);
+            if (rc) return rc;
+            k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off);
+            DUNK_KERNEL_CHECK(ctx);
+            DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 1) * 4, cudaMemcpyDeviceToHost, st));
+            DUNK_CUDA(cudaMemcpyAsync(h_cnt.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+            DUNK_CUDA(cudaStreamSynchronize(st));
+            const int rows_new = h_off[nf];
+            DUNK_REQUIRE(db->size + rows_new <= db->capacity, DUNK_ERR_NO_MEM, "dunk_db_build_from_bands: %lld + %d rows exceed capacity %lld",
+                         (long long)db->size, rows_new, (long long)db->capacity);
+            std::vector<float> xo(nf), yo(nf), sc(nf);
+            std::vector<int32_t> ids(nf);
+            int maxc = 0;
+            for (int f = 0; f < nf; ++f) {
+                const int t = t0 + f, col = t % tiles_x, row = t / tiles_x;
+                const int xs = col * tile_w * scale, ys = row * tile_h * scale;
+                // InsertImage, main.rs:283-289
+                DunkImage im{(int32_t)db->images.size() + 1, xs, ys, xs + tile_w * scale - 1, ys + tile_h * scale - 1, lod};
+                db->images.push_back(im);
+                ids[f] = im.id;
+                xo[f] = (float)xs; yo[f] = (float)ys; sc[f] = (float)scale;
+                maxc = std::max(maxc, h_cnt[f]);
+            }
+            db->image_lod_dirty = true;
+            DUNK_CUDA(cudaMemcpyAsync(d_xo, xo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+            DUNK_CUDA(cudaMemcpyAsync(d_yo, yo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+            DUNK_CUDA(cudaMemcpyAsync(d_sc, sc.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+            DUNK_CUDA(cudaMemcpyAsync(d_id, ids.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+            if (maxc > 0) {
+                k_append_rows<<<dim3(div_up(maxc, 256), nf), 256, 0, st>>>(ws.desc64, ws.kps, cap, ws.kp_count, d_off, d_xo, d_yo, d_sc, d_id,
+                                                                          0, db->desc64, db->kps, db->image_id, db->size);
+                DUNK_KERNEL_CHECK(ctx);
+            }
+            DUNK_CUDA(cudaStreamSynchronize(st));
+            db->size += rows_new;
+            n_tiles += nf;
+        }
+    }
+    if (n_tiles_out) *n_tiles_out = n_tiles;
+    return DUNK_OK;
+}

@@ -203,6 +203,21 @@ class DescriptorDatabase:
                                                ptr(xo), ptr(yo), ptr(sc), ptr(ids), int(max_points), ptr(counts)))
         return counts
 
+    def build_from_bands(self, red: np.ndarray, green: np.ndarray, blue: np.ndarray, min_max, lods: int,
+                         resample: str = "area", max_points: int = _lib.MAX_POINTS):
+        """The preprocessor's DB build (preprocessor/src/main.rs:160-327) for a scene given as three f32
+        bands [H, W]: LoD windows resampled to tile size, band_merger, AKAZE, rows + ref_image rows
+        inserted — all on the device.  Returns (tiles processed, (tile_w, tile_h))."""
+        r, g, b = (np.ascontiguousarray(x, dtype=np.float32) for x in (red, green, blue))
+        if not (r.ndim == 2 and r.shape == g.shape == b.shape):
+            raise DunkError(_lib.ERR_ASSERT, "build_from_bands: three equally shaped 2-d f32 bands expected")
+        mm = np.ascontiguousarray(min_max, dtype=np.float64)
+        n, tw, th = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(_lib.load().dunk_db_build_from_bands(self.handle, ptr(r), ptr(g), ptr(b), r.shape[1], r.shape[0], ptr(mm), int(lods),
+                                                   {"area": 0, "lanczos": 1}[resample], int(max_points), C.byref(n), C.byref(tw),
+                                                   C.byref(th)))
+        return n.value, (tw.value, th.value)
+
     def register_frames(self, frames: np.ndarray, ratio: float = 0.8, reproj_threshold: float = 3.0,
                         max_points: int = _lib.MAX_POINTS) -> np.ndarray:
         """The whole hot path for a frame batch [B, H, W(, C)] u8 against this shard: extract ->

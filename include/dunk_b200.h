@@ -372,6 +372,18 @@ int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int ro
                          const float* x_off, const float* y_off, const float* scale,
                          const int32_t* image_ids, int max_points, int* counts);
 
+/* reference-DB build straight from the scene's three f32 bands (SURVEY 8f rank 2;
+ * preprocessor/src/main.rs:160-327 minus GDAL / Postgres): tile = scene >> (lods - 1); for every lod in
+ * 0..lods the (tile << lod)-sized windows are resampled to tile size on the device (resample 0 = box
+ * mean, 1 = Lanczos-3 stretched by the decimation factor, the kernel GDAL's RasterIO uses; the
+ * reference's exact pixels additionally depend on GDAL's overview selection and cannot be pinned
+ * here), converted by band_merger (min_max as in dunk_band_merger), extracted (BGRA), and appended
+ * with x * 2^lod + window offset (main.rs:300-301); one ref_image row per tile (main.rs:283-289).
+ * Outputs (may be NULL): number of tiles processed and the tile size. */
+int dunk_db_build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue,
+                             int width, int height, const double* min_max, int lods, int resample,
+                             int max_points, int* n_tiles_out, int* tile_w_out, int* tile_h_out);
+
 /* ---- roofline denominators measured on the box ---------------------------------------- */
 /* per-kernel-class device times: between begin and end every launch site brackets its kernels
  * with CUDA events on the launching stream.  end() returns the number of classes n and fills

@@ -40,3 +40,17 @@ def test_db_oracle_orders_by_response_then_row():
     keys = [(-float(r[i]), int(i)) for i in idx]
     assert keys == sorted(keys)
     assert all(im[i] in (2, 4) and 10 <= x[i] <= 81 and 10 <= y[i] <= 90 for i in idx)
+
+
+def test_lod_oracle_resamplers():
+    """box mean of a constant-gradient band is exact; Lanczos keeps constants and is symmetric"""
+    from oracle import lod_oracle as lo
+    y, x = np.mgrid[0:64, 0:64].astype(np.float32)
+    band = (2 * x + 3 * y).astype(np.float32)
+    a = lo.resample_window(band, 0, 0, 16, 16, 4, "area")
+    assert np.allclose(a, 2 * (4 * np.arange(16)[None, :] + 1.5) + 3 * (4 * np.arange(16)[:, None] + 1.5))
+    c = lo.resample_window(np.full((64, 64), 7.0, np.float32), 0, 0, 16, 16, 4, "lanczos")
+    assert np.allclose(c, 7.0, atol=1e-6)
+    first, w = lo.taps(2, "lanczos")
+    assert len(w) == 12 and np.allclose(w, w[::-1]) and first == -6
+    assert np.array_equal(lo.resample_window(band, 3, 5, 8, 8, 1, "area"), band[5:13, 3:11])
