@@ -94,6 +94,8 @@ SIGNATURES = {
     "dunk_knn_match_hamming": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _f, _vp, _i, _pi]),
     "dunk_knn2_hamming": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
     "dunk_match_crosscheck_hamming": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i, _pi]),
+    "dunk_knn2_l2": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp, _vp]),
+    "dunk_knn2_l2_dev": (_i, [_vp, _i, _vp, _i, _vp, _i64, _i, _vp, _vp, _vp]),
     "dunk_db_create": (_i, [_vp, _i64, _i, C.POINTER(_vp)]),
     "dunk_db_destroy": (None, [_vp]),
     "dunk_db_append": (_i, [_vp, _vp, _vp, _vp, _i64]),

@@ -94,6 +94,24 @@ def knn2(origin_desc: np.ndarray, target_desc: np.ndarray,
     return idx, dist
 
 
+def knn2_l2(origin_desc: np.ndarray, target_desc: np.ndarray, ctx: Optional[_lib.Context] = None):
+    """Float-descriptor 2-NN (north_star extension; the reference only builds NORM_HAMMING matchers,
+    lib.rs:101,121): BFMatcher(NORM_L2).knnMatch(origin, target, 2) for N x 64 or N x 128 f32 descriptors,
+    dot products on tcgen05 tensor cores, exact f32 re-rank.  Returns (idx nq x 2 i32, dist nq x 2 f32,
+    stats = (queries re-done exactly, slabs))."""
+    ctx = ctx or default_context()
+    q = np.ascontiguousarray(origin_desc, dtype=np.float32)
+    t = np.ascontiguousarray(target_desc, dtype=np.float32)
+    if q.ndim != 2 or t.ndim != 2 or (q.shape[0] and t.shape[0] and q.shape[1] != t.shape[1]):
+        raise DunkError(_lib.ERR_ASSERT, f"float descriptors must be N x D with equal D: {q.shape} vs {t.shape}")
+    dim = q.shape[1] if q.shape[0] else t.shape[1]
+    idx = np.empty((q.shape[0], 2), dtype=np.int32)
+    dist = np.empty((q.shape[0], 2), dtype=np.float32)
+    stats = np.zeros(2, dtype=np.int32)
+    check(_lib.load().dunk_knn2_l2(ctx.handle, ptr(q), q.shape[0], ptr(t), t.shape[0], int(dim), ptr(idx), ptr(dist), ptr(stats)))
+    return idx, dist, (int(stats[0]), int(stats[1]))
+
+
 def get_bruteforce_matches(origin_desc: np.ndarray, target_desc: np.ndarray,
                            ctx: Optional[_lib.Context] = None) -> np.ndarray:
     """lib.rs:116-126 — BFMatcher(NORM_HAMMING, crossCheck=true).match."""

@@ -113,6 +113,21 @@ int dunk_match_crosscheck_hamming(dunk_ctx* ctx, const uint8_t* query, int nq,
                                   const uint8_t* train, int64_t nt, int desc_bytes,
                                   DunkDMatch* out, int out_cap, int* n_out);
 
+/* ---- stage 2, float descriptors (north_star only; the reference builds no NORM_L2 matcher) ------
+ * replaces cv::BFMatcher(NORM_L2).knnMatch(query, train, 2) for f32 descriptors of dim = 64 or 128
+ * floats.  ||q-t||^2 = ||q||^2 + ||t||^2 - 2 q.t: the dot products run on tcgen05 tensor cores
+ * (kind::tf32, TMA-fed, TMEM accumulators) and only NOMINATE 4 candidates per (query, slab); the
+ * returned neighbours are re-ranked with exact f32 distances and proven complete against the tf32
+ * error bound, queries that cannot be proven fall back to an exact scan.  idx: nq x 2 int32
+ * (ties -> lower train index), dist: nq x 2 f32 (sqrt of the exact squared distance).
+ * stats (may be NULL): {queries re-done by the exact fallback, slabs used}.  nt < 2 -> -211. */
+int dunk_knn2_l2(dunk_ctx* ctx, const float* query, int nq, const float* train, int64_t nt, int dim,
+                 int32_t* idx, float* dist, int* stats);
+/* device-resident variant (16-byte aligned inputs; async on the slot's stream except for two
+ * 4-byte read-backs) */
+int dunk_knn2_l2_dev(dunk_ctx* ctx, int slot, const void* q_dev, int nq, const void* t_dev, int64_t nt,
+                     int dim, void* idx_dev, void* dist_dev, int* stats);
+
 /* ---- HBM-resident reference descriptor database (feature_database read side) ----
  * rows = models::Keypoint (feature_database/src/models.rs:30-41): SoA arrays in HBM,
  * descriptors padded to 64-B rows.  One dunk_db is one shard (one GPU). */

@@ -103,3 +103,23 @@ def random_db_rows(n: int, seed: int, row_offset: int = 0, desc_bytes: int = 61)
     v[:, 7] &= np.uint64(0x0000003FFFFFFFFF)
     rows = v.astype("<u8").view(np.uint8).reshape(n, 64)
     return np.ascontiguousarray(rows[:, :desc_bytes])
+
+
+def knn2_l2(q, t, chunk=256):
+    """cv::BFMatcher(NORM_L2).knnMatch(q, t, 2) for f32 descriptors: squared differences summed in f32
+    (sequential order), sqrt, two smallest by (distance, index).  Pinned against cv2 4.13.0 in
+    tests/golden/l2_golden.npz: indices identical, distances within 1e-6 relative (OpenCV's SIMD sum
+    associates differently)."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    t = np.ascontiguousarray(t, dtype=np.float32)
+    idx = np.empty((q.shape[0], 2), np.int32)
+    dist = np.empty((q.shape[0], 2), np.float32)
+    for a in range(0, q.shape[0], chunk):
+        d = q[a:a + chunk, None, :] - t[None, :, :]
+        d2 = np.zeros(d.shape[:2], np.float32)
+        for k in range(d.shape[2]):
+            d2 = d2 + d[:, :, k] * d[:, :, k]
+        order = np.argsort(d2, axis=1, kind="stable")[:, :2]
+        idx[a:a + chunk] = order
+        dist[a:a + chunk] = np.sqrt(np.take_along_axis(d2, order, axis=1))
+    return idx, dist

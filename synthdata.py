@@ -77,3 +77,21 @@ def window_homography(x0: float, y0: float, seed: int, jitter: float = 1.0) -> n
     T = np.array([[1.0, 0, -x0], [0, 1.0, -y0], [0, 0, 1.0]])
     C = np.array([[1.0, 0, -512.0], [0, 1.0, -512.0], [0, 0, 1.0]])
     return np.linalg.inv(C) @ A @ C @ T
+
+
+L2_CASES = {"a": (300, 5000, 64), "b": (77, 1031, 128), "c": (129, 257, 64)}
+
+
+def l2_descriptors(name: str):
+    """Seeded unit-norm f32 descriptor sets of the float-matcher golden cases (tests/golden/l2_golden.npz
+    stores only cv2's answers): queries are noisy copies of train rows; case "c" plants exact duplicates."""
+    nq, nt, dim = L2_CASES[name]
+    rng = np.random.default_rng(31 + ord(name))
+    t = rng.normal(size=(nt, dim)).astype(np.float32)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    q = (t[rng.integers(0, nt, nq)] + rng.normal(0, 0.08, (nq, dim))).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    if name == "c":
+        t[100:104] = t[7]                      # distance ties -> lower train index
+        q[:8] = t[7]
+    return np.ascontiguousarray(q), np.ascontiguousarray(t)

@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ by running the reference's OpenCV entry
 points (through cv2, the same C++ library the `opencv` crate binds) with the reference's exact
-arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|akaze|pnp|warp|all]
+arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|akaze|pnp|warp|l2|all]
 The OpenCV version is recorded in every file (parity is defined against that version)."""
 import os
 import sys
@@ -218,6 +218,21 @@ def make_warp():
     print("warp_golden.npz written")
 
 
+def make_l2():
+    """cv2.BFMatcher(NORM_L2).knnMatch(q, t, 2) on the seeded f32 descriptor sets of synthdata.l2_descriptors
+    (north_star's float matcher); only cv2's answers are stored"""
+    import synthdata
+    out = {"opencv_version": np.array(cv2.__version__)}
+    for name in synthdata.L2_CASES:
+        q, t = synthdata.l2_descriptors(name)
+        m = cv2.BFMatcher(cv2.NORM_L2, False).knnMatch(q, t, 2)
+        out[f"{name}_idx"] = np.array([[x.trainIdx for x in r] for r in m], np.int32)
+        out[f"{name}_dist"] = np.array([[x.distance for x in r] for r in m], np.float32)
+        out[f"{name}_checksum"] = np.array([float(q.astype(np.float64).sum()), float(t.astype(np.float64).sum())])
+    np.savez_compressed(os.path.join(HERE, "l2_golden.npz"), **out)
+    print("l2_golden.npz written")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("match", "all"):
@@ -230,3 +245,5 @@ if __name__ == "__main__":
         make_pnp()
     if what in ("warp", "all") and "make_warp" in globals():
         make_warp()
+    if what in ("l2", "all") and "make_l2" in globals():
+        make_l2()

@@ -55,3 +55,17 @@ def test_random_db_rows_layout():
     again = mo.random_db_rows(10, 7, row_offset=5 + 990)
     assert np.array_equal(again, r[990:])
     assert abs(np.unpackbits(r[:, :60]).mean() - 0.5) < 0.01
+
+
+def test_l2_oracle_matches_cv2_golden():
+    """BFMatcher(NORM_L2).knnMatch k=2 on f32 descriptors: indices identical (incl. duplicate-row ties),
+    distances within 1e-6 relative"""
+    import os
+    import synthdata
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "l2_golden.npz"))
+    for name in synthdata.L2_CASES:
+        q, t = synthdata.l2_descriptors(name)
+        assert np.allclose([q.astype(np.float64).sum(), t.astype(np.float64).sum()], G[f"{name}_checksum"], rtol=0, atol=1e-9)
+        idx, dist = mo.knn2_l2(q, t)
+        assert np.array_equal(idx, G[f"{name}_idx"])
+        assert np.abs(dist - G[f"{name}_dist"]).max() <= 1e-6 * max(1.0, float(G[f"{name}_dist"].max()))
