@@ -112,6 +112,21 @@ def knn2_l2(origin_desc: np.ndarray, target_desc: np.ndarray, ctx: Optional[_lib
     return idx, dist, (int(stats[0]), int(stats[1]))
 
 
+def get_knn_matches_l2(origin_desc: np.ndarray, target_desc: np.ndarray, k: int, filter_strength: float,
+                       ctx: Optional[_lib.Context] = None) -> np.ndarray:
+    """`get_knn_matches` (lib.rs:94-114) for float descriptors: the same Lowe ratio rule
+    `m0.distance < m1.distance * filter_strength` (f32, strict) on the L2 neighbours.  DMATCH_DTYPE in query order."""
+    if k < 2:
+        raise DunkError(_lib.ERR_OUT_OF_RANGE, "k < 2: the ratio test needs two neighbours (lib.rs:108)")
+    idx, dist, _ = knn2_l2(origin_desc, target_desc, ctx)
+    keep = dist[:, 0] < dist[:, 1] * np.float32(filter_strength)
+    out = np.zeros(int(keep.sum()), dtype=DMATCH_DTYPE)
+    out["query_idx"] = np.nonzero(keep)[0]
+    out["train_idx"] = idx[keep, 0]
+    out["distance"] = dist[keep, 0]
+    return out
+
+
 def get_bruteforce_matches(origin_desc: np.ndarray, target_desc: np.ndarray,
                            ctx: Optional[_lib.Context] = None) -> np.ndarray:
     """lib.rs:116-126 — BFMatcher(NORM_HAMMING, crossCheck=true).match."""

@@ -54,3 +54,12 @@ def test_errors(dunk, ctx):
     assert e.value.code == -211
     with pytest.raises(dunk.DunkError):
         fe.knn2_l2(np.zeros((4, 48), np.float32), np.zeros((9, 48), np.float32), ctx)
+
+
+def test_ratio_filter_matches_oracle(dunk, ctx):
+    q, t = synthdata.l2_descriptors("a")
+    m = dunk.feature_extraction.get_knn_matches_l2(q, t, 2, 0.7, ctx)
+    oi, od = mo.knn2_l2(q, t)
+    keep = od[:, 0] < od[:, 1] * np.float32(0.7)
+    assert np.array_equal(m["query_idx"], np.nonzero(keep)[0]) and np.array_equal(m["train_idx"], oi[keep, 0])
+    assert 0 < len(m) < len(q)
