@@ -58,8 +58,8 @@ def test_errors(dunk, ctx):
 
 def test_ratio_filter_matches_oracle(dunk, ctx):
     q, t = synthdata.l2_descriptors("a")
-    m = dunk.feature_extraction.get_knn_matches_l2(q, t, 2, 0.7, ctx)
+    m = dunk.feature_extraction.get_knn_matches_l2(q, t, 2, 0.5, ctx)
     oi, od = mo.knn2_l2(q, t)
-    keep = od[:, 0] < od[:, 1] * np.float32(0.7)
+    keep = od[:, 0] < od[:, 1] * np.float32(0.5)
     assert np.array_equal(m["query_idx"], np.nonzero(keep)[0]) and np.array_equal(m["train_idx"], oi[keep, 0])
     assert 0 < len(m) < len(q)
