@@ -367,29 +367,44 @@ k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout,
     const float* lin = Lin + (size_t)f * in_stride;
     const float* lfl = Lflow + (size_t)f * flow_stride;
     const int x0 = blockIdx.x * T - K, y0 = blockIdx.y * T - K;
-    const int tid = threadIdx.y * 16 + threadIdx.x;
-    // 50 independent 4-byte async copies per thread (zero-filled outside the image): the whole
-    // 51 KB tile is in flight at once, no registers are staged
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    // tile load: thread (tx, ty) copies elements (ty + 16k, tx + 16m), k, m < 5: 50 independent 4-byte async
+    // copies per thread (the whole 51 KB tile in flight, no registers staged), global and shared addresses are
+    // a per-thread base plus compile-time offsets; a warp writes 2 rows x 16 columns = 32 distinct banks
+    const bool tile_inside = x0 >= 0 && y0 >= 0 && x0 + kFedS <= W && y0 + kFedS <= H;
+    {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(bufA + ty * kFedS + tx);
+        const unsigned sb = (unsigned)__cvta_generic_to_shared(bufB + ty * kFedS + tx);
+        if (tile_inside) {
+            const float* pa = lin + (size_t)(y0 + ty) * W + (x0 + tx);
+            const float* pc = lfl + (size_t)(y0 + ty) * W + (x0 + tx);
 #pragma unroll
-    for (int it = 0; it < kFedS * kFedS / 256; ++it) {
-        const int i = tid + it * 256;
-        const int r = i / kFedS, c = i - r * kFedS;
-        const int gx = x0 + c, gy = y0 + r;
-        const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
-        const size_t o = in ? (size_t)gy * W + gx : 0;
-        const unsigned nbytes = in ? 4u : 0u;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(bufA + i)),
-                     "l"(lin + o), "r"(nbytes) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(bufB + i)),
-                     "l"(lfl + o), "r"(nbytes) : "memory");
+            for (int k = 0; k < kFedP; ++k) {
+                const float* ra = pa + (size_t)(16 * k) * W;
+                const float* rc = pc + (size_t)(16 * k) * W;
+#pragma unroll
+                for (int m = 0; m < kFedP; ++m) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + (16 * k * kFedS + 16 * m) * 4), "l"(ra + 16 * m) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sb + (16 * k * kFedS + 16 * m) * 4), "l"(rc + 16 * m) : "memory");
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kFedP; ++k)
+#pragma unroll
+                for (int m = 0; m < kFedP; ++m) {
+                    const int gx = x0 + tx + 16 * m, gy = y0 + ty + 16 * k;
+                    const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+                    const size_t o = in ? (size_t)gy * W + gx : 0;
+                    const unsigned nbytes = in ? 4u : 0u;     // zero-fill outside the image
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa + (16 * k * kFedS + 16 * m) * 4), "l"(lin + o), "r"(nbytes) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sb + (16 * k * kFedS + 16 * m) * 4), "l"(lfl + o), "r"(nbytes) : "memory");
+                }
+        }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    const int px = threadIdx.x * kFedP, py = threadIdx.y * kFedP;
-    auto in_img = [&](int lx, int ly) {
-        const int gx = x0 + lx, gy = y0 + ly;
-        return lx >= 0 && lx < kFedS && ly >= 0 && ly < kFedS && gx >= 0 && gx < W && gy >= 0 && gy < H;
-    };
+    const int px = tx * kFedP, py = ty * kFedP;
     float L[kFedP][kFedP];
     float CE[kFedP][kFedP + 1];   // CE[r][j]: boundary between columns px+j-1 | px+j of row py+r
     float CS[kFedP + 1][kFedP];   // CS[i][c]: boundary between rows py+i-1 | py+i of column px+c
@@ -397,29 +412,58 @@ k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout,
 #pragma unroll
     for (int r = 0; r < kFedP; ++r)
 #pragma unroll
-        for (int c = 0; c < kFedP; ++c) {
-            L[r][c] = bufA[(py + r) * kFedS + px + c];
-            const int gx = x0 + px + c, gy = y0 + py + r;
-            if ((gy == 0 || gy == H - 1) && (gx == 0 || gx == W - 1)) corner |= 1u << (r * kFedP + c);
+        for (int c = 0; c < kFedP; ++c) L[r][c] = bufA[(py + r) * kFedS + px + c];
+    // block-uniform fast path: the whole tile lies inside the image.  Ring reads are clamped into the tile; a
+    // tile-edge boundary then gets some finite conductivity instead of 0, which only touches cells of the outer
+    // rings — those are invalid after the first step anyway (the valid region shrinks by one ring per step)
+    if (tile_inside) {
+        int cx[kFedP + 2], cy[kFedP + 2];
+#pragma unroll
+        for (int j = 0; j < kFedP + 2; ++j) {
+            cx[j] = min(max(px - 1 + j, 0), kFedS - 1);
+            cy[j] = min(max(py - 1 + j, 0), kFedS - 1);
         }
 #pragma unroll
-    for (int r = 0; r < kFedP; ++r)
+        for (int r = 0; r < kFedP; ++r) {
+            const float* row = bufB + (py + r) * kFedS;
 #pragma unroll
-        for (int j = 0; j <= kFedP; ++j) {
-            const int cl = px + j - 1, cr = px + j, ly = py + r;
-            float v = 0.f;
-            if (in_img(cl, ly) && in_img(cr, ly)) v = __fadd_rn(bufB[ly * kFedS + cl], bufB[ly * kFedS + cr]);
-            CE[r][j] = v;
+            for (int j = 0; j <= kFedP; ++j) CE[r][j] = __fadd_rn(row[cx[j]], row[cx[j + 1]]);
         }
 #pragma unroll
-    for (int i = 0; i <= kFedP; ++i)
+        for (int i = 0; i <= kFedP; ++i)
 #pragma unroll
-        for (int c = 0; c < kFedP; ++c) {
-            const int lu = py + i - 1, ld = py + i, lx = px + c;
-            float v = 0.f;
-            if (in_img(lx, lu) && in_img(lx, ld)) v = __fadd_rn(bufB[lu * kFedS + lx], bufB[ld * kFedS + lx]);
-            CS[i][c] = v;
-        }
+            for (int c = 0; c < kFedP; ++c) CS[i][c] = __fadd_rn(bufB[cy[i] * kFedS + px + c], bufB[cy[i + 1] * kFedS + px + c]);
+    } else {
+        auto in_img = [&](int lx, int ly) {
+            const int gx = x0 + lx, gy = y0 + ly;
+            return lx >= 0 && lx < kFedS && ly >= 0 && ly < kFedS && gx >= 0 && gx < W && gy >= 0 && gy < H;
+        };
+#pragma unroll
+        for (int r = 0; r < kFedP; ++r)
+#pragma unroll
+            for (int c = 0; c < kFedP; ++c) {
+                const int gx = x0 + px + c, gy = y0 + py + r;
+                if ((gy == 0 || gy == H - 1) && (gx == 0 || gx == W - 1)) corner |= 1u << (r * kFedP + c);
+            }
+#pragma unroll
+        for (int r = 0; r < kFedP; ++r)
+#pragma unroll
+            for (int j = 0; j <= kFedP; ++j) {
+                const int cl = px + j - 1, cr = px + j, ly = py + r;
+                float v = 0.f;
+                if (in_img(cl, ly) && in_img(cr, ly)) v = __fadd_rn(bufB[ly * kFedS + cl], bufB[ly * kFedS + cr]);
+                CE[r][j] = v;
+            }
+#pragma unroll
+        for (int i = 0; i <= kFedP; ++i)
+#pragma unroll
+            for (int c = 0; c < kFedP; ++c) {
+                const int lu = py + i - 1, ld = py + i, lx = px + c;
+                float v = 0.f;
+                if (in_img(lx, lu) && in_img(lx, ld)) v = __fadd_rn(bufB[lu * kFedS + lx], bufB[ld * kFedS + lx]);
+                CS[i][c] = v;
+            }
+    }
     __syncthreads();   // bufB (conductivities) becomes the second ping-pong buffer
     float* cur = bufA;
     float* nxt = bufB;
@@ -485,10 +529,16 @@ k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout,
         for (int c = 0; c < kFedP; ++c) nxt[(py + r) * kFedS + px + c] = L[r][c];
     __syncthreads();
     float* lout = Lout + (size_t)f * out_stride;
-    for (int i = tid; i < T * T; i += 256) {
-        const int r = i / T, c = i - r * T;
-        const int gx = x0 + K + c, gy = y0 + K + r;
-        if (gx < W && gy < H) lout[(size_t)gy * W + gx] = nxt[(r + K) * kFedS + c + K];
+    // valid window [K, kFedS - K)^2 -> global, same (ty + 16k, tx + 16m) mapping as the load
+#pragma unroll
+    for (int k = 0; k < kFedP; ++k) {
+        const int ly = ty + 16 * k, gy = y0 + ly;
+        if (ly < K || ly >= kFedS - K || gy >= H) continue;
+#pragma unroll
+        for (int m = 0; m < kFedP; ++m) {
+            const int lx = tx + 16 * m, gx = x0 + lx;
+            if (lx >= K && lx < kFedS - K && gx < W) lout[(size_t)gy * W + gx] = nxt[ly * kFedS + lx];
+        }
     }
 }
 
