@@ -132,6 +132,7 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
        const float* __restrict__ Lt, const float* __restrict__ Lx, const float* __restrict__ Ly, size_t pyr_stride,
        LevelsDev lv, uint4* __restrict__ desc64_all) {
     __shared__ int vals_all[kWarpsPerBlock][29 * 3];
+    __shared__ float pts_all[kWarpsPerBlock][441][3];
     const int f = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ki = blockIdx.x * kWarpsPerBlock + warp;
@@ -148,6 +149,42 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
     const float* lt = Lt + (size_t)f * pyr_stride + e.plane_off;
     const float* lx = Lx + (size_t)f * pyr_stride + e.plane_off;
     const float* ly = Ly + (size_t)f * pyr_stride + e.plane_off;
+    // The three cell grids (2x2 of 10x10, 3x3 of 7x7, 4x4 of 5x5 samples) all sample the same 21 x 21 lattice
+    // of offsets (k, l) in -10..10.  Phase 1 gathers every lattice point ONCE with all 32 lanes (441 x 3 plane
+    // reads instead of 1241 x 3): the 14 rounds are fully unrolled with clamped (always valid) addresses, so all
+    // 42 loads of a lane are in flight together — the kernel is bound by gather latency, not arithmetic.
+    // Phase 2 lets the 29 cell lanes add their samples from shared memory in OpenCV's (k, l) order, so the
+    // f32 sums are bit-identical.
+    float (*pts)[3] = pts_all[warp];
+    {
+        float ri[14], rx[14], ry[14];
+        bool ok[14];
+#pragma unroll
+        for (int it = 0; it < 14; ++it) {
+            const int p = min(lane + 32 * it, 440);
+            const int k = p / 21 - 10, l = p % 21 - 10;
+            const float sy = __fadd_rn(yf, __fadd_rn(__fmul_rn(__fmul_rn((float)l, co), fscale),
+                                                     __fmul_rn(__fmul_rn((float)k, si), fscale)));
+            const float sx = __fadd_rn(xf, __fadd_rn(__fmul_rn(__fmul_rn((float)(-l), si), fscale),
+                                                     __fmul_rn(__fmul_rn((float)k, co), fscale)));
+            const int y1 = __float2int_rn(sy), x1 = __float2int_rn(sx);
+            ok[it] = y1 >= 0 && y1 < e.h && x1 >= 0 && x1 < e.w;
+            const size_t o = (size_t)min(max(y1, 0), e.h - 1) * e.w + min(max(x1, 0), e.w - 1);
+            ri[it] = __ldg(lt + o);
+            rx[it] = __ldg(lx + o);
+            ry[it] = __ldg(ly + o);
+        }
+#pragma unroll
+        for (int it = 0; it < 14; ++it) {
+            const int p = lane + 32 * it;
+            if (p < 441) {
+                pts[p][0] = ok[it] ? ri[it] : __int_as_float(0x7fc00000);     // NaN marks a sample outside the image
+                pts[p][1] = __fadd_rn(__fmul_rn(-rx[it], si), __fmul_rn(ry[it], co));
+                pts[p][2] = __fadd_rn(__fmul_rn(rx[it], co), __fmul_rn(ry[it], si));
+            }
+        }
+    }
+    __syncwarp();
     if (lane < 29) {
         // cell -> (grid, i, j): pattern 10; steps 10, 7, 5 -> 2x2, 3x3, 4x4 cells starting at -10
         int step, n, local;
@@ -157,23 +194,17 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
         const int i0 = -10 + (local / n) * step, j0 = -10 + (local % n) * step;
         float di = 0.f, dx = 0.f, dy = 0.f;
         int nsamples = 0;
-        for (int k = i0; k < i0 + step; ++k)
-            for (int l = j0; l < j0 + step; ++l) {
-                const float sy = __fadd_rn(yf, __fadd_rn(__fmul_rn(__fmul_rn((float)l, co), fscale),
-                                                         __fmul_rn(__fmul_rn((float)k, si), fscale)));
-                const float sx = __fadd_rn(xf, __fadd_rn(__fmul_rn(__fmul_rn((float)(-l), si), fscale),
-                                                         __fmul_rn(__fmul_rn((float)k, co), fscale)));
-                const int y1 = __float2int_rn(sy), x1 = __float2int_rn(sx);
-                if (y1 < 0 || y1 >= e.h || x1 < 0 || x1 >= e.w) continue;
-                const size_t o = (size_t)y1 * e.w + x1;
-                const float ri = lt[o], rx = lx[o], ry = ly[o];
-                di = __fadd_rn(di, ri);
-                const float rry = __fadd_rn(__fmul_rn(rx, co), __fmul_rn(ry, si));
-                const float rrx = __fadd_rn(__fmul_rn(-rx, si), __fmul_rn(ry, co));
-                dx = __fadd_rn(dx, rrx);
-                dy = __fadd_rn(dy, rry);
+        for (int k = i0; k < i0 + step; ++k) {
+            const float* row = pts[(k + 10) * 21 + (j0 + 10)];
+            for (int l = 0; l < step; ++l) {
+                const float r0 = row[3 * l];
+                if (r0 != r0) continue;
+                di = __fadd_rn(di, r0);
+                dx = __fadd_rn(dx, row[3 * l + 1]);
+                dy = __fadd_rn(dy, row[3 * l + 2]);
                 ++nsamples;
             }
+        }
         if (nsamples > 0) {
             const float inv = __fdiv_rn(1.0f, (float)nsamples);
             di = __fmul_rn(di, inv); dx = __fmul_rn(dx, inv); dy = __fmul_rn(dy, inv);

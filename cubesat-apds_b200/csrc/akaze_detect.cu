@@ -19,21 +19,34 @@ __global__ void __launch_bounds__(256)
 k_extrema(const float* __restrict__ Ldet, size_t pyr_stride, LevelDev e, int level, int row_base, float thr,
           Cand* __restrict__ cand_raw, int cand_cap, int* __restrict__ cand_count, int* __restrict__ row_count,
           int total_rows) {
+    // a block covers 32 x 32 pixels; every thread issues its 4 centre loads (rows y, y+8, y+16, y+24) before
+    // testing any of them: almost every pixel fails the threshold, so the kernel is one streaming read and
+    // needs the memory-level parallelism, not the arithmetic
     const int f = blockIdx.z;
     const int x = e.border + blockIdx.x * 32 + threadIdx.x;
-    const int y = e.border + blockIdx.y * 8 + threadIdx.y;
-    if (x >= e.w - e.border || y >= e.h - e.border) return;
+    const int y0 = e.border + blockIdx.y * 32 + threadIdx.y;
+    if (x >= e.w - e.border) return;
     const float* L = Ldet + (size_t)f * pyr_stride + e.plane_off;
-    const float* c = L + (size_t)y * e.w + x;
-    const float v = c[0];
-    if (!(v > thr)) return;
-    const float* u = c - e.w;
-    const float* d = c + e.w;
-    if (v <= c[-1] || v <= c[1] || v <= u[-1] || v <= u[0] || v <= u[1] || v <= d[-1] || v <= d[0] || v <= d[1]) return;
-    const int i = atomicAdd(&cand_count[f], 1);
-    if (i < cand_cap) {
-        cand_raw[(size_t)f * cand_cap + i] = Cand{x, y, level, v};
-        atomicAdd(&row_count[(size_t)f * (total_rows + 1) + row_base + y], 1);
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = y0 + 8 * k;
+        v[k] = y < e.h - e.border ? L[(size_t)y * e.w + x] : -1.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = y0 + 8 * k;
+        if (!(v[k] > thr) || y >= e.h - e.border) continue;
+        const float* c = L + (size_t)y * e.w + x;
+        const float* u = c - e.w;
+        const float* d = c + e.w;
+        const float vv = v[k];
+        if (vv <= c[-1] || vv <= c[1] || vv <= u[-1] || vv <= u[0] || vv <= u[1] || vv <= d[-1] || vv <= d[0] || vv <= d[1]) continue;
+        const int i = atomicAdd(&cand_count[f], 1);
+        if (i < cand_cap) {
+            cand_raw[(size_t)f * cand_cap + i] = Cand{x, y, level, vv};
+            atomicAdd(&row_count[(size_t)f * (total_rows + 1) + row_base + y], 1);
+        }
     }
 }
 
@@ -415,7 +428,7 @@ int akaze_detect(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const Aka
         if (iw <= 0 || ih <= 0) continue;
         {
             ProfScope ps(ctx, st, "detect.extrema", (double)frames * iw * ih * 4);
-            k_extrema<<<dim3(div_up(iw, 32), div_up(ih, 8), frames), dim3(32, 8), 0, st>>>(
+            k_extrema<<<dim3(div_up(iw, 32), div_up(ih, 32), frames), dim3(32, 8), 0, st>>>(
                 ws.Ldet, pyr, lv.lv[i], i, row_base_h[i], dthreshold, ws.cand_raw, ws.cand_cap, ws.cand_count, ws.row_count,
                 ws.total_rows);
             DUNK_KERNEL_CHECK(ctx);
