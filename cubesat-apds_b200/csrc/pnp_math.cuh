@@ -492,6 +492,186 @@ DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], dou
     return err[N] / n;
 }
 
+// ---- P3P minimal solver (SOLVEPNP_P3P, and OpenCV's kernel whenever exactly 4 points are given) ----
+// Unknown depths s0, s1 = u s0, s2 = v s0 along the unit bearings of three image points; eliminating s0 and v
+// from the three law-of-cosines equations leaves a quartic in u (coefficients derived symbolically,
+// tools/derive_p3p.py).  Roots with OpenCV's Ferrari / Cardano routines (p3p.cpp solve_deg4 / solve_deg3),
+// triad alignment of the camera-frame triangle with the world triangle (they are congruent), and the fourth
+// point selects the solution with the smallest squared reprojection error in normalised coordinates.
+DUNK_HD inline int solve_deg2(double a, double b, double c, double* x) {
+    const double delta = b * b - 4 * a * c;
+    if (delta < 0) return 0;
+    const double inv_2a = 0.5 / a;
+    if (delta == 0) { x[0] = -b * inv_2a; return 1; }
+    const double s = sqrt(delta);
+    x[0] = (-b + s) * inv_2a;
+    x[1] = (-b - s) * inv_2a;
+    return 2;
+}
+
+DUNK_HD inline int solve_deg3(double a, double b, double c, double d, double* x) {
+    if (a == 0) {
+        if (b == 0) {
+            if (c == 0) return 0;
+            x[0] = -d / c;
+            return 1;
+        }
+        return solve_deg2(b, c, d, x);
+    }
+    const double inv_a = 1.0 / a;
+    const double b_a = inv_a * b, c_a = inv_a * c, d_a = inv_a * d, b_a2 = b_a * b_a;
+    const double Q = (3 * c_a - b_a2) / 9;
+    const double R = (9 * b_a * c_a - 27 * d_a - 2 * b_a * b_a2) / 54;
+    const double Q3 = Q * Q * Q, D = Q3 + R * R, b_a_3 = (1.0 / 3.0) * b_a;
+    if (Q == 0) {
+        if (R == 0) { x[0] = x[1] = x[2] = -b_a_3; return 3; }
+        const double cr = pow(fabs(2 * R), 1.0 / 3.0);
+        x[0] = (R < 0 ? -cr : cr) - b_a_3;
+        return 1;
+    }
+    if (D <= 0) {
+        double arg = R / sqrt(-Q3);
+        arg = arg > 1. ? 1. : arg < -1. ? -1. : arg;
+        const double theta = acos(arg), sq = sqrt(-Q);
+        x[0] = 2 * sq * cos(theta / 3.0) - b_a_3;
+        x[1] = 2 * sq * cos((theta + 2 * 3.14159265358979323846) / 3.0) - b_a_3;
+        x[2] = 2 * sq * cos((theta + 4 * 3.14159265358979323846) / 3.0) - b_a_3;
+        return 3;
+    }
+    double AD = 0, BD = 0;
+    const double R_abs = fabs(R);
+    if (R_abs > DBL_EPSILON) {
+        AD = pow(R_abs + sqrt(D), 1.0 / 3.0);
+        AD = R >= 0 ? AD : -AD;
+        BD = -Q / AD;
+    }
+    x[0] = AD + BD - b_a_3;
+    return 1;
+}
+
+DUNK_HD inline int solve_deg4(double a, double b, double c, double d, double e, double* x) {
+    if (a == 0) return solve_deg3(b, c, d, e, x);
+    const double inv_a = 1.0 / a;
+    b *= inv_a; c *= inv_a; d *= inv_a; e *= inv_a;
+    const double b2 = b * b, bc = b * c, b3 = b2 * b;
+    double r[3];
+    if (solve_deg3(1, -c, d * b - 4 * e, 4 * c * e - d * d - b2 * e, r) == 0) return 0;
+    const double r0 = r[0];
+    const double R2 = 0.25 * b2 - c + r0;
+    if (R2 < 0) return 0;
+    const double R = sqrt(R2);
+    double D2, E2;
+    if (R < 10e-12) {
+        const double temp = r0 * r0 - 4 * e;
+        if (temp < 0) D2 = E2 = -1;
+        else {
+            const double st = sqrt(temp);
+            D2 = 0.75 * b2 - 2 * c + 2 * st;
+            E2 = D2 - 4 * st;
+        }
+    } else {
+        const double uu = 0.75 * b2 - 2 * c - R2, vv = 0.25 * (1.0 / R) * (4 * bc - 8 * d - b3);
+        D2 = uu + vv;
+        E2 = uu - vv;
+    }
+    const double b_4 = 0.25 * b, R_2 = 0.5 * R;
+    int n = 0;
+    if (D2 >= 0) {
+        const double D = sqrt(D2);
+        x[0] = R_2 + 0.5 * D - b_4;
+        x[1] = x[0] - D;
+        n = 2;
+    }
+    if (E2 >= 0) {
+        const double E = sqrt(E2);
+        x[n] = -R_2 + 0.5 * E - b_4;
+        x[n + 1] = x[n] - E;
+        n += 2;
+    }
+    return n;
+}
+
+// orthonormal frame of a triangle as the COLUMNS of M (row-major 3 x 3)
+DUNK_HD inline void triad(const double* p0, const double* p1, const double* p2, double* M) {
+    double e1[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    const double n1 = 1.0 / sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    e1[0] *= n1; e1[1] *= n1; e1[2] *= n1;
+    const double w[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+    double e3[3] = {e1[1] * w[2] - e1[2] * w[1], e1[2] * w[0] - e1[0] * w[2], e1[0] * w[1] - e1[1] * w[0]};
+    const double n3 = 1.0 / sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+    e3[0] *= n3; e3[1] *= n3; e3[2] *= n3;
+    const double e2[3] = {e3[1] * e1[2] - e3[2] * e1[1], e3[2] * e1[0] - e3[0] * e1[2], e3[0] * e1[1] - e3[1] * e1[0]};
+    for (int r = 0; r < 3; ++r) { M[3 * r] = e1[r]; M[3 * r + 1] = e2[r]; M[3 * r + 2] = e3[r]; }
+}
+
+// cv::solvePnP(4 points, SOLVEPNP_P3P); idx selects the 4 points (null = 0..3).  false: no real solution
+DUNK_HD inline bool p3p_solve4(const float* obj, const float* img, const int* idx, const Camera& cam, bool f32_normalised,
+                               double (&Rout)[9], double (&tout)[3]) {
+    double P[4][3], xy[4][2], f[3][3];
+    for (int i = 0; i < 4; ++i) {
+        const int j = idx ? idx[i] : i;
+        P[i][0] = obj[3 * j]; P[i][1] = obj[3 * j + 1]; P[i][2] = obj[3 * j + 2];
+        double xn = ((double)img[2 * j] - cam.uc) * (1.0 / cam.fu), yn = ((double)img[2 * j + 1] - cam.vc) * (1.0 / cam.fv);
+        if (f32_normalised) { xn = (double)(float)xn; yn = (double)(float)yn; }
+        xy[i][0] = xn; xy[i][1] = yn;
+    }
+    for (int i = 0; i < 3; ++i) {
+        const double nr = 1.0 / sqrt(xy[i][0] * xy[i][0] + xy[i][1] * xy[i][1] + 1.0);
+        f[i][0] = xy[i][0] * nr; f[i][1] = xy[i][1] * nr; f[i][2] = nr;
+    }
+    auto d2 = [&](int i, int j) {
+        return (P[i][0] - P[j][0]) * (P[i][0] - P[j][0]) + (P[i][1] - P[j][1]) * (P[i][1] - P[j][1]) + (P[i][2] - P[j][2]) * (P[i][2] - P[j][2]);
+    };
+    auto dot = [&](int i, int j) { return f[i][0] * f[j][0] + f[i][1] * f[j][1] + f[i][2] * f[j][2]; };
+    const double a = d2(0, 1), b = d2(0, 2), c = d2(1, 2), p = dot(0, 1), q = dot(0, 2), r = dot(1, 2);
+    if (a == 0 || b == 0 || c == 0) return false;
+    const double k4 = -a * a + 4 * a * b * r * r - 2 * a * b + 2 * a * c - b * b + 2 * b * c - c * c;
+    const double k3 = -4 * (-a * a * q * r + 2 * a * b * p * r * r - a * b * p + a * b * q * r + a * c * p + a * c * q * r - b * b * p + 2 * b * c * p - c * c * p);
+    const double k2 = -2 * (2 * a * a * q * q + 2 * a * a * r * r - a * a - 4 * a * b * p * q * r - 2 * a * b * r * r - 4 * a * c * p * q * r - 2 * a * c * q * q +
+                            2 * b * b * p * p + b * b - 4 * b * c * p * p - 2 * b * c + 2 * c * c * p * p + c * c);
+    const double k1 = -4 * (-a * a * q * r + a * b * p + a * b * q * r + 2 * a * c * p * q * q - a * c * p + a * c * q * r - b * b * p + 2 * b * c * p - c * c * p);
+    const double k0 = -a * a + 2 * a * b + 4 * a * c * q * q - 2 * a * c - b * b + 2 * b * c - c * c;
+    double roots[4];
+    const int nr = solve_deg4(k4, k3, k2, k1, k0, roots);
+    double Mw[9];
+    triad(P[0], P[1], P[2], Mw);
+    bool found = false;
+    double best = 0;
+    for (int s = 0; s < nr; ++s) {
+        const double u = roots[s];
+        if (!(u > 0)) continue;
+        const double den = 2 * a * (q - r * u);
+        if (den == 0) continue;
+        const double v = (-a * u * u + a + 2 * b * p * u - b * u * u - b - 2 * c * p * u + c * u * u + c) / den;
+        const double w = 1 + u * u - 2 * u * p;
+        if (!(v > 0 && w > 0)) continue;
+        const double s0 = sqrt(a / w), s1 = u * s0, s2 = v * s0;
+        const double C0[3] = {s0 * f[0][0], s0 * f[0][1], s0 * f[0][2]};
+        const double C1[3] = {s1 * f[1][0], s1 * f[1][1], s1 * f[1][2]};
+        const double C2[3] = {s2 * f[2][0], s2 * f[2][1], s2 * f[2][2]};
+        double Mc[9], R[9], t[3];
+        triad(C0, C1, C2, Mc);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[3 * i + j] = Mc[3 * i] * Mw[3 * j] + Mc[3 * i + 1] * Mw[3 * j + 1] + Mc[3 * i + 2] * Mw[3 * j + 2];
+        for (int i = 0; i < 3; ++i) t[i] = C0[i] - (R[3 * i] * P[0][0] + R[3 * i + 1] * P[0][1] + R[3 * i + 2] * P[0][2]);
+        const double X = R[0] * P[3][0] + R[1] * P[3][1] + R[2] * P[3][2] + t[0];
+        const double Y = R[3] * P[3][0] + R[4] * P[3][1] + R[5] * P[3][2] + t[1];
+        const double Z = R[6] * P[3][0] + R[7] * P[3][1] + R[8] * P[3][2] + t[2];
+        const double ex = X / Z - xy[3][0], ey = Y / Z - xy[3][1];
+        const double e = ex * ex + ey * ey;
+        bool fin = e == e;
+        for (int i = 0; i < 9; ++i) fin = fin && (R[i] - R[i] == 0);
+        if (!fin) continue;
+        if (!found || e < best) {
+            found = true;
+            best = e;
+            for (int i = 0; i < 9; ++i) Rout[i] = R[i];
+            for (int i = 0; i < 3; ++i) tout[i] = t[i];
+        }
+    }
+    return found;
+}
+
 // cv::projectPoints (zero distortion) + PnPRansacCallback::computeError for one point: the f64
 // projection is rounded to f32, the squared distance is f32.  R2 = Rodrigues(rvec) of the model.
 // (separate multiplies and adds: OpenCV's build does not contract them into FMAs)

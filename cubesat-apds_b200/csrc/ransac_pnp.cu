@@ -28,7 +28,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxRound = 128;       // hypotheses solved + scored per round
 constexpr int kFirstRound = 32;      // the adaptive stop usually fires inside the first round
 constexpr unsigned long long kRngCoeff = 4164903690ull;
-constexpr int kModelPoints = 5;
+constexpr int kMaxModelPoints = 5;   // EPnP kernel: 5-point samples; P3P kernel: 4-point samples
 
 struct Rng {
     unsigned long long state;
@@ -53,7 +53,7 @@ __device__ int update_num_iters(double p, double ep, int model_points, int max_i
 struct Shared {
     unsigned long long rng_state;
     int niters, iter, best_count, best_h, done, nh;
-    int hyp[kMaxRound][kModelPoints];
+    int hyp[kMaxRound][kMaxModelPoints];
     int counts[kMaxRound];
     double model[kMaxRound][12];     // Rodrigues(rvec(R)) (9) + t (3) of every hypothesis of the round
     double best[12];
@@ -115,11 +115,15 @@ __device__ int warp_count_inliers(const double* model, const Camera& cam, const 
     return c;
 }
 
-// 5-point EPnP + the model's rvec round trip; false when the pose is not finite
+// minimal solve (5-point EPnP or 4-point P3P) + the model's rvec round trip; false when there is no finite pose
 __device__ bool solve_minimal(const float* obj, const float* img, const int* idx, int n_pts, const Camera& cam, double* model) {
-    SerialExec ex{obj, img, idx, n_pts, cam, true};
     double R[9], t[3], r[3];
-    epnp_solve(ex, cam, R, t);
+    if (n_pts == 4) {
+        if (!p3p_solve4(obj, img, idx, cam, true, R, t)) return false;
+    } else {
+        SerialExec ex{obj, img, idx, n_pts, cam, true};
+        epnp_solve(ex, cam, R, t);
+    }
     rodrigues_to_vector(R, r);
     bool ok = true;
 #pragma unroll
@@ -133,8 +137,8 @@ __device__ bool solve_minimal(const float* obj, const float* img, const int* idx
 // obj: [total][3] f32, img: [total][2] f32 (already rounded from the caller's f64, as OpenCV does)
 __global__ void __launch_bounds__(kThreads)
 pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ img_all, const int* __restrict__ starts,
-                  const int* __restrict__ counts, const double* __restrict__ K_all, int max_iters, float thr, double confidence,
-                  double* __restrict__ rt_out /* [B][6] rvec, tvec */, uint8_t* __restrict__ mask_out,
+                  const int* __restrict__ counts, const double* __restrict__ K_all, int method, int max_iters, float thr,
+                  double confidence, double* __restrict__ rt_out /* [B][6] rvec, tvec */, uint8_t* __restrict__ mask_out,
                   int* __restrict__ info_out /* [B][4]: found, inliers, iterations, hypotheses */) {
     __shared__ Shared sh;
     const int b = blockIdx.x;
@@ -158,18 +162,28 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
         }
     };
 
-    if (n < kModelPoints) {   // the host API rejects n < 4 (-215) and n == 4 (P3P kernel, not built)
+    // solvepnp.cpp: 5-point samples + EPnP kernel, except 4-point samples + P3P kernel when P3P is requested or
+    // when there are exactly 4 correspondences
+    const int mp = (method == DUNK_PNP_P3P || n == 4) ? 4 : 5;
+    if (n < 4) {   // the host API rejects this (-215)
         for (int i = tid; i < n; i += kThreads) mask[i] = 0;
         finish(0, 0, 0, 0, nullptr, nullptr);
         return;
     }
-    if (n == kModelPoints) {
-        // solvepnp.cpp: model_points == npoints -> one solvePnP on all (f32) points, every point an inlier
+    if (n == mp) {
+        // model_points == npoints -> one solvePnP on all (f32) points, every point an inlier
         double R[9], t[3], r[3];
-        SerialExec ex{obj, img, nullptr, n, cam, true};
-        epnp_solve(ex, cam, R, t);
-        rodrigues_to_vector(R, r);
         bool ok = true;
+        if (mp == 4) ok = p3p_solve4(obj, img, nullptr, cam, true, R, t);
+        else {
+            SerialExec ex{obj, img, nullptr, n, cam, true};
+            epnp_solve(ex, cam, R, t);
+        }
+        if (!ok) {
+            for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0);
+            t[0] = t[1] = t[2] = 0;
+        }
+        rodrigues_to_vector(R, r);
         for (int i = 0; i < 3; ++i) ok = ok && isfinite(r[i]) && isfinite(t[i]);
         for (int i = tid; i < n; i += kThreads) mask[i] = ok;
         finish(ok, ok ? n : 0, 0, 0, r, t);
@@ -189,8 +203,8 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
             const int want = min(round == 0 ? kFirstRound : kMaxRound, sh.niters - sh.iter);
             Rng rng{sh.rng_state};
             for (int h = 0; h < want; ++h) {
-                int idx[kModelPoints];
-                for (int i = 0; i < kModelPoints; ++i) {
+                int idx[kMaxModelPoints];
+                for (int i = 0; i < mp; ++i) {
                     int v;
                     bool dup;
                     do {
@@ -200,7 +214,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
                     } while (dup);
                     idx[i] = v;
                 }
-                for (int i = 0; i < kModelPoints; ++i) sh.hyp[h][i] = idx[i];
+                for (int i = 0; i < mp; ++i) sh.hyp[h][i] = idx[i];
             }
             sh.rng_state = rng.state;
             sh.nh = want;
@@ -210,7 +224,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
         // ---- (2) solve: one thread per hypothesis -------------------------------------------
         if (tid < nh) {
             double model[12];
-            const bool ok = solve_minimal(obj, img, sh.hyp[tid], kModelPoints, cam, model);
+            const bool ok = solve_minimal(obj, img, sh.hyp[tid], mp, cam, model);
             for (int i = 0; i < 12; ++i) sh.model[tid][i] = model[i];
             sh.counts[tid] = ok ? 0 : -1;
         }
@@ -226,10 +240,10 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
         if (tid == 0) {
             for (int h = 0; h < nh && sh.iter < sh.niters; ++h) {
                 const int good = sh.counts[h];
-                if (good > max(sh.best_count, kModelPoints - 1)) {
+                if (good > max(sh.best_count, mp - 1)) {
                     sh.best_count = good;
                     for (int i = 0; i < 12; ++i) sh.best[i] = sh.model[h][i];
-                    sh.niters = update_num_iters(confidence, (double)(n - good) / n, kModelPoints, sh.niters);
+                    sh.niters = update_num_iters(confidence, (double)(n - good) / n, mp, sh.niters);
                 }
                 ++sh.iter;
             }
@@ -284,7 +298,7 @@ pnp_score_kernel(const float* __restrict__ obj, const float* __restrict__ img, i
     const Camera cam{Kp[0], Kp[4], Kp[2], Kp[5]};
     const float thr2 = (float)((double)thr * (double)thr);
     if (h < n_hyp && lane == 0) {
-        SerialExec ex{obj, img, samples + h * kModelPoints, kModelPoints, cam, true};
+        SerialExec ex{obj, img, samples + h * 5, 5, cam, true};
         double R[9], t[3], r[3];
         epnp_solve(ex, cam, R, t);
         rodrigues_to_vector(R, r);
@@ -317,17 +331,15 @@ int dunk_pnp_ransac_batch(dunk_ctx* ctx, const double* obj, const double* img, c
     DUNK_REQUIRE(ctx && offsets && K && rvecs && tvecs && info && n_problems >= 0, DUNK_ERR_BAD_ARG,
                  "dunk_pnp_ransac_batch: NULL argument");
     if (n_problems == 0) return DUNK_OK;
-    DUNK_REQUIRE(method == DUNK_PNP_EPNP, DUNK_ERR_BAD_ARG,
-                 "dunk_pnp_ransac: method %d not implemented (SOLVEPNP_EPNP = 1, the reference's default, is)", method);
+    DUNK_REQUIRE(method == DUNK_PNP_EPNP || method == DUNK_PNP_P3P, DUNK_ERR_BAD_ARG,
+                 "dunk_pnp_ransac: method %d not implemented (SOLVEPNP_EPNP = 1, the reference's default, and SOLVEPNP_P3P = 2 are)",
+                 method);
     const int total = offsets[n_problems];
     for (int b = 0; b < n_problems; ++b) {
         const int n = offsets[b + 1] - offsets[b];
         // cv::solvePnPRansac: CV_Assert(npoints >= 4 && ...) -> StsAssert (-215); reference test
         // pnp_solver_ransac_no_work_lthan_3_points, homographier/src/homographier/mod.rs:627-638
         DUNK_REQUIRE(n >= 4, DUNK_ERR_ASSERT, "dunk_pnp_ransac: problem %d has %d correspondences, at least 4 are needed", b, n);
-        DUNK_REQUIRE(n != 4, DUNK_ERR_BAD_ARG,
-                     "dunk_pnp_ransac: problem %d has exactly 4 correspondences; OpenCV switches to its P3P kernel there, "
-                     "which is not implemented", b);
     }
     DUNK_REQUIRE(obj && img, DUNK_ERR_BAD_ARG, "dunk_pnp_ransac_batch: NULL points");
     SlotGuard g(ctx);
@@ -359,7 +371,8 @@ int dunk_pnp_ransac_batch(dunk_ctx* ctx, const double* obj, const double* img, c
     DUNK_CUDA(cudaMemcpyAsync(d_K, K, (size_t)n_problems * 72, cudaMemcpyHostToDevice, st));
     {
         ProfScope ps(ctx, st, "ransac.pnp", 0.0);
-        pnp_ransac_kernel<<<n_problems, kThreads, 0, st>>>(d_obj, d_img, d_off, d_cnt, d_K, iters, thr, confidence, d_rt, d_mask, d_info);
+        pnp_ransac_kernel<<<n_problems, kThreads, 0, st>>>(d_obj, d_img, d_off, d_cnt, d_K, method, iters, thr, confidence, d_rt, d_mask,
+                                                           d_info);
         ctx->launches.fetch_add(1);
         DUNK_CUDA(cudaGetLastError());
     }
@@ -406,7 +419,7 @@ int dunk_pnp_score_hypotheses(dunk_ctx* ctx, const double* obj, const double* im
     DUNK_REQUIRE(ctx && obj && img && K && samples && counts && rt && n >= 5 && n_hyp >= 0, DUNK_ERR_BAD_ARG,
                  "dunk_pnp_score_hypotheses: bad argument");
     if (n_hyp == 0) return DUNK_OK;
-    for (int i = 0; i < n_hyp * kModelPoints; ++i)
+    for (int i = 0; i < n_hyp * 5; ++i)
         DUNK_REQUIRE(samples[i] >= 0 && samples[i] < n, DUNK_ERR_OUT_OF_RANGE,
                      "dunk_pnp_score_hypotheses: sample index %d outside 0..%d", samples[i], n - 1);
     SlotGuard g(ctx);
@@ -422,13 +435,13 @@ int dunk_pnp_score_hypotheses(dunk_ctx* ctx, const double* obj, const double* im
     float* d_obj = cv.take<float>((size_t)n * 3);
     float* d_img = cv.take<float>((size_t)n * 2);
     double* d_K = cv.take<double>(9);
-    int* d_s = cv.take<int>((size_t)n_hyp * kModelPoints);
+    int* d_s = cv.take<int>((size_t)n_hyp * 5);
     int* d_c = cv.take<int>(n_hyp);
     double* d_rt = cv.take<double>((size_t)n_hyp * 6);
     DUNK_CUDA(cudaMemcpyAsync(d_obj, h_obj.data(), h_obj.size() * 4, cudaMemcpyHostToDevice, st));
     DUNK_CUDA(cudaMemcpyAsync(d_img, h_img.data(), h_img.size() * 4, cudaMemcpyHostToDevice, st));
     DUNK_CUDA(cudaMemcpyAsync(d_K, K, 72, cudaMemcpyHostToDevice, st));
-    DUNK_CUDA(cudaMemcpyAsync(d_s, samples, (size_t)n_hyp * kModelPoints * 4, cudaMemcpyHostToDevice, st));
+    DUNK_CUDA(cudaMemcpyAsync(d_s, samples, (size_t)n_hyp * 5 * 4, cudaMemcpyHostToDevice, st));
     pnp_score_kernel<<<div_up(n_hyp, kWarps), kThreads, 0, st>>>(d_obj, d_img, n, d_K, d_s, n_hyp, (float)thr, d_c, d_rt);
     ctx->launches.fetch_add(1);
     DUNK_CUDA(cudaGetLastError());

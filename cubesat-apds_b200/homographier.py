@@ -244,7 +244,7 @@ def pnp_solver_ransac(point_correspondences, camera_intrinsic, iter_count: int, 
 
 
 def pnp_solver_ransac_batch(obj_list, img_list, camera_intrinsics, iter_count: int, reproj_thres: float, confidence: float,
-                            ctx: Optional[_lib.Context] = None):
+                            ctx: Optional[_lib.Context] = None, method: Optional[SolvePnPMethod] = None):
     """Frame-batched pnp_solver_ransac (one CTA per frame; partitioned by frame, no collective).
     camera_intrinsics: one 3x3 for all frames or one per frame.
     Returns (rvecs [B,3], tvecs [B,3], inlier masks list, info [B,4] = found/inliers/iters/hypotheses)."""
@@ -261,7 +261,8 @@ def pnp_solver_ransac_batch(obj_list, img_list, camera_intrinsics, iter_count: i
     mask = np.zeros(max(int(offsets[-1]), 1), dtype=np.uint8)
     info = np.zeros((B, 4), dtype=np.int32)
     check(_lib.load().dunk_pnp_ransac_batch(ctx.handle, ptr(obj), ptr(img), ptr(offsets), B, ptr(K), int(iter_count),
-                                            float(reproj_thres), float(confidence), int(SolvePnPMethod.SOLVEPNP_EPNP),
+                                            float(reproj_thres), float(confidence),
+                                            int(SolvePnPMethod.SOLVEPNP_EPNP if method is None else method),
                                             ptr(rvecs), ptr(tvecs), ptr(mask), ptr(info)))
     return rvecs, tvecs, [mask[offsets[i]:offsets[i + 1]].astype(bool) for i in range(B)], info
 

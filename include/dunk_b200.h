@@ -257,8 +257,9 @@ int dunk_ransac_score_hypotheses(dunk_ctx* ctx, const float* src, const float* d
  * OpenCV the f64 points are rounded to f32 first.  rvec/tvec: 3 f64 each.  inliers: indices of the
  * inliers of the best minimal model in increasing order (capacity inliers_cap; may be NULL).
  * *found = 0 when no pose was found (the reference returns Ok(None), mod.rs:367).
- * n < 4 -> DUNK_ERR_ASSERT (-215, reference test mod.rs:627-638).  Only DUNK_PNP_EPNP is
- * implemented; other methods and n == 4 (where OpenCV switches to its P3P kernel) ->
+ * n < 4 -> DUNK_ERR_ASSERT (-215, reference test mod.rs:627-638).  Methods: DUNK_PNP_EPNP (5-point
+ * samples, EPnP kernel) and DUNK_PNP_P3P (4-point samples, P3P kernel; also used, as in OpenCV,
+ * whenever n == 4); the final pose is EPnP over the inliers in both cases.  Other methods ->
  * DUNK_ERR_BAD_ARG. */
 int dunk_pnp_ransac(dunk_ctx* ctx, const double* obj, const double* img, int n, const double* K,
                     int iters, float thr, double confidence, int method, double* rvec, double* tvec,

@@ -363,3 +363,197 @@ def solve_pnp_ransac(obj, img, K, iters=100, thr=8.0, confidence=0.99):
     if sol is None:
         return False, rv, tv, np.zeros(0, np.int32)
     return True, sol[0], sol[1], np.nonzero(mask)[0].astype(np.int32)
+
+
+# ----------------------------------------------------------------------------- P3P (SOLVEPNP_P3P)
+# OpenCV's p3p.cpp (Gao et al.) solves a quartic for the ratio of two depths and aligns the three
+# camera-frame points with Horn's quaternion method.  The restatement below uses the same unknowns
+# (Fischler-Bolles form s1 = u s0, s2 = v s0; the quartic's coefficients were derived symbolically,
+# tools/derive_p3p.py), OpenCV's Ferrari / Cardano root finder (solve_deg4 / solve_deg3), a triad
+# alignment (exact for the congruent triangles P3P produces) and OpenCV's rule for the 4th point: the
+# solution with the smallest squared reprojection error in normalised coordinates wins.  Every correct
+# P3P returns the same geometric solutions, so poses agree with cv2 to rounding (~1e-9), not bitwise.
+def _solve_deg2(a, b, c):
+    delta = b * b - 4 * a * c
+    if delta < 0:
+        return []
+    inv_2a = 0.5 / a
+    if delta == 0:
+        return [-b * inv_2a]
+    s = math.sqrt(delta)
+    return [(-b + s) * inv_2a, (-b - s) * inv_2a]
+
+
+def _solve_deg3(a, b, c, d):
+    if a == 0:
+        if b == 0:
+            return [] if c == 0 else [-d / c]
+        return _solve_deg2(b, c, d)
+    inv_a = 1.0 / a
+    b_a, c_a, d_a = inv_a * b, inv_a * c, inv_a * d
+    b_a2 = b_a * b_a
+    Q = (3 * c_a - b_a2) / 9
+    R = (9 * b_a * c_a - 27 * d_a - 2 * b_a * b_a2) / 54
+    Q3 = Q * Q * Q
+    D = Q3 + R * R
+    b_a_3 = (1.0 / 3.0) * b_a
+    if Q == 0:
+        if R == 0:
+            return [-b_a_3] * 3
+        return [math.copysign(abs(2 * R) ** (1 / 3.0), R) - b_a_3]
+    if D <= 0:
+        theta = math.acos(max(-1.0, min(1.0, R / math.sqrt(-Q3))))
+        sq = math.sqrt(-Q)
+        return [2 * sq * math.cos(theta / 3.0) - b_a_3, 2 * sq * math.cos((theta + 2 * math.pi) / 3.0) - b_a_3,
+                2 * sq * math.cos((theta + 4 * math.pi) / 3.0) - b_a_3]
+    AD, BD = 0.0, 0.0
+    R_abs = abs(R)
+    if R_abs > DBL_EPSILON:
+        AD = (R_abs + math.sqrt(D)) ** (1 / 3.0)
+        AD = AD if R >= 0 else -AD
+        BD = -Q / AD
+    return [AD + BD - b_a_3]
+
+
+def _solve_deg4(a, b, c, d, e):
+    if a == 0:
+        return _solve_deg3(b, c, d, e)
+    inv_a = 1.0 / a
+    b, c, d, e = b * inv_a, c * inv_a, d * inv_a, e * inv_a
+    b2, bc, b3 = b * b, b * c, b * b * b
+    r = _solve_deg3(1, -c, d * b - 4 * e, 4 * c * e - d * d - b2 * e)
+    if not r:
+        return []
+    r0 = r[0]
+    R2 = 0.25 * b2 - c + r0
+    if R2 < 0:
+        return []
+    R = math.sqrt(R2)
+    if R < 10e-12:
+        temp = r0 * r0 - 4 * e
+        if temp < 0:
+            D2 = E2 = -1.0
+        else:
+            st = math.sqrt(temp)
+            D2 = 0.75 * b2 - 2 * c + 2 * st
+            E2 = D2 - 4 * st
+    else:
+        uu = 0.75 * b2 - 2 * c - R2
+        vv = 0.25 * (1.0 / R) * (4 * bc - 8 * d - b3)
+        D2, E2 = uu + vv, uu - vv
+    b_4, R_2 = 0.25 * b, 0.5 * R
+    out = []
+    if D2 >= 0:
+        D = math.sqrt(D2)
+        x0 = R_2 + 0.5 * D - b_4
+        out += [x0, x0 - D]
+    if E2 >= 0:
+        E = math.sqrt(E2)
+        x2 = -R_2 + 0.5 * E - b_4
+        out += [x2, x2 - E]
+    return out
+
+
+def _triad(p0, p1, p2):
+    e1 = p1 - p0
+    e1 = e1 / math.sqrt(float(e1 @ e1))
+    e3 = np.cross(e1, p2 - p0)
+    e3 = e3 / math.sqrt(float(e3 @ e3))
+    return np.stack([e1, np.cross(e3, e1), e3], 1)          # columns
+
+
+def p3p_solutions(obj3, xy3):
+    """all (R, t) with R X_i + t on the bearing of normalised image point i, i = 0..2"""
+    P = np.asarray(obj3, np.float64)
+    f = np.c_[np.asarray(xy3, np.float64), np.ones(3)]
+    f = f / np.sqrt((f * f).sum(1))[:, None]
+    a, b, c = ((P[0] - P[1]) ** 2).sum(), ((P[0] - P[2]) ** 2).sum(), ((P[1] - P[2]) ** 2).sum()
+    p, q, r = float(f[0] @ f[1]), float(f[0] @ f[2]), float(f[1] @ f[2])
+    if a == 0 or b == 0 or c == 0:
+        return []
+    k4 = -a * a + 4 * a * b * r * r - 2 * a * b + 2 * a * c - b * b + 2 * b * c - c * c
+    k3 = -4 * (-a * a * q * r + 2 * a * b * p * r * r - a * b * p + a * b * q * r + a * c * p + a * c * q * r - b * b * p + 2 * b * c * p - c * c * p)
+    k2 = -2 * (2 * a * a * q * q + 2 * a * a * r * r - a * a - 4 * a * b * p * q * r - 2 * a * b * r * r - 4 * a * c * p * q * r - 2 * a * c * q * q
+               + 2 * b * b * p * p + b * b - 4 * b * c * p * p - 2 * b * c + 2 * c * c * p * p + c * c)
+    k1 = -4 * (-a * a * q * r + a * b * p + a * b * q * r + 2 * a * c * p * q * q - a * c * p + a * c * q * r - b * b * p + 2 * b * c * p - c * c * p)
+    k0 = -a * a + 2 * a * b + 4 * a * c * q * q - 2 * a * c - b * b + 2 * b * c - c * c
+    sols = []
+    for u in _solve_deg4(k4, k3, k2, k1, k0):
+        if not (u > 0):
+            continue
+        den = 2 * a * (q - r * u)
+        if den == 0:
+            continue
+        v = (-a * u * u + a + 2 * b * p * u - b * u * u - b - 2 * c * p * u + c * u * u + c) / den
+        w = 1 + u * u - 2 * u * p
+        if not (v > 0 and w > 0):
+            continue
+        s0 = math.sqrt(a / w)
+        C = np.stack([s0 * f[0], u * s0 * f[1], v * s0 * f[2]])
+        R = _triad(C[0], C[1], C[2]) @ _triad(P[0], P[1], P[2]).T
+        t = C[0] - R @ P[0]
+        if np.isfinite(R).all() and np.isfinite(t).all():
+            sols.append((R, t))
+    return sols
+
+
+def solve_pnp_p3p(obj4, img4, K, f32_normalised=False):
+    """cv::solvePnP(4 points, SOLVEPNP_P3P): P3P on the first three points, the fourth picks the solution.
+    Returns (rvec, tvec) or None."""
+    obj4 = np.asarray(obj4, np.float64).reshape(4, 3)
+    img4 = np.asarray(img4, np.float64).reshape(4, 2)
+    fu, fv, uc, vc = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    xn, yn = (img4[:, 0] - uc) * (1.0 / fu), (img4[:, 1] - vc) * (1.0 / fv)
+    if f32_normalised:
+        xn, yn = xn.astype(np.float32).astype(np.float64), yn.astype(np.float32).astype(np.float64)
+    xy = np.stack([xn, yn], 1)
+    best = None
+    for R, t in p3p_solutions(obj4[:3], xy[:3]):
+        X = R @ obj4[3] + t
+        e = (X[0] / X[2] - xy[3, 0]) ** 2 + (X[1] / X[2] - xy[3, 1]) ** 2
+        if best is None or e < best[0]:
+            best = (e, R, t)
+    if best is None:
+        return None
+    return rodrigues_to_vector(best[1]), best[2]
+
+
+def solve_pnp_ransac_p3p(obj, img, K, iters=100, thr=8.0, confidence=0.99):
+    """cv::solvePnPRansac(..., flags = SOLVEPNP_P3P): 4-point samples, P3P kernel, final EPnP on the inliers
+    (solvepnp.cpp replaces P3P by EPNP for the final solve)."""
+    obj32 = np.ascontiguousarray(obj, dtype=np.float64).reshape(-1, 3).astype(np.float32)
+    img32 = np.ascontiguousarray(img, dtype=np.float64).reshape(-1, 2).astype(np.float32)
+    K = np.asarray(K, dtype=np.float64).reshape(3, 3)
+    n = obj32.shape[0]
+    if n < 4:
+        raise ValueError("-215: solvePnPRansac needs at least 4 correspondences")
+    objd, imgd = obj32.astype(np.float64), img32.astype(np.float64)
+    none = (False, np.zeros(3), np.zeros(3), np.zeros(0, np.int32))
+    if n == 4:
+        sol = solve_pnp_p3p(objd, imgd, K, True)
+        return none if sol is None else (True, sol[0], sol[1], np.arange(4, dtype=np.int32))
+    thr2 = np.float32(float(thr) * float(thr))
+    rng = CvRNG()
+    niters, best, best_count, it = iters, None, 0, 0
+    while it < niters:
+        idx = []
+        for _ in range(4):
+            v = rng.uniform(0, n)
+            while v in idx:
+                v = rng.uniform(0, n)
+            idx.append(v)
+        sol = solve_pnp_p3p(objd[idx], imgd[idx], K, True)
+        if sol is not None:
+            mask = reproj_err_f32(obj32, img32, sol[0], sol[1], K) <= thr2
+            good = int(mask.sum())
+            if good > max(best_count, 3):
+                best, best_count = (sol, mask), good
+                niters = ransac_update_num_iters(confidence, (n - good) / n, 4, niters)
+        it += 1
+    if best is None:
+        return none
+    mask = best[1]
+    sol = solve_pnp_epnp(objd[mask], imgd[mask], K)
+    if sol is None:
+        return False, best[0][0], best[0][1], np.zeros(0, np.int32)
+    return True, sol[0], sol[1], np.nonzero(mask)[0].astype(np.int32)

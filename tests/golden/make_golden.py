@@ -169,6 +169,22 @@ def make_pnp():
         out[f"c{i}_rvec"], out[f"c{i}_tvec"] = r.ravel(), t.ravel()
         out[f"c{i}_inliers"] = np.zeros(0, np.int32) if inl is None else inl.ravel().astype(np.int32)
         print(f"pnp case {i}: n={n} found={ok} inliers={len(out[f'c{i}_inliers'])}")
+    # the same cases through the P3P kernel (4-point samples; the final pose is still EPnP on the inliers)
+    for i, (n, of, noise, iters, thr, conf, relief) in enumerate(PNP_CASES):
+        obj, img = pnp_case(i, n, of, noise, relief)
+        ok, r, t, inl = cv2.solvePnPRansac(obj, img, PNP_K, np.zeros((4, 1)), None, None, False, iters, thr, conf, None,
+                                           cv2.SOLVEPNP_P3P)
+        out[f"p{i}_found"] = np.array(bool(ok))
+        out[f"p{i}_rvec"], out[f"p{i}_tvec"] = r.ravel(), t.ravel()
+        out[f"p{i}_inliers"] = np.zeros(0, np.int32) if inl is None else inl.ravel().astype(np.int32)
+    # exactly 4 correspondences: OpenCV runs P3P once whatever the flag is
+    for j in range(12):
+        obj, img = pnp_case(200 + j, 4, 0.0, 0.3, "cube")
+        ok, r, t, inl = cv2.solvePnPRansac(obj, img, PNP_K, np.zeros((4, 1)), None, None, False, 100, 8.0, 0.99, None,
+                                           cv2.SOLVEPNP_EPNP)
+        out[f"q{j}_obj"], out[f"q{j}_img"], out[f"q{j}_found"] = obj, img, np.array(bool(ok))
+        out[f"q{j}_rt"] = np.r_[r.ravel(), t.ravel()]
+    out["n_four"] = np.array(12)
     # plain EPnP solves (f64 points and f32 points take different undistortPoints precisions)
     rng = np.random.default_rng(99)
     for j, n in enumerate((6, 7, 12, 40, 300)):

@@ -31,6 +31,15 @@ double hc_epnp(const float* obj, const float* img, const int* idx, int n, const 
     return e;
 }
 
+int hc_p3p(const float* obj, const float* img, const int* idx, const double* K, int f32n, double* rvec, double* tvec) {
+    Camera cam{K[0], K[4], K[2], K[5]};
+    double R[9], t[3];
+    if (!p3p_solve4(obj, img, idx, cam, f32n != 0, R, t)) return 0;
+    rodrigues_to_vector(R, rvec);
+    for (int i = 0; i < 3; ++i) tvec[i] = t[i];
+    return 1;
+}
+
 void hc_reproj_err(const double* rvec, const double* tvec, const double* K, const float* obj, const float* img, int n, float* err) {
     Camera cam{K[0], K[4], K[2], K[5]};
     double R2[9];

@@ -58,3 +58,36 @@ def test_too_few_points():
 def test_sample_stream_is_the_homography_stream_with_5_points():
     s = po.sample_stream(100, 4)
     assert s.shape == (4, 5) and all(len(set(r)) == 5 for r in s.tolist())
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_solve_pnp_ransac_p3p_matches_cv2(i):
+    """flags = SOLVEPNP_P3P (the method the reference's own `pnp_solver_works` test passes, mod.rs:640-681)"""
+    iters, thr, conf = G[f"c{i}_params"]
+    found, r, t, inl = po.solve_pnp_ransac_p3p(G[f"c{i}_obj"], G[f"c{i}_img"], K, int(iters), float(thr), float(conf))
+    assert found == bool(G[f"p{i}_found"])
+    assert np.array_equal(inl, G[f"p{i}_inliers"])
+    if found:
+        assert np.abs(r - G[f"p{i}_rvec"]).max() < 1e-6 and np.abs(t - G[f"p{i}_tvec"]).max() < 1e-6
+
+
+def _reproj(obj, img, rt):
+    return np.abs(po.project_points(obj, rt[:3], rt[3:], K) - img).max(axis=1)
+
+
+def test_four_points_run_p3p_once():
+    """n == 4: one P3P solve.  Both implementations must return a pose that reproduces the first three points exactly
+    and the fourth equally well (near-double roots of the quartic make the pose itself ill-conditioned in ~4 % of cases)"""
+    same = 0
+    for j in range(int(G["n_four"])):
+        obj, img = G[f"q{j}_obj"], G[f"q{j}_img"]
+        found, r, t, inl = po.solve_pnp_ransac_p3p(obj, img, K)
+        assert found == bool(G[f"q{j}_found"])
+        if not found:
+            continue
+        o32, i32 = obj.astype(np.float32).astype(np.float64), img.astype(np.float32).astype(np.float64)
+        e_ours, e_cv = _reproj(o32, i32, np.r_[r, t]), _reproj(o32, i32, G[f"q{j}_rt"])
+        assert e_ours[:3].max() < 1e-3 and e_cv[:3].max() < 1e-3
+        assert abs(e_ours[3] - e_cv[3]) <= 0.05 * max(e_cv[3], 1e-3)
+        same += np.abs(np.r_[r, t] - G[f"q{j}_rt"]).max() < 1e-6
+    assert same >= int(G["n_four"]) - 2

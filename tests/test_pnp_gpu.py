@@ -69,7 +69,54 @@ def test_reference_test_too_few_points(dunk, ctx):
 def test_unsupported_methods_fail_loudly(dunk, ctx):
     hg = dunk.homographier
     with pytest.raises(hg.MatError):
-        hg.pnp_solver_ransac((G["c0_obj"], G["c0_img"]), K, 100, 8.0, 0.99, None, hg.SolvePnPMethod.SOLVEPNP_P3P, ctx)
+        hg.pnp_solver_ransac((G["c0_obj"], G["c0_img"]), K, 100, 8.0, 0.99, None, hg.SolvePnPMethod.SOLVEPNP_ITERATIVE, ctx)
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_pnp_ransac_p3p_vs_cv2_golden(dunk, ctx, i):
+    """SOLVEPNP_P3P: 4-point samples through the P3P kernel, final EPnP on the inliers"""
+    hg = dunk.homographier
+    iters, thr, conf = G[f"c{i}_params"]
+    sol = hg.pnp_solver_ransac((G[f"c{i}_obj"], G[f"c{i}_img"]), K, int(iters), float(thr), float(conf), None,
+                               hg.SolvePnPMethod.SOLVEPNP_P3P, ctx)
+    if not bool(G[f"p{i}_found"]):
+        assert sol is None
+        return
+    assert sol is not None
+    assert np.array_equal(sol.inliers.mat.ravel(), G[f"p{i}_inliers"])
+    assert np.abs(sol.rvec.mat.ravel() - G[f"p{i}_rvec"]).max() < POSE_ATOL
+    assert np.abs(sol.tvec.mat.ravel() - G[f"p{i}_tvec"]).max() < POSE_ATOL
+
+
+def test_reference_test_pnp_solver_works(dunk, ctx):
+    """mod.rs:640-681 (#[ignore]d in the reference): 5 correspondences, SOLVEPNP_P3P, 10000 iterations, threshold 100,
+    confidence 0.5 -> Ok(Some(_)); camera_matrix() of the test module is not in scope of the hot path: a generic K"""
+    hg = dunk.homographier
+    corres = [hg.ImgObjCorrespondence((0, 5, 1), (-1.48, 0.39)), hg.ImgObjCorrespondence((5, 0, 0), (2.14, -1.92)),
+              hg.ImgObjCorrespondence((5, 5, 1.5), (1.74, 0.56)), hg.ImgObjCorrespondence((0, 0, 1), (-2, -1.62)),
+              hg.ImgObjCorrespondence((2, 8, -2), (-0.16, 0.3))]
+    Kc = np.array([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0]])
+    res = hg.pnp_solver_ransac(corres, hg.Cmat(Kc, np.float64), 10000, 100.0, 0.5, None, hg.SolvePnPMethod.SOLVEPNP_P3P, ctx)
+    obj = np.array([c.obj_point for c in corres]); img = np.array([c.img_point for c in corres])
+    f, rv, tv, inl = po.solve_pnp_ransac_p3p(obj, img, Kc, 10000, 100.0, 0.5)
+    assert (res is not None) == f
+    if f:
+        assert np.array_equal(res.inliers.mat.ravel(), inl)
+
+
+def test_four_points_use_p3p(dunk, ctx):
+    hg = dunk.homographier
+    ok = 0
+    for j in range(int(G["n_four"])):
+        obj, img = G[f"q{j}_obj"], G[f"q{j}_img"]
+        sol = hg.pnp_solver_ransac((obj, img), K, 100, 8.0, 0.99, None, None, ctx)
+        assert (sol is not None) == bool(G[f"q{j}_found"])
+        if sol is None:
+            continue
+        assert sol.inliers.mat.ravel().tolist() == [0, 1, 2, 3]
+        f, r, t, _ = po.solve_pnp_ransac_p3p(obj, img, K)
+        ok += np.abs(np.r_[sol.rvec.mat.ravel(), sol.tvec.mat.ravel()] - np.r_[r, t]).max() < 1e-6
+    assert ok >= int(G["n_four"]) - 2
 
 
 def test_batch_equals_single(dunk, ctx):

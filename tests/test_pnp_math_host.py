@@ -96,3 +96,26 @@ def test_minimal_samples_score_like_the_oracle(hc, i):
         assert c_host == c_oracle or max(c_host, c_oracle) <= 4
         acceptable += c_oracle > 4
     assert acceptable >= 1
+
+
+def test_p3p_host_math_matches_oracle(hc):
+    """the device's P3P (quartic + triad) on the host vs the oracle: same success flag, same pose up to the quartic's
+    conditioning"""
+    hc.hc_p3p.restype = C.c_int
+    rng = np.random.default_rng(3)
+    close = total = 0
+    for _ in range(200):
+        rv = rng.normal(0, 0.5, 3)
+        tv = np.array([0.3, -0.2, 8.0]) + rng.normal(0, 0.5, 3)
+        obj = rng.uniform(-2, 2, (4, 3)).astype(np.float32)
+        P = obj.astype(np.float64) @ po.rodrigues_to_matrix(rv).T + tv
+        img = (np.stack([K[0, 0] * P[:, 0] / P[:, 2] + K[0, 2], K[1, 1] * P[:, 1] / P[:, 2] + K[1, 2]], 1)
+               + rng.normal(0, 0.3, (4, 2))).astype(np.float32)
+        r, t = np.zeros(3), np.zeros(3)
+        ok = hc.hc_p3p(ptr(obj), ptr(img), None, ptr(np.ascontiguousarray(K)), 1, ptr(r), ptr(t))
+        sol = po.solve_pnp_p3p(obj.astype(np.float64), img.astype(np.float64), K, True)
+        assert bool(ok) == (sol is not None)
+        if ok:
+            total += 1
+            close += np.abs(np.r_[r, t] - np.r_[sol[0], sol[1]]).max() < 1e-6
+    assert total > 150 and close >= 0.95 * total
