@@ -614,6 +614,17 @@ def run_match(args):
     os._exit(0)
 
 
+def measured_traffic(kernel, shape_key):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), only when the
+    capture was taken at this run's shape; otherwise None (the contract allows null)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        e = t.get(kernel, {})
+        return e.get("dram_bytes_per_launch") if e.get("shape") == shape_key else None
+    except Exception:
+        return None
+
+
 def stage_times(ctx, lib, db, slot, f_dev, B, ws, ws_bytes, res_dev, args):
     """Device time per stage, measured with the library's CUDA-event profiler over extra steps."""
     from cubesat_apds_b200._lib import check
@@ -643,7 +654,9 @@ def stage_times(ctx, lib, db, slot, f_dev, B, ws, ws_bytes, res_dev, args):
             peak = popc * 1e3 / 16.0
             return {"bound": "int", "kernel": top, "achieved": ach, "peak": peak, "unit": "Gpairs/s (16 POPC per pair)",
                     "frac": ach / peak, "peak_source": "POPC-pipe microbenchmark measured in this run (%.2f Tpopc/s)" % popc,
-                    "traffic": None, "share_of_step": t["ms"] / sum(s["ms"] for s in stages.values())}
+                    "traffic": measured_traffic("hamming_top2_kernel", f"pipeline frames={B} scene={args.scene}"),
+                    "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read + write, profiles/r1_traffic.json)",
+                    "share_of_step": t["ms"] / sum(s["ms"] for s in stages.values())}
         ach = t["alg_bytes_or_ops"] / (t["ms"] * 1e-3) / 1e9                # GB/s
         return {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": ach / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None,

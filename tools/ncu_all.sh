@@ -22,6 +22,9 @@ ncu -i gpurun_out/prof_hamming_final.ncu-rep --page raw --csv > gpurun_out/prof_
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:l2_candidates -s 2 -c 2 -o gpurun_out/prof_l2_final -f \
   python tools/bench_match_l2.py 3163 2000000 64 > gpurun_out/ncu_l2.log 2>&1
 ncu -i gpurun_out/prof_l2_final.ncu-rep --page raw --csv > gpurun_out/prof_l2_final_raw.csv 2>/dev/null
+# (b2) DRAM traffic of the matcher launch at the bench's own shape (64 frames x 289 k rows): one cheap pass
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:hamming_top2 -s 4 -c 1 --csv \
+  --log-file gpurun_out/traffic_hamming_pipeline.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_traffic.log 2>&1
 # (d) extraction kernels
 bash tools/ncu_extract.sh > gpurun_out/ncu_extract_sh.log 2>&1
 rm -f gpurun_out/*.ncu-rep
