@@ -109,3 +109,25 @@ def test_sharded_phases_equal_unsharded(dunk, ctx):
     for s in shards:
         s.close()
     whole.close()
+
+
+def test_degenerate_frames_and_databases_do_not_break_the_batch(dunk, ctx):
+    """a flat frame (no keypoints), a frame of noise (no consistent matches) and a real frame in one batch; then a DB
+    with a single row (no 2-NN possible): every frame gets a result record, nothing is registered by accident"""
+    import synthdata
+    fd = dunk.feature_database
+    tile = synthdata.synth_image(512, 512, 7)
+    db = fd.DescriptorDatabase(ctx, capacity=20000)
+    db.append_tiles(tile[None], [0], [0], [1], [1])
+    flat = np.full((512, 512), 128, np.uint8)
+    noise = np.random.default_rng(0).integers(0, 256, (512, 512), dtype=np.uint8)
+    res = db.register_frames(np.stack([flat, tile, noise]))
+    assert res["keypoints"][0] == 0 and res["found"][0] == 0 and res["matches"][0] == 0
+    assert res["found"][1] == 1 and res["inliers"][1] > 100
+    assert np.abs(res["H"][1].reshape(3, 3) - np.eye(3)).max() < 1e-3
+    assert res["found"][2] == 0 or res["inliers"][2] < 12
+    one = fd.DescriptorDatabase(ctx, capacity=4)
+    one.append(db.read_descriptors(0, 1))
+    r1 = one.register_frames(tile[None])
+    assert r1["found"][0] == 0 and r1["matches"][0] == 0 and r1["keypoints"][0] > 100
+    db.close(); one.close()
