@@ -34,6 +34,7 @@ struct KnnPlan {
 };
 
 KnnPlan plan_knn2(dunk_ctx* ctx, int nq, uint32_t nt);
+size_t knn2_partial_bound(dunk_ctx* ctx, size_t nq_max);
 // scratch needed for slab partials
 inline size_t knn2_partial_bytes(const KnnPlan& p, int nq) { return (size_t)p.gx * nq * 16; }
 

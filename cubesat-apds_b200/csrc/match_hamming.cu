@@ -10,6 +10,7 @@
 // stable-argsort rule OpenCV's batchDistance follows.  Slabs (grid.x)
 // are merged by (distance, index) in a second tiny kernel; the same merge serves the
 // multi-GPU shards after the allgather.
+#include <algorithm>
 #include "match.h"
 
 namespace dunk {
@@ -357,16 +358,41 @@ KnnPlan plan_knn2(dunk_ctx* ctx, int nq, uint32_t nt) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<kQT>, p.threads, p.smem);
         if (occ < 1) occ = 1;
     }
-    // equal-sized slabs so that (query groups x slabs) fills ~2 waves of warp slots
+    // equal-sized slabs: (query groups x slabs) work items on `slots` resident warps.  All items cost the same,
+    // so the launch takes ceil(items / slots) rounds; pick the slab count whose last round is fullest
+    // (e.g. 1233 query groups x 4 slabs would be 2.08 rounds = 69 % efficiency, x 19 slabs is 9.9 rounds = 99 %).
+    // Slabs stay >= 32 tiles (2048 rows) so the per-item set-up (64 query registers, barrier ring) is amortised.
     const long long slots = (long long)ctx->sm_count * occ * kWarpsPerCta;
-    long long slabs = (slots * 2 + p.gy - 1) / p.gy;
-    if (slabs > total_tiles) slabs = total_tiles;
-    if (slabs < 1) slabs = 1;
+    const long long max_slabs = std::max<long long>(1, std::min<long long>(total_tiles / 32, 4096));
+    long long slabs = 1;
+    double best_eff = -1.0;
+    for (long long s = 1; s <= max_slabs; ++s) {
+        const long long tps = div_up(total_tiles, s);
+        const long long real_slabs = div_up(total_tiles, tps);
+        const long long items = real_slabs * p.gy;
+        const long long rounds = (items + slots - 1) / slots;
+        const double eff = (double)items / (double)(rounds * slots);
+        // prefer clearly better efficiency; among near-equals the fewer slabs (less merge work)
+        if (eff > best_eff + 0.02) { best_eff = eff; slabs = real_slabs; }
+        if (items > 16 * slots) break;
+    }
     p.tiles_per_cta = div_up(total_tiles, slabs);
     if (p.tiles_per_cta < 1) p.tiles_per_cta = 1;
     p.gx = div_up(total_tiles, p.tiles_per_cta);   // slabs
     if (p.gx < 1) p.gx = 1;
     return p;
+}
+
+// upper bound of plan.gx * nq * 16 over every query count <= nq_max (callers that size a workspace before the
+// query count is known): the planner never creates more than max(query groups, 16 * resident warps) work items
+size_t knn2_partial_bound(dunk_ctx* ctx, size_t nq_max) {
+    const KnnPlan probe = plan_knn2(ctx, 1, 1);   // initialises the occupancy query
+    (void)probe;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<kQT>, kWarpsPerCta * 32, probe.smem);
+    const size_t slots = (size_t)ctx->sm_count * (size_t)std::max(occ, 1) * kWarpsPerCta;
+    const size_t groups = (nq_max + 32 * kQT - 1) / (32 * kQT);
+    return std::max(groups, 16 * slots + groups) * (32 * kQT) * 16;
 }
 
 #define DUNK_LAUNCH_CHECK(ctx)                                                        \

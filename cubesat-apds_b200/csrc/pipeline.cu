@@ -149,8 +149,8 @@ static PipelinePlan plan_pipeline(dunk_ctx* ctx, int rows, int cols, int frames,
     p.ws_bytes = akaze_workspace_bytes(p.lt, frames, p.cand_cap, p.kp_cap);
     const size_t nq_max = (size_t)frames * p.kp_cap;
     // worst-case slab count for the matcher: plan with the largest query count
-    const KnnPlan kp = plan_knn2(ctx, (int)std::min<size_t>(nq_max, 1u << 30), (uint32_t)std::max<int64_t>(db_rows, 1));
-    p.partial_bytes = (size_t)kp.gx * nq_max * 16;
+    (void)db_rows;
+    p.partial_bytes = knn2_partial_bound(ctx, nq_max);
     p.total_bytes = al(p.ws_bytes) + al((frames + 1) * 4) + al(nq_max * 64) + al(nq_max * 16) + al(p.partial_bytes) +
                     2 * al(nq_max * 8) + al(nq_max * 16) + al(frames * 4) + al((size_t)frames * 72) + al(nq_max) +
                     al((size_t)frames * 16) + al((size_t)frames * sizeof(DunkRegistration));
