@@ -2,6 +2,7 @@
 // Follows Compute_Main_Orientation / MLDB_Full_Descriptor_Invoker of OpenCV's AKAZEFeatures.cpp as
 // restated in oracle/akaze_oracle.py: same sample tables, same f32 operation order (the sums are
 // kept sequential per window / per grid cell so that rounding matches), fastAtan2 polynomial.
+#include <algorithm>
 #include "akaze.h"
 #include <cfloat>
 #include <cmath>
@@ -14,8 +15,12 @@ struct OriTable {
     signed char xi[109], yi[109];
     float w[109];
 };
-__constant__ OriTable c_ori;
-__constant__ unsigned char c_cmp_a[486], c_cmp_b[486];   // value indices (cell * 3 + channel)
+// global, not __constant__: lanes index it with 32 distinct offsets (see g_cmp below)
+__device__ OriTable c_ori;
+// value indices (cell * 3 + channel) of the two operands of descriptor bit `dpos`, a | b << 8.  In GLOBAL memory
+// on purpose: lane l of a warp reads entry w * 32 + l, a coalesced 64-byte read; the constant cache would replay
+// the 32 distinct addresses one by one
+__device__ unsigned short g_cmp[512];
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     // cv::hal::fastAtan32f (mathfuncs_core), degrees
@@ -67,9 +72,9 @@ k_orientation(DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restr
     const float* ly = Ly + (size_t)f * pyr_stride + e.plane_off;
     const float ang_step = (float)(2.0 * M_PI / kSlices);
     for (int s = lane; s < kAng; s += 32) {
-        const int y = min(max(y0 + c_ori.yi[s] * scale, 0), e.h - 1);
-        const int x = min(max(x0 + c_ori.xi[s] * scale, 0), e.w - 1);
-        const float w = c_ori.w[s];
+        const int y = min(max(y0 + __ldg(&c_ori.yi[s]) * scale, 0), e.h - 1);
+        const int x = min(max(x0 + __ldg(&c_ori.xi[s]) * scale, 0), e.w - 1);
+        const float w = __ldg(&c_ori.w[s]);
         const float rx = __fmul_rn(w, lx[(size_t)y * e.w + x]);
         const float ry = __fmul_rn(w, ly[(size_t)y * e.w + x]);
         sh.rx[s] = rx;
@@ -132,11 +137,14 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
        const float* __restrict__ Lt, const float* __restrict__ Lx, const float* __restrict__ Ly, size_t pyr_stride,
        LevelsDev lv, uint4* __restrict__ desc64_all) {
     __shared__ int vals_all[kWarpsPerBlock][29 * 3];
-    __shared__ float pts_all[kWarpsPerBlock][441][3];
+    __shared__ float pri_all[kWarpsPerBlock][441];     // Lt at the lattice points (NaN = outside the image)
+    __shared__ float2 pxy_all[kWarpsPerBlock][441];    // rotated (Lx, Ly)
     const int f = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ki = blockIdx.x * kWarpsPerBlock + warp;
-    if (ki >= kp_count[f]) return;
+    // a fixed, small grid strides over the frame's keypoints: a grid sized for the keypoint CAPACITY is > 90 %
+    // empty blocks whose turnover (45 KB of shared memory each) would dominate the kernel
+    const int count = kp_count[f];
+    for (int ki = blockIdx.x * kWarpsPerBlock + warp; ki < count; ki += gridDim.x * kWarpsPerBlock) {
     int* vals = vals_all[warp];
     const DunkKeyPoint kp = kps_all[(size_t)f * kp_cap + ki];
     const LevelDev& e = lv.lv[kp.class_id];
@@ -155,7 +163,8 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
     // 42 loads of a lane are in flight together — the kernel is bound by gather latency, not arithmetic.
     // Phase 2 lets the 29 cell lanes add their samples from shared memory in OpenCV's (k, l) order, so the
     // f32 sums are bit-identical.
-    float (*pts)[3] = pts_all[warp];
+    float* pri = pri_all[warp];
+    float2* pxy = pxy_all[warp];
     {
         float ri[14], rx[14], ry[14];
         bool ok[14];
@@ -178,9 +187,9 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
         for (int it = 0; it < 14; ++it) {
             const int p = lane + 32 * it;
             if (p < 441) {
-                pts[p][0] = ok[it] ? ri[it] : __int_as_float(0x7fc00000);     // NaN marks a sample outside the image
-                pts[p][1] = __fadd_rn(__fmul_rn(-rx[it], si), __fmul_rn(ry[it], co));
-                pts[p][2] = __fadd_rn(__fmul_rn(rx[it], co), __fmul_rn(ry[it], si));
+                pri[p] = ok[it] ? ri[it] : __int_as_float(0x7fc00000);     // NaN marks a sample outside the image
+                pxy[p] = make_float2(__fadd_rn(__fmul_rn(-rx[it], si), __fmul_rn(ry[it], co)),
+                                     __fadd_rn(__fmul_rn(rx[it], co), __fmul_rn(ry[it], si)));
             }
         }
     }
@@ -194,15 +203,26 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
         const int i0 = -10 + (local / n) * step, j0 = -10 + (local % n) * step;
         float di = 0.f, dx = 0.f, dy = 0.f;
         int nsamples = 0;
-        for (int k = i0; k < i0 + step; ++k) {
-            const float* row = pts[(k + 10) * 21 + (j0 + 10)];
-            for (int l = 0; l < step; ++l) {
-                const float r0 = row[3 * l];
-                if (r0 != r0) continue;
-                di = __fadd_rn(di, r0);
-                dx = __fadd_rn(dx, row[3 * l + 1]);
-                dy = __fadd_rn(dy, row[3 * l + 2]);
-                ++nsamples;
+        // uniform 10 x 10 trip counts (cells of 7 x 7 / 5 x 5 samples mask the rest): the inner loop is fully
+        // unrolled with its 20 shared loads issued together; predicated adds keep OpenCV's (k, l) order exactly
+        for (int kk = 0; kk < 10; ++kk) {
+            const bool krow = kk < step;
+            const int rowbase = ((krow ? i0 + kk : i0) + 10) * 21 + (j0 + 10);
+            float r0[10];
+            float2 xy[10];
+#pragma unroll
+            for (int l = 0; l < 10; ++l) {
+                const int idx = rowbase + min(l, step - 1);
+                r0[l] = pri[idx];
+                xy[l] = pxy[idx];
+            }
+#pragma unroll
+            for (int l = 0; l < 10; ++l) {
+                const bool use = krow && l < step && r0[l] == r0[l];
+                di = use ? __fadd_rn(di, r0[l]) : di;
+                dx = use ? __fadd_rn(dx, xy[l].x) : dx;
+                dy = use ? __fadd_rn(dy, xy[l].y) : dy;
+                nsamples += use;
             }
         }
         if (nsamples > 0) {
@@ -219,7 +239,10 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
     for (int w = 0; w < 16; ++w) {
         const int dpos = w * 32 + lane;
         bool bit = false;
-        if (dpos < 486) bit = vals[c_cmp_a[dpos]] > vals[c_cmp_b[dpos]];
+        if (dpos < 486) {
+            const unsigned ab = __ldg(&g_cmp[dpos]);
+            bit = vals[ab & 255u] > vals[ab >> 8];
+        }
         word[w] = __ballot_sync(0xffffffffu, bit);
     }
     if (lane < 4) {
@@ -227,6 +250,8 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
         v.x = word[lane * 4 + 0]; v.y = word[lane * 4 + 1]; v.z = word[lane * 4 + 2]; v.w = word[lane * 4 + 3];
         // word[] is warp-uniform; select with a switch-free copy
         desc64_all[((size_t)f * kp_cap + ki) * 4 + lane] = v;
+    }
+    __syncwarp();
     }
 }
 
@@ -268,8 +293,9 @@ int upload_tables() {
         return DUNK_ERR_ASSERT;
     }
     DUNK_CUDA(cudaMemcpyToSymbol(c_ori, &t, sizeof t));
-    DUNK_CUDA(cudaMemcpyToSymbol(c_cmp_a, a, sizeof a));
-    DUNK_CUDA(cudaMemcpyToSymbol(c_cmp_b, b, sizeof b));
+    unsigned short ab[512] = {0};
+    for (int i = 0; i < 486; ++i) ab[i] = (unsigned short)(a[i] | (b[i] << 8));
+    DUNK_CUDA(cudaMemcpyToSymbol(g_cmp, ab, sizeof ab));
     g_tables_ready = true;
     return DUNK_OK;
 }
@@ -288,8 +314,9 @@ int akaze_describe(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const A
     }
     {
         ProfScope ps(ctx, st, "describe.mldb", 0.0);
-        k_mldb<<<grid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lt, ws.Lx, ws.Ly, lt.pyramid_floats, lv,
-                                                     ws.desc64);
+        const dim3 mgrid(std::min(div_up(ws.kp_cap, kWarpsPerBlock), 64), frames);
+        k_mldb<<<mgrid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lt, ws.Lx, ws.Ly, lt.pyramid_floats, lv,
+                                                      ws.desc64);
         DUNK_KERNEL_CHECK(ctx);
     }
     return DUNK_OK;
