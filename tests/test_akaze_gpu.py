@@ -58,6 +58,19 @@ def test_extract_vs_oracle_fresh_image(dunk, ctx):
     assert_parity(rep)
 
 
+def test_extract_odd_size_bgr_vs_oracle(dunk, ctx):
+    """517 x 333 BGR (no extent is a multiple of any tile size: every kernel runs partial and border tiles)"""
+    import synthdata
+    g = synthdata.synth_image(333, 517, 9)
+    img = np.stack([g, np.roll(g, 3, 1), np.roll(g, -2, 0)], -1).copy()
+    kps, desc = ao.detect_and_compute(img)
+    r = dunk.feature_extraction.akaze_keypoint_descriptor_extraction_def(img, None, ctx)
+    rep = compare(kps, desc, r.keypoints, r.descriptors)
+    print(rep)
+    assert len(kps) > 100
+    assert_parity(rep)
+
+
 def test_gray_bgr_bgra_identical(dunk, ctx):
     g = G["a_img"][:200, :240]
     fe = dunk.feature_extraction
