@@ -245,94 +245,77 @@ k_halfsample(const float* __restrict__ src, size_t src_stride, int sw, int sh, f
 }
 
 // ---- per level: Lsmooth = Gauss5(Lt_init), Lflow = PM-G2(Scharr(Lsmooth), k) --------------------
-// Same arithmetic as gauss5_tile + scharr_at above; all tile extents are compile-time, every stage is
-// a flat 256-thread loop, and tiles that do not touch the image border skip the clamp / reflect work.
-__global__ void __launch_bounds__(kBX* kBY)
+// No shared memory: a warp owns 32 adjacent columns and walks down the rows.
+// Horizontal neighbours come from warp shuffles, vertical neighbours from rolling register windows (5 rows of
+// the row-filtered values, 3 rows of the Gauss5 output), so a pixel costs ~6 SHFL instead of ~25 shared-memory
+// accesses.  Lanes 3..28 produce outputs (halo 2 for the Gaussian + 1 for Scharr on each side): 26 columns per
+// warp, kPrepRows rows per warp (+6 halo rows).  Same arithmetic expressions as gauss5_tile + scharr_at above
+// (the keypoint sets stay identical to OpenCV's).
+constexpr int kPrepCols = 26;
+constexpr int kPrepRows = 64;
+
+__global__ void __launch_bounds__(256)
 k_prep_level(const float* __restrict__ Lt, size_t lt_stride, int W, int H, Gauss5 g,
-             const float* __restrict__ kcontrast, float kscale, float* __restrict__ Lsmooth,
-             float* __restrict__ Lflow, size_t plane_stride) {
-    constexpr int AW = kTW + 6, AH = kTH + 6;     // clamped input, halo 3
-    constexpr int TWd = kTW + 2;                  // row-filtered, halo 1 in x, 3 in y
-    constexpr int BW = kTW + 2, BH = kTH + 2;     // Gauss5 output, halo 1
-    __shared__ float A[AH * AW];
-    __shared__ float T[AH * TWd];
-    __shared__ float B[BH * BW];
+                  const float* __restrict__ kcontrast, float kscale, float* __restrict__ Lsmooth,
+                  float* __restrict__ Lflow, size_t plane_stride) {
     const int f = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xs0 = (blockIdx.x * 8 + warp) * kPrepCols;      // first output column of this warp
+    if (xs0 >= W) return;
+    const int x = xs0 - 3 + lane;                             // this lane's column (may be outside the image)
+    const int xc = clampi(x, 0, W - 1);
+    const int y0 = blockIdx.y * kPrepRows;
     const float* src = Lt + (size_t)f * lt_stride;
-    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
-    const int tid = threadIdx.y * kBX + threadIdx.x;
-    const bool interior = x0 >= 3 && y0 >= 3 && x0 + kTW + 3 <= W && y0 + kTH + 3 <= H;
-    if (interior) {
-        const float* base = src + (size_t)(y0 - 3) * W + (x0 - 3);
-#pragma unroll
-        for (int it = 0; it < (AH * AW + 255) / 256; ++it) {
-            const int i = tid + it * 256;
-            if (i < AH * AW) {
-                const int ly = i / AW, lx = i - ly * AW;
-                A[i] = base[(size_t)ly * W + lx];
-            }
-        }
-    } else {
-#pragma unroll
-        for (int it = 0; it < (AH * AW + 255) / 256; ++it) {
-            const int i = tid + it * 256;
-            if (i < AH * AW) {
-                const int ly = i / AW, lx = i - ly * AW;
-                A[i] = src[(size_t)clampi(y0 + ly - 3, 0, H - 1) * W + clampi(x0 + lx - 3, 0, W - 1)];
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < (AH * TWd + 255) / 256; ++it) {
-        const int i = tid + it * 256;
-        if (i < AH * TWd) {
-            const int ly = i / TWd, lx = i - ly * TWd;
-            const float* a = &A[ly * AW + lx + 2];
-            T[i] = g.k[0] * a[0] + g.k[1] * (a[-1] + a[1]) + g.k[2] * (a[-2] + a[2]);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < (BH * BW + 255) / 256; ++it) {
-        const int i = tid + it * 256;
-        if (i < BH * BW) {
-            const int ly = i / BW, lx = i - ly * BW;
-            const float* t = &T[(ly + 2) * TWd + lx];
-            B[i] = g.k[0] * t[0] + g.k[1] * (t[-TWd] + t[TWd]) + g.k[2] * (t[-2 * TWd] + t[2 * TWd]);
-        }
-    }
-    __syncthreads();
-    if (!(x0 >= 1 && y0 >= 1 && x0 + kTW + 1 <= W && y0 + kTH + 1 <= H)) {
-        // B(lx, ly) sits at global (x0-1+lx, y0-1+ly); cells outside the image take the reflect-101 value
-        // (what Scharr's BORDER_DEFAULT sees)
-        for (int i = tid; i < BH * BW; i += 256) {
-            const int ly = i / BW, lx = i - ly * BW;
-            const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
-            if (gx < 0 || gx >= W || gy < 0 || gy >= H) {
-                const int rx = reflect101(gx, W), ry = reflect101(gy, H);
-                const int sx = rx - (x0 - 1), sy = ry - (y0 - 1);
-                if (sx >= 0 && sx < BW && sy >= 0 && sy < BH && rx >= 0 && ry >= 0) B[i] = B[sy * BW + sx];
-            }
-        }
-        __syncthreads();
-    }
-    const float k = __fmul_rn(kcontrast[f], kscale);
-    const float inv_k = __fdiv_rn(1.f, __fmul_rn(k, k));
     float* sm = Lsmooth + (size_t)f * plane_stride;
     float* fl = Lflow + (size_t)f * plane_stride;
+    const float k = __fmul_rn(kcontrast[f], kscale);
+    const float inv_k = __fdiv_rn(1.f, __fmul_rn(k, k));
+    const bool out_lane = lane >= 3 && lane < 3 + kPrepCols && x < W;
+    const bool left_edge = x - 1 < 0, right_edge = x + 1 >= W;
+    const unsigned full = 0xffffffffu;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;          // row-filtered rows yy-4 .. yy
+    float ul = 0.f, uc = 0.f, ur = 0.f, ml = 0.f, mc = 0.f, mr = 0.f;   // Gauss5 rows yb-2 (u) and yb-1 (m), with x neighbours
+    const int y_end = min(y0 + kPrepRows, H);
+    // software pipeline: the loads of the next 4 rows are in flight while the current 4 rows are processed
+    // (one load per lane per row would leave ~16 KB in flight per SM; Little's law then caps the kernel at ~2 TB/s)
+    constexpr int kAhead = 4;
+    float nxt[kAhead];
 #pragma unroll
-    for (int it = 0; it < kTW * kTH / 256; ++it) {
-        const int i = tid + it * 256;
-        const int ly = i / kTW, lx = i - ly * kTW;
-        const int gx = x0 + lx, gy = y0 + ly;
-        if (gx < W && gy < H) {
-            float dx, dy;
-            scharr_at(&B[ly * BW + lx + 1], &B[(ly + 1) * BW + lx + 1], &B[(ly + 2) * BW + lx + 1], dx, dy);
-            sm[(size_t)gy * W + gx] = B[(ly + 1) * BW + lx + 1];
-            // pm_g2: 1 / (1 + (Lx^2 + Ly^2) / k^2)
-            fl[(size_t)gy * W + gx] =
-                __fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(inv_k, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)))));
+    for (int i = 0; i < kAhead; ++i) nxt[i] = src[(size_t)clampi(y0 - 3 + i, 0, H - 1) * W + xc];
+    for (int base = y0 - 3; base <= y_end + 2; base += kAhead) {
+        float cur[kAhead];
+#pragma unroll
+        for (int i = 0; i < kAhead; ++i) cur[i] = nxt[i];
+#pragma unroll
+        for (int i = 0; i < kAhead; ++i) nxt[i] = src[(size_t)clampi(base + kAhead + i, 0, H - 1) * W + xc];
+#pragma unroll
+        for (int i = 0; i < kAhead; ++i) {
+        const int yy = base + i;
+        if (yy > y_end + 2) break;
+        const float a = cur[i];
+        const float am1 = __shfl_up_sync(full, a, 1), ap1 = __shfl_down_sync(full, a, 1);
+        const float am2 = __shfl_up_sync(full, a, 2), ap2 = __shfl_down_sync(full, a, 2);
+        t0 = t1; t1 = t2; t2 = t3; t3 = t4;
+        t4 = g.k[0] * a + g.k[1] * (am1 + ap1) + g.k[2] * (am2 + ap2);
+        const int yb = yy - 2;                                  // Gauss5 row that is complete now
+        if (yb < y0 - 1) continue;
+        const float b = g.k[0] * t2 + g.k[1] * (t1 + t3) + g.k[2] * (t0 + t4);
+        float bl = __shfl_up_sync(full, b, 1), br = __shfl_down_sync(full, b, 1);
+        if (left_edge) bl = br;                                 // reflect-101 of the smoothed image (Scharr's border)
+        if (right_edge) br = bl;
+        const int y = yb - 1;                                   // output row: needs Gauss5 rows y-1 (u), y (m), y+1 (b)
+        if (y >= y0 && y < y_end && out_lane) {
+            // rows outside the image are replaced by their reflection: row -1 -> row 1, row H -> row H-2
+            const float ul_ = y - 1 < 0 ? bl : ul, uc_ = y - 1 < 0 ? b : uc, ur_ = y - 1 < 0 ? br : ur;
+            const float dl_ = y + 1 >= H ? ul : bl, dc_ = y + 1 >= H ? uc : b, dr_ = y + 1 >= H ? ur : br;
+            const float lx = 3.f * (ur_ - ul_) + 10.f * (mr - ml) + 3.f * (dr_ - dl_);
+            const float ly = 3.f * (dl_ - ul_) + 10.f * (dc_ - uc_) + 3.f * (dr_ - ur_);
+            const size_t o = (size_t)y * W + x;
+            sm[o] = mc;
+            fl[o] = __fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(inv_k, __fadd_rn(__fmul_rn(lx, lx), __fmul_rn(ly, ly)))));
+        }
+        ul = ml; uc = mc; ur = mr;
+        ml = bl; mc = b; mr = br;
         }
     }
 }
@@ -872,7 +855,8 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
         const dim3 grid(div_up(e.w, kTW), div_up(e.h, kTH), frames);
         {
             ProfScope ps(ctx, st, "scale.prep_level", (double)frames * e.w * e.h * 12);
-            k_prep_level<<<grid, blk, 0, st>>>(init, init_stride, e.w, e.h, g5, ws.kcontrast, kscale, ws.Lsmooth, ws.Lflow, plane);
+            k_prep_level<<<dim3(div_up(e.w, 8 * kPrepCols), div_up(e.h, kPrepRows), frames), 256, 0, st>>>(
+                init, init_stride, e.w, e.h, g5, ws.kcontrast, kscale, ws.Lsmooth, ws.Lflow, plane);
             DUNK_KERNEL_CHECK(ctx);
         }
         if ((rc = hessian(i, ws.Lsmooth, plane))) return rc;
