@@ -614,6 +614,266 @@ def run_match(args):
     os._exit(0)
 
 
+def cv2_akaze():
+    import cv2
+    cv2.setNumThreads(os.cpu_count() or 1)
+    return cv2, cv2.AKAZE_create(cv2.AKAZE_DESCRIPTOR_MLDB, 0, 3, 0.001, 4, 4, cv2.KAZE_DIFF_PM_G2, (1 << 18) - 1)
+
+
+def config2_frames(n, distinct=16):
+    """frames synth(1024, seed = 100 + i); `distinct` images cycled to bound the host time"""
+    import synthdata
+    base = np.stack([synthdata.synth_image(FRAME, FRAME, 100 + i) for i in range(min(n, distinct))])
+    return np.ascontiguousarray(base[np.arange(n) % base.shape[0]])
+
+
+def extract_cpu(frames, n):
+    cv2, ak = cv2_akaze()
+    ak.detectAndCompute(frames[0], None)
+    t0 = time.perf_counter()
+    for i in range(n):
+        ak.detectAndCompute(frames[i % len(frames)], None)
+    dt = (time.perf_counter() - t0) / n
+    return dt, cv2.__version__
+
+
+def run_extract(args):
+    """--workload extract — BASELINE config 2: a batch of 1024 x 1024 u8 frames through AKAZE detect + MLDB
+    describe, nothing else.  Frames partition over the ranks with no collective (weak scaling)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import cubesat_apds_b200 as dunk
+    from cubesat_apds_b200._lib import KEYPOINT_DTYPE, PipelineView, check, load
+
+    rank, local_rank, world = env_rank()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load()
+    ctx = dunk.Context(local_rank, 4)
+    slot = ctx.reserve_slot()
+    stream = torch.cuda.ExternalStream(ctx.stream(slot), device=dev)
+    B, sub = args.extract_frames, 64
+    frames = config2_frames(B)
+    f_pin = torch.from_numpy(frames).pin_memory()
+    f_dev = torch.empty(frames.nbytes, dtype=torch.uint8, device=dev)
+    f_dev.copy_(f_pin.view(-1))
+    ws_bytes = int(lib.dunk_pipeline_workspace_bytes(ctx.handle, sub, FRAME, FRAME))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    view = PipelineView()
+    cap = 8192                                              # output rows per frame of the host-buffer call
+    kps_host = np.zeros((B, cap), dtype=KEYPOINT_DTYPE)
+    desc_host = np.zeros((B, cap, 61), dtype=np.uint8)
+    counts = np.zeros(B, dtype=np.int32)
+    torch.cuda.synchronize(dev)
+
+    def device_step():
+        total = 0
+        for f0 in range(0, B, sub):
+            nf = min(sub, B - f0)
+            check(lib.dunk_pipeline_extract_dev(ctx.handle, slot, f_dev.data_ptr() + f0 * FRAME * FRAME, nf, FRAME, FRAME, 1,
+                                                FRAME, FRAME * FRAME, 0, ws.data_ptr(), ws_bytes, C.byref(view)))
+            total += view.total_queries
+        return total
+
+    def e2e_step():
+        # the reference-facing call: host frames in, host keypoints + descriptors out (H2D and D2H inside)
+        check(lib.dunk_akaze_extract_batch(ctx.handle, frames.ctypes.data, B, FRAME, FRAME, 1, FRAME, FRAME * FRAME, 0,
+                                           kps_host.ctypes.data, desc_host.ctypes.data, cap, counts.ctypes.data))
+        return int(counts.sum())
+
+    def barrier():
+        ctx.sync(slot)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        n_kp = device_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launch_count
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    t1e.record(stream)
+    barrier()
+    launches = ctx.launch_count - launches0
+    total_ms = t0e.elapsed_time(t1e)
+    clocks = sampler.stop() if sampler else None
+    n_e2e = e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        stages = profile_stages(ctx, lib, slot, device_step, max(2, args.steps))
+        ms = total_ms / args.steps
+        out = {"metric": "extract_frames_per_s", "value": world * B * 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32 stencils", "data": "synthetic",
+               "config": {"workload": f"config2-extract: batch of {B} frames {FRAME}x{FRAME} u8 gray per GPU (synth(1024, 100+i)) -> AKAZE "
+                                      f"detect + MLDB-486 describe only, sub-batches of {sub}",
+                          "frames_per_step_per_gpu": B, "keypoints_per_frame_mean": n_kp / B,
+                          "parallelism": f"frame-batch dp{world}",
+                          "l2": "inputs larger than L2 (%.0f MB of frames + %.1f GB scale-space workspace per sub-batch)"
+                                % (frames.nbytes / 1e6, ws_bytes / 1e9)},
+               "e2e": {"value": world * B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(frames.nbytes),
+                       "d2h_bytes_per_step": int(n_e2e * (KEYPOINT_DTYPE.itemsize + 61) + 4 * B),
+                       "call": "dunk_akaze_extract_batch (pageable host buffers)"},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "stages_ms_per_step": stages, "roofline": hbm_roofline(stages, peaks, peak_src)}
+        if not args.no_cpu_baseline and world == 1:
+            dt, ver = extract_cpu(frames, 16)
+            out["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+                                   "sample": f"16 of the {B} frames through cv2 {ver} AKAZE.detectAndCompute, {dt * 1e3:.0f} ms/frame"}
+        print(json.dumps(out), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def config4_bands(size, seed=11):
+    """config 4 scene as the three f32 bands the preprocessor reads (geotiff_extractor); the synthetic scene is
+    one u8 plane, so the bands are that plane with per-band gains (band_merger's min-max undoes them)"""
+    scene = build_scene(size, seed).astype(np.float32)
+    return scene * 40.0, scene * 36.0 + 100.0, scene * 30.0 + 50.0, np.array([0, 255 * 40.0, 100, 100 + 255 * 36.0, 50, 50 + 255 * 30.0], np.float64)
+
+
+def build_cpu(bands, mm, lods, n_tiles_sample):
+    """the preprocessor's per-tile work on the CPU (main.rs:258-301): window -> INTER_AREA down-sample -> band_merger
+    (numpy) -> cv2 AKAZE; a bounded sample of LoD-0 tiles plus the one top-LoD tile"""
+    from oracle import geo_oracle
+    cv2, ak = cv2_akaze()
+    H, W = bands[0].shape
+    tw, th = W >> (lods - 1), H >> (lods - 1)
+    todo = [(0, t % (W // tw), t // (W // tw)) for t in range(n_tiles_sample - 1)] + [(lods - 1, 0, 0)]
+    t0 = time.perf_counter()
+    for lod, cx, cy in todo:
+        s = 1 << lod
+        win = [b[cy * th * s:(cy + 1) * th * s, cx * tw * s:(cx + 1) * tw * s] for b in bands]
+        if s > 1:
+            win = [cv2.resize(w_, (tw, th), interpolation=cv2.INTER_AREA) for w_ in win]
+        rgba = geo_oracle.band_merger(win[0].ravel(), win[1].ravel(), win[2].ravel(), mm).reshape(th, tw, 4)
+        ak.detectAndCompute(np.ascontiguousarray(rgba[..., [2, 1, 0, 3]]), None)
+    return (time.perf_counter() - t0) / len(todo), cv2.__version__, (tw, th)
+
+
+def run_build(args):
+    """--workload build — BASELINE config 4: the reference-DB build.  One scene (three f32 bands, args.build_scene^2)
+    -> LoD windows (tile = scene >> 3, 4 LoDs: 64 + 16 + 4 + 1 = 85 tiles) resampled on the device -> band_merger ->
+    AKAZE -> rows appended to the HBM DB with x * 2^lod + offset coordinates.  N > 1: every rank builds its own
+    scene (independent replicas, no collective)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import cubesat_apds_b200 as dunk
+    from cubesat_apds_b200._lib import check, load
+
+    rank, local_rank, world = env_rank()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load()
+    ctx = dunk.Context(local_rank, 4)
+    slot = ctx.reserve_slot()
+    S, lods = args.build_scene, 4
+    r, g, b, mm = config4_bands(S)
+    bands_dev = [torch.from_numpy(x).to(dev) for x in (r, g, b)]
+    db = dunk.feature_database.DescriptorDatabase(ctx, capacity=4_000_000)
+    n, tw, th = C.c_int(0), C.c_int(0), C.c_int(0)
+    torch.cuda.synchronize(dev)
+
+    def device_step():
+        db.clear()
+        check(lib.dunk_db_build_from_bands_dev(db.handle, bands_dev[0].data_ptr(), bands_dev[1].data_ptr(), bands_dev[2].data_ptr(),
+                                               S, S, mm.ctypes.data, lods, 0, 0, C.byref(n), C.byref(tw), C.byref(th)))
+
+    def e2e_step():
+        db.clear()
+        return db.build_from_bands(r, g, b, mm, lods)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launch_count
+    # the call synchronises internally (it returns row counts), so the device time is its wall time between two syncs
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        device_step()
+    barrier()
+    total_ms = (time.perf_counter() - w0) * 1e3
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    rows, tiles = len(db), n.value
+    e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - w0) * 1e3
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        stages = profile_stages(ctx, lib, slot, device_step, 2)
+        ms = total_ms / args.steps
+        mpix = sum((S >> lod << lod) ** 2 for lod in range(lods)) / 1e6          # source pixels read per build
+        out = {"metric": "db_build_tiles_per_s", "value": world * tiles * 1e3 / ms, "unit": "tiles/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32 stencils", "data": "synthetic",
+               "config": {"workload": f"config4-build: {S}x{S} scene (3 f32 bands) -> {tiles} tiles of {tw.value}x{th.value} over {lods} LoDs "
+                                      f"(box-mean decimation) -> band_merger -> AKAZE -> {rows} DB rows in HBM",
+                          "tiles": tiles, "db_rows": rows, "source_mpix_per_s": world * mpix * 1e3 / ms,
+                          "parallelism": f"replicas{world}" if world > 1 else "1 GPU",
+                          "l2": "inputs larger than L2 (%.2f GB of bands)" % (3 * r.nbytes / 1e9)},
+               "e2e": {"value": world * tiles * 1e3 / (e2e_ms / args.steps), "unit": "tiles/s", "h2d_bytes_per_step": int(3 * r.nbytes),
+                       "d2h_bytes_per_step": int(tiles * 8), "call": "dunk_db_build_from_bands (pageable host bands)"},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "stages_ms_per_step": stages, "roofline": hbm_roofline(stages, peaks, peak_src)}
+        if not args.no_cpu_baseline and world == 1:
+            dt, ver, _ = build_cpu((r, g, b), mm, lods, 6)
+            out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "tiles/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                   "sample": f"5 LoD-0 tiles + the top-LoD tile: numpy band_merger + cv2 {ver} INTER_AREA + AKAZE, "
+                                             f"{dt * 1e3:.0f} ms/tile"}
+        print(json.dumps(out), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def measured_traffic(kernel, shape_key):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), only when the
     capture was taken at this run's shape; otherwise None (the contract allows null)."""
@@ -623,6 +883,34 @@ def measured_traffic(kernel, shape_key):
         return e.get("dram_bytes_per_launch") if e.get("shape") == shape_key else None
     except Exception:
         return None
+
+
+def profile_stages(ctx, lib, slot, fn, n):
+    """run fn() n times between dunk_profile_begin / _end; per-kernel-class device times per call"""
+    from cubesat_apds_b200._lib import check
+    import ctypes as C
+    check(lib.dunk_profile_begin(ctx.handle))
+    for _ in range(n):
+        fn()
+    ctx.sync(slot)
+    names = (C.c_char * 4096)()
+    ms = (C.c_double * 64)()
+    cnt = (C.c_int * 64)()
+    alg = (C.c_double * 64)()
+    k = lib.dunk_profile_end(ctx.handle, names, 4096, ms, cnt, alg, 64)
+    labels = names.value.decode().split(";")[:k]
+    return {lab: {"ms": ms[i] / n, "launches": cnt[i] // n, "alg_bytes_or_ops": alg[i] / n} for i, lab in enumerate(labels)}
+
+
+def hbm_roofline(stages, peaks, peak_src):
+    """roofline object for the stage with the largest device time (all extraction stages are HBM-side)"""
+    top = max(stages, key=lambda s: stages[s]["ms"])
+    t = stages[top]
+    ach = t["alg_bytes_or_ops"] / (t["ms"] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "peak_source": peak_src, "traffic": None,
+            "launches_per_step": t["launches"], "ms_per_step": t["ms"],
+            "share_of_step": t["ms"] / sum(x["ms"] for x in stages.values())}
 
 
 def stage_times(ctx, lib, db, slot, f_dev, B, ws, ws_bytes, res_dev, args):
@@ -790,8 +1078,11 @@ def main():
     ap.add_argument("--ref-full-db", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicated-db", action="store_true", help="N>1: replicate the DB instead of sharding it")
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "match"],
-                    help="pipeline = config 5 (default, the headline metric); match = config 3 (sharded matcher only)")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "match", "extract", "build"],
+                    help="pipeline = config 5 (default, the headline metric); match = config 3 (sharded matcher only); "
+                         "extract = config 2 (extraction only); build = config 4 (reference-DB build from a scene)")
+    ap.add_argument("--extract-frames", type=int, default=256, help="--workload extract: frames per step per GPU")
+    ap.add_argument("--build-scene", type=int, default=10980, help="--workload build: scene edge (pixels)")
     ap.add_argument("--db-rows", type=int, default=50_000_000, help="--workload match: reference descriptors")
     ap.add_argument("--queries", type=int, default=3163, help="--workload match: query descriptors per frame")
     args = ap.parse_args()
@@ -802,6 +1093,10 @@ def main():
             args.warmup = 3
         if args.workload == "match":
             run_match(args)
+        elif args.workload == "extract":
+            run_extract(args)
+        elif args.workload == "build":
+            run_build(args)
         elif env_rank()[2] > 1 and not args.replicated_db:
             run_ours_sharded(args)
         else:

@@ -102,6 +102,8 @@ SIGNATURES = {
     "dunk_db_append_random": (_i, [_vp, _i64, _u64]),
     "dunk_db_append_random_at": (_i, [_vp, _i64, _u64, _u64]),
     "dunk_db_size": (_i64, [_vp]),
+    "dunk_db_clear": (_i, [_vp]),
+    "dunk_selftest_gamma_lut": (_i, [_vp, _vp]),
     "dunk_db_read": (_i, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "dunk_db_create_image": (_i, [_vp, _i, _i, _i, _i, _i, _pi]),
     "dunk_db_read_image": (_i, [_vp, _i, _vp]),
@@ -135,6 +137,7 @@ SIGNATURES = {
     "dunk_db_descriptors_dev": (_vp, [_vp]),
     "dunk_db_append_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _vp, _vp, _vp, _vp, _i, _vp]),
     "dunk_db_build_from_bands": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _pi, _pi, _pi]),
+    "dunk_db_build_from_bands_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _pi, _pi, _pi]),
     "dunk_find_homography": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _pi]),
     "dunk_find_homography_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "dunk_ransac_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _vp, _vp]),

@@ -8,7 +8,9 @@
 //     evaluates), i.e. the 3-D object points pnp_solver_ransac consumes.
 // All HBM-bound streaming kernels: one thread per pixel / point, coalesced loads and stores.
 #include <cmath>
+#include <mutex>
 #include "ctx.h"
+#include "gamma_lut.cuh"
 
 struct dunk_elevation {
     dunk_ctx* ctx = nullptr;
@@ -27,25 +29,47 @@ constexpr double kWgs84F = 1.0 / 298.257223563;
 constexpr double kWgs84Es = 2 * kWgs84F - kWgs84F * kWgs84F;
 constexpr double kDegToRad = 0.017453292519943296;
 
-// f32_to_u8(...).unwrap_or(0)
-__device__ __forceinline__ unsigned char f32_to_u8(float v, float vmin, float vmax, float gamma) {
-    if (isnan(v)) return 0;
-    const float fl = __fdiv_rn(__fsub_rn(v, vmin), __fsub_rn(vmax, vmin));
-    if (!(fl >= 0.f && fl <= 1.f)) return 0;                 // gamma_correction: GammaOutOfRange
-    // f32::powf is correctly rounded in practice (glibc evaluates it in double): do the same
-    const float g = (float)pow((double)fl, (double)gamma);
-    const float x = __fmul_rn(g, 255.f);
-    return (unsigned char)(int)floorf(__fadd_rn(x, 0.5f));   // round half away from zero, x >= 0
+__device__ float g_gamma_thr[256];
+
+__global__ void k_gamma_thresholds() {
+    const int k = threadIdx.x;
+    if (k == 0) { g_gamma_thr[0] = 0.f; return; }
+    // smallest bit pattern in [0, bits(1.0f)] whose value is >= k (positive floats order like their bits)
+    unsigned lo = 0, hi = 0x3f800000u;          // value(hi) = 255 >= k always
+    while (lo < hi) {
+        const unsigned mid = lo + (hi - lo) / 2;
+        if (gamma_u8_direct(__uint_as_float(mid)) >= k) hi = mid; else lo = mid + 1;
+    }
+    g_gamma_thr[k] = __uint_as_float(lo);
+}
+
+// every f32 in [0, 1]: table result vs direct formula
+__global__ void __launch_bounds__(256) k_gamma_selftest(unsigned long long* __restrict__ mismatches) {
+    __shared__ float s_thr[256];
+    s_thr[threadIdx.x] = g_gamma_thr[threadIdx.x];
+    __syncthreads();
+    unsigned long long bad = 0;
+    for (unsigned long long bits = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; bits <= 0x3f800000ull;
+         bits += (unsigned long long)gridDim.x * blockDim.x) {
+        const float fl = __uint_as_float((unsigned)bits);
+        bad += gamma_u8_lut(s_thr, fl) != gamma_u8_direct(fl);
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 __global__ void __launch_bounds__(256)
 k_band_merger(const float* __restrict__ r, const float* __restrict__ g, const float* __restrict__ b, long long n, float rmin,
-              float rmax, float gmin, float gmax, float bmin, float bmax, float gamma, uchar4* __restrict__ rgba, int bgra) {
+              float rmax, float gmin, float gmax, float bmin, float bmax, const float* __restrict__ thr,
+              uchar4* __restrict__ rgba, int bgra) {
+    __shared__ float s_thr[256];
+    s_thr[threadIdx.x] = thr[threadIdx.x];
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float vr = r[i], vg = g[i], vb = b[i];
     uchar4 o;
-    const unsigned char cr = f32_to_u8(vr, rmin, rmax, gamma), cg = f32_to_u8(vg, gmin, gmax, gamma), cb = f32_to_u8(vb, bmin, bmax, gamma);
+    const unsigned char cr = f32_to_u8_lut(s_thr, vr, rmin, rmax), cg = f32_to_u8_lut(s_thr, vg, gmin, gmax),
+                        cb = f32_to_u8_lut(s_thr, vb, bmin, bmax);
     o.x = bgra ? cb : cr;
     o.y = cg;
     o.z = bgra ? cr : cb;
@@ -115,11 +139,48 @@ bool invert_geotransform(const double* gt, double* out) {
 }
 
 }  // namespace
+
+const float* gamma_table(dunk_ctx* ctx, cudaStream_t st) {
+    static std::mutex mu;
+    static bool ready[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    const int dev = ctx->device;
+    void* p = nullptr;
+    if (dev < 0 || dev >= 64 || cudaGetSymbolAddress(&p, g_gamma_thr) != cudaSuccess) return nullptr;
+    if (!ready[dev]) {
+        k_gamma_thresholds<<<1, 256, 0, st>>>();
+        ctx->launches.fetch_add(1);
+        // once per device and process; synchronous so that every other stream may read the table afterwards
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+        ready[dev] = true;
+    }
+    return (const float*)p;
+}
+
 }  // namespace dunk
 
 using namespace dunk;
 
 extern "C" {
+
+/* compares the threshold table with the direct pow formula on every f32 in [0, 1]; *mismatches must be 0 */
+int dunk_selftest_gamma_lut(dunk_ctx* ctx, uint64_t* mismatches) {
+    DUNK_REQUIRE(ctx && mismatches, DUNK_ERR_BAD_ARG, "dunk_selftest_gamma_lut: NULL argument");
+    SlotGuard g(ctx);
+    cudaStream_t st = g.stream();
+    DUNK_REQUIRE(gamma_table(ctx, st), DUNK_ERR_CUDA, "dunk_selftest_gamma_lut: gamma table");
+    unsigned long long* d = (unsigned long long*)ctx->dev_scratch(g.s, 256);
+    if (!d) return DUNK_ERR_NO_MEM;
+    DUNK_CUDA(cudaMemsetAsync(d, 0, 8, st));
+    k_gamma_selftest<<<ctx->sm_count * 8, 256, 0, st>>>(d);
+    ctx->launches.fetch_add(1);
+    DUNK_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    DUNK_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st));
+    DUNK_CUDA(cudaStreamSynchronize(st));
+    *mismatches = h;
+    return DUNK_OK;
+}
 
 int dunk_band_merger(dunk_ctx* ctx, const float* red, const float* green, const float* blue, int64_t n, const double* min_max,
                      int bgra, uint8_t* out_rgba) {
@@ -137,7 +198,8 @@ int dunk_band_merger(dunk_ctx* ctx, const float* red, const float* green, const 
     float* d_g = cv.take<float>(chunk);
     float* d_b = cv.take<float>(chunk);
     uchar4* d_o = cv.take<uchar4>(chunk);
-    const float gamma = 1.0f / 2.2f;
+    const float* thr = gamma_table(ctx, st);
+    DUNK_REQUIRE(thr, DUNK_ERR_CUDA, "dunk_band_merger: gamma table");
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = std::min(chunk, n - off);
         DUNK_CUDA(cudaMemcpyAsync(d_r, red + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
@@ -146,7 +208,7 @@ int dunk_band_merger(dunk_ctx* ctx, const float* red, const float* green, const 
         {
             ProfScope ps(ctx, st, "geo.band_merger", (double)m * 16.0);
             k_band_merger<<<div_up(m, 256), 256, 0, st>>>(d_r, d_g, d_b, m, (float)min_max[0], (float)min_max[1], (float)min_max[2],
-                                                        (float)min_max[3], (float)min_max[4], (float)min_max[5], gamma, d_o, bgra);
+                                                        (float)min_max[3], (float)min_max[4], (float)min_max[5], thr, d_o, bgra);
             ctx->launches.fetch_add(1);
             DUNK_CUDA(cudaGetLastError());
         }
@@ -164,10 +226,12 @@ int dunk_band_merger_dev(dunk_ctx* ctx, int slot, const void* red_dev, const voi
     DUNK_REQUIRE(red_dev && green_dev && blue_dev && out_dev, DUNK_ERR_BAD_ARG, "dunk_band_merger_dev: NULL pointer");
     DUNK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->slots[slot].stream;
+    const float* thr = gamma_table(ctx, st);
+    DUNK_REQUIRE(thr, DUNK_ERR_CUDA, "dunk_band_merger_dev: gamma table");
     ProfScope ps(ctx, st, "geo.band_merger", (double)n * 16.0);
     k_band_merger<<<div_up(n, 256), 256, 0, st>>>((const float*)red_dev, (const float*)green_dev, (const float*)blue_dev, n,
                                                 (float)min_max[0], (float)min_max[1], (float)min_max[2], (float)min_max[3],
-                                                (float)min_max[4], (float)min_max[5], 1.0f / 2.2f, (uchar4*)out_dev, bgra);
+                                                (float)min_max[4], (float)min_max[5], thr, (uchar4*)out_dev, bgra);
     ctx->launches.fetch_add(1);
     DUNK_CUDA(cudaGetLastError());
     return DUNK_OK;

@@ -217,6 +217,15 @@ void dunk_db_destroy(dunk_db* db) {
 
 int64_t dunk_db_size(dunk_db* db) { return db ? db->size : 0; }
 
+int dunk_db_clear(dunk_db* db) {
+    DUNK_REQUIRE(db, DUNK_ERR_BAD_ARG, "dunk_db_clear: db is NULL");
+    std::lock_guard<std::mutex> lk(db->mu);
+    db->size = 0;
+    db->images.clear();
+    db->image_lod_dirty = true;
+    return DUNK_OK;
+}
+
 int dunk_db_append(dunk_db* db, const uint8_t* desc, const DunkKeyPoint* kps, const int32_t* image_ids,
                    int64_t n) {
     DUNK_REQUIRE(db, DUNK_ERR_BAD_ARG, "dunk_db_append: db is NULL");

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include "akaze.h"
+#include "gamma_lut.cuh"
 #include "match.h"
 #include "pipeline.h"
 
@@ -537,7 +538,10 @@ struct ResampleTaps {
 __global__ void __launch_bounds__(256)
 k_lod_tiles(const float* __restrict__ red, const float* __restrict__ green, const float* __restrict__ blue, int W, int H,
             int tile_w, int tile_h, int scale, int tiles_x, int tile0, ResampleTaps taps, float rmin, float rmax, float gmin,
-            float gmax, float bmin, float bmax, uchar4* __restrict__ out) {
+            float gmax, float bmin, float bmax, const float* __restrict__ thr, uchar4* __restrict__ out) {
+    __shared__ float s_thr[256];
+    s_thr[threadIdx.x] = thr[threadIdx.x];
+    __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, t = tile0 + blockIdx.z;
     if (x >= tile_w) return;
     const int tcol = t % tiles_x, trow = t / tiles_x;
@@ -571,13 +575,7 @@ k_lod_tiles(const float* __restrict__ red, const float* __restrict__ green, cons
 #pragma unroll
         for (int b = 0; b < 3; ++b) v[b] = (float)__ddiv_rn(acc[b], wsum_y);
     }
-    auto to_u8 = [](float val, float lo, float hi) -> unsigned char {
-        if (isnan(val)) return 0;
-        const float fl = __fdiv_rn(__fsub_rn(val, lo), __fsub_rn(hi, lo));
-        if (!(fl >= 0.f && fl <= 1.f)) return 0;
-        const float g = (float)pow((double)fl, (double)(1.0f / 2.2f));
-        return (unsigned char)(int)floorf(__fadd_rn(__fmul_rn(g, 255.f), 0.5f));
-    };
+    auto to_u8 = [&](float val, float lo, float hi) -> unsigned char { return f32_to_u8_lut(s_thr, val, lo, hi); };
     uchar4 o;
     o.z = to_u8(v[0], rmin, rmax);   // BGRA (raster_to_mat)
     o.y = to_u8(v[1], gmin, gmax);
@@ -613,9 +611,12 @@ bool make_taps(int scale, int resample, ResampleTaps* t) {
 }  // namespace
 }  // namespace dunk
 
-extern "C" int dunk_db_build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue, int width, int height,
-                                        const double* min_max, int lods, int resample, int max_points, int* n_tiles_out,
-                                        int* tile_w_out, int* tile_h_out) {
+namespace dunk {
+namespace {
+// bands_on_device: red/green/blue are device pointers (the scene already in HBM); otherwise host pointers copied in first
+int build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue, bool bands_on_device, int width, int height,
+                     const double* min_max, int lods, int resample, int max_points, int* n_tiles_out, int* tile_w_out,
+                     int* tile_h_out) {
     DUNK_REQUIRE(db && red && green && blue && min_max, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: NULL argument");
     DUNK_REQUIRE(lods >= 1 && lods <= 5, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: lods=%d (1..5)", lods);
     DUNK_REQUIRE(resample == 0 || resample == 1, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: resample %d (0 = area, 1 = Lanczos-3)", resample);
@@ -628,19 +629,27 @@ extern "C" int dunk_db_build_from_bands(dunk_db* db, const float* red, const flo
     SlotGuard g(ctx);
     cudaStream_t st = g.stream();
     const size_t plane = (size_t)width * height;
-    const int sub = 8;
+    // tiles per extraction batch: about 64 Mpx of tile area (the batch the stencil kernels fill the GPU with)
+    const int sub = (int)std::min<long long>(64, std::max<long long>(1, (64ll << 20) / ((long long)tile_w * tile_h)));
     const LevelTable lt = make_level_table(tile_w, tile_h);
     long long c = (long long)tile_w * tile_h / 32;
     c = std::min<long long>(std::max<long long>(c, 2048), 1 << 20);
     const int cap = (int)c;
     const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cap, cap);
     const size_t tile_bytes = (size_t)tile_w * tile_h * 4;
-    const size_t need = 3 * al(plane * 4) + al(ws_bytes) + al(sub * tile_bytes) + al((sub + 1) * 4) + 4 * al(sub * 4);
+    const size_t need = (bands_on_device ? 0 : 3 * al(plane * 4)) + al(ws_bytes) + al(sub * tile_bytes) + al((sub + 1) * 4) + 4 * al(sub * 4);
     void* scratch = ctx->dev_scratch(g.s, need);
     if (!scratch) return DUNK_ERR_NO_MEM;
     char* ptr = (char*)scratch;
-    float* d_band[3];
-    for (int b = 0; b < 3; ++b) { d_band[b] = (float*)ptr; ptr += al(plane * 4); }
+    const float* d_band[3] = {red, green, blue};
+    if (!bands_on_device) {
+        const float* h_band[3] = {red, green, blue};
+        for (int b = 0; b < 3; ++b) {
+            d_band[b] = (const float*)ptr;
+            DUNK_CUDA(cudaMemcpyAsync(ptr, h_band[b], plane * 4, cudaMemcpyHostToDevice, st));
+            ptr += al(plane * 4);
+        }
+    }
     AkazeWorkspace ws;
     akaze_carve_workspace(ptr, lt, sub, cap, cap, &ws);
     ptr += al(ws_bytes);
@@ -650,64 +659,91 @@ extern "C" int dunk_db_build_from_bands(dunk_db* db, const float* red, const flo
     float* d_yo = (float*)ptr; ptr += al(sub * 4);
     float* d_sc = (float*)ptr; ptr += al(sub * 4);
     int32_t* d_id = (int32_t*)ptr;
-    DUNK_CUDA(cudaMemcpyAsync(d_band[0], red, plane * 4, cudaMemcpyHostToDevice, st));
-    DUNK_CUDA(cudaMemcpyAsync(d_band[1], green, plane * 4, cudaMemcpyHostToDevice, st));
-    DUNK_CUDA(cudaMemcpyAsync(d_band[2], blue, plane * 4, cudaMemcpyHostToDevice, st));
-    int n_tiles = 0;
-    std::vector<int> h_off(sub + 1), h_cnt(sub);
+    // the reference walks lod-major, tile-minor (main.rs:212-271); a batch may span several LoDs
+    struct TileJob { int lod, t, tiles_x; };
+    std::vector<TileJob> jobs;
     for (int lod = 0; lod < lods; ++lod) {
         const int scale = 1 << lod;
         const int tiles_x = width / (tile_w * scale), tiles_y = height / (tile_h * scale);    // main.rs:215-216
         ResampleTaps taps;
         DUNK_REQUIRE(make_taps(scale, resample, &taps), DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: decimation %d too large", scale);
-        const int total = tiles_x * tiles_y;
-        for (int t0 = 0; t0 < total; t0 += sub) {
-            const int nf = std::min(sub, total - t0);
-            {
-                ProfScope ps(ctx, st, "lod.resample_merge", (double)nf * tile_w * tile_h * (12.0 * scale * scale + 4.0));
-                k_lod_tiles<<<dim3(div_up(tile_w, 256), tile_h, nf), 256, 0, st>>>(
-                    d_band[0], d_band[1], d_band[2], width, height, tile_w, tile_h, scale, tiles_x, t0, taps, (float)min_max[0],
-                    (float)min_max[1], (float)min_max[2], (float)min_max[3], (float)min_max[4], (float)min_max[5], (uchar4*)d_tiles);
-                DUNK_KERNEL_CHECK(ctx);
-            }
-            int rc = akaze_run(ctx, st, lt, ws, d_tiles, tile_bytes, tile_w * 4, 4, nf, max_points <= 0 ? 0 : max_points);
-            if (rc) return rc;
-            k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off);
+        for (int t = 0; t < tiles_x * tiles_y; ++t) jobs.push_back({lod, t, tiles_x});
+    }
+    const float* thr = gamma_table(ctx, st);
+    DUNK_REQUIRE(thr, DUNK_ERR_CUDA, "dunk_db_build_from_bands: gamma table");
+    int n_tiles = 0;
+    std::vector<int> h_off(sub + 1), h_cnt(sub);
+    for (size_t j0 = 0; j0 < jobs.size(); j0 += sub) {
+        const int nf = (int)std::min<size_t>(sub, jobs.size() - j0);
+        for (int f0 = 0; f0 < nf;) {            // one resample launch per run of equal LoD
+            int f1 = f0;
+            while (f1 < nf && jobs[j0 + f1].lod == jobs[j0 + f0].lod) ++f1;
+            const TileJob& jb = jobs[j0 + f0];
+            const int scale = 1 << jb.lod, run = f1 - f0;
+            ResampleTaps taps;
+            make_taps(scale, resample, &taps);
+            ProfScope ps(ctx, st, "lod.resample_merge", (double)run * tile_w * tile_h * (12.0 * scale * scale + 4.0));
+            k_lod_tiles<<<dim3(div_up(tile_w, 256), tile_h, run), 256, 0, st>>>(
+                d_band[0], d_band[1], d_band[2], width, height, tile_w, tile_h, scale, jb.tiles_x, jb.t, taps, (float)min_max[0],
+                (float)min_max[1], (float)min_max[2], (float)min_max[3], (float)min_max[4], (float)min_max[5], thr,
+                (uchar4*)(d_tiles + (size_t)f0 * tile_bytes));
             DUNK_KERNEL_CHECK(ctx);
-            DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 1) * 4, cudaMemcpyDeviceToHost, st));
-            DUNK_CUDA(cudaMemcpyAsync(h_cnt.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-            DUNK_CUDA(cudaStreamSynchronize(st));
-            const int rows_new = h_off[nf];
-            DUNK_REQUIRE(db->size + rows_new <= db->capacity, DUNK_ERR_NO_MEM, "dunk_db_build_from_bands: %lld + %d rows exceed capacity %lld",
-                         (long long)db->size, rows_new, (long long)db->capacity);
-            std::vector<float> xo(nf), yo(nf), sc(nf);
-            std::vector<int32_t> ids(nf);
-            int maxc = 0;
-            for (int f = 0; f < nf; ++f) {
-                const int t = t0 + f, col = t % tiles_x, row = t / tiles_x;
-                const int xs = col * tile_w * scale, ys = row * tile_h * scale;
-                // InsertImage, main.rs:283-289
-                DunkImage im{(int32_t)db->images.size() + 1, xs, ys, xs + tile_w * scale - 1, ys + tile_h * scale - 1, lod};
-                db->images.push_back(im);
-                ids[f] = im.id;
-                xo[f] = (float)xs; yo[f] = (float)ys; sc[f] = (float)scale;
-                maxc = std::max(maxc, h_cnt[f]);
-            }
-            db->image_lod_dirty = true;
-            DUNK_CUDA(cudaMemcpyAsync(d_xo, xo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-            DUNK_CUDA(cudaMemcpyAsync(d_yo, yo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-            DUNK_CUDA(cudaMemcpyAsync(d_sc, sc.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-            DUNK_CUDA(cudaMemcpyAsync(d_id, ids.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
-            if (maxc > 0) {
-                k_append_rows<<<dim3(div_up(maxc, 256), nf), 256, 0, st>>>(ws.desc64, ws.kps, cap, ws.kp_count, d_off, d_xo, d_yo, d_sc, d_id,
-                                                                          0, db->desc64, db->kps, db->image_id, db->size);
-                DUNK_KERNEL_CHECK(ctx);
-            }
-            DUNK_CUDA(cudaStreamSynchronize(st));
-            db->size += rows_new;
-            n_tiles += nf;
+            f0 = f1;
         }
+        int rc = akaze_run(ctx, st, lt, ws, d_tiles, tile_bytes, tile_w * 4, 4, nf, max_points <= 0 ? 0 : max_points);
+        if (rc) return rc;
+        k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off);
+        DUNK_KERNEL_CHECK(ctx);
+        DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 1) * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaMemcpyAsync(h_cnt.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaStreamSynchronize(st));
+        const int rows_new = h_off[nf];
+        DUNK_REQUIRE(db->size + rows_new <= db->capacity, DUNK_ERR_NO_MEM, "dunk_db_build_from_bands: %lld + %d rows exceed capacity %lld",
+                     (long long)db->size, rows_new, (long long)db->capacity);
+        std::vector<float> xo(nf), yo(nf), sc(nf);
+        std::vector<int32_t> ids(nf);
+        int maxc = 0;
+        for (int f = 0; f < nf; ++f) {
+            const TileJob& jb = jobs[j0 + f];
+            const int scale = 1 << jb.lod, col = jb.t % jb.tiles_x, row = jb.t / jb.tiles_x;
+            const int xs = col * tile_w * scale, ys = row * tile_h * scale;
+            // InsertImage, main.rs:283-289
+            DunkImage im{(int32_t)db->images.size() + 1, xs, ys, xs + tile_w * scale - 1, ys + tile_h * scale - 1, jb.lod};
+            db->images.push_back(im);
+            ids[f] = im.id;
+            xo[f] = (float)xs; yo[f] = (float)ys; sc[f] = (float)scale;
+            maxc = std::max(maxc, h_cnt[f]);
+        }
+        db->image_lod_dirty = true;
+        DUNK_CUDA(cudaMemcpyAsync(d_xo, xo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+        DUNK_CUDA(cudaMemcpyAsync(d_yo, yo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+        DUNK_CUDA(cudaMemcpyAsync(d_sc, sc.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+        DUNK_CUDA(cudaMemcpyAsync(d_id, ids.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+        if (maxc > 0) {
+            k_append_rows<<<dim3(div_up(maxc, 256), nf), 256, 0, st>>>(ws.desc64, ws.kps, cap, ws.kp_count, d_off, d_xo, d_yo, d_sc, d_id,
+                                                                      0, db->desc64, db->kps, db->image_id, db->size);
+            DUNK_KERNEL_CHECK(ctx);
+        }
+        DUNK_CUDA(cudaStreamSynchronize(st));
+        db->size += rows_new;
+        n_tiles += nf;
     }
     if (n_tiles_out) *n_tiles_out = n_tiles;
     return DUNK_OK;
+}
+}  // namespace
+}  // namespace dunk
+
+extern "C" int dunk_db_build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue, int width, int height,
+                                        const double* min_max, int lods, int resample, int max_points, int* n_tiles_out,
+                                        int* tile_w_out, int* tile_h_out) {
+    return dunk::build_from_bands(db, red, green, blue, false, width, height, min_max, lods, resample, max_points, n_tiles_out,
+                                  tile_w_out, tile_h_out);
+}
+
+extern "C" int dunk_db_build_from_bands_dev(dunk_db* db, const void* red_dev, const void* green_dev, const void* blue_dev, int width,
+                                            int height, const double* min_max, int lods, int resample, int max_points,
+                                            int* n_tiles_out, int* tile_w_out, int* tile_h_out) {
+    return dunk::build_from_bands(db, (const float*)red_dev, (const float*)green_dev, (const float*)blue_dev, true, width, height,
+                                  min_max, lods, resample, max_points, n_tiles_out, tile_w_out, tile_h_out);
 }

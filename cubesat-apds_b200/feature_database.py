@@ -163,6 +163,10 @@ class DescriptorDatabase:
         except Exception:
             pass
 
+    def clear(self):
+        """drop every keypoint and ref_image row, keep the HBM buffers (the migrations' down.sql + up.sql)"""
+        check(_lib.load().dunk_db_clear(self.handle))
+
     def __len__(self) -> int:
         return int(_lib.load().dunk_db_size(self.handle))
 

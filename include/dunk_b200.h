@@ -142,6 +142,8 @@ int dunk_db_append_random(dunk_db* db, int64_t n, uint64_t seed);
  * so the union of the shards equals the unsharded DB whatever the shard count */
 int dunk_db_append_random_at(dunk_db* db, int64_t n, uint64_t seed, uint64_t global_row_offset);
 int64_t dunk_db_size(dunk_db* db);
+/* forget every keypoint and ref_image row (capacity and device buffers are kept): TRUNCATE keypoint, ref_image */
+int dunk_db_clear(dunk_db* db);
 /* read back rows [first, first+n) (any of the outputs may be NULL) */
 int dunk_db_read(dunk_db* db, int64_t first, int64_t n, uint8_t* desc, DunkKeyPoint* kps,
                  int32_t* image_ids);
@@ -399,6 +401,10 @@ int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int ro
 int dunk_db_build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue,
                              int width, int height, const double* min_max, int lods, int resample,
                              int max_points, int* n_tiles_out, int* tile_w_out, int* tile_h_out);
+/* same with the three bands already resident in HBM (width*height f32 each, device pointers) */
+int dunk_db_build_from_bands_dev(dunk_db* db, const void* red_dev, const void* green_dev, const void* blue_dev,
+                                 int width, int height, const double* min_max, int lods, int resample,
+                                 int max_points, int* n_tiles_out, int* tile_w_out, int* tile_h_out);
 
 /* ---- roofline denominators measured on the box ---------------------------------------- */
 /* per-kernel-class device times: between begin and end every launch site brackets its kernels
@@ -407,6 +413,9 @@ int dunk_db_build_from_bands(dunk_db* db, const float* red, const float* green, 
 int dunk_profile_begin(dunk_ctx* ctx);
 int dunk_profile_end(dunk_ctx* ctx, char* names, int names_cap, double* ms, int* launches,
                      double* alg, int cap);
+/* f32_to_u8's gamma step is evaluated through a 255-entry threshold table built from the direct formula;
+ * this compares the two on every f32 in [0, 1] (2^30 values, ~1 s): *mismatches must come back 0 */
+int dunk_selftest_gamma_lut(dunk_ctx* ctx, uint64_t* mismatches);
 /* POPC-pipe peak in 1e12 popc/s (best of 4 timed launches of `iters` x 32 popc per thread) */
 int dunk_microbench_popc(dunk_ctx* ctx, int iters, double* tpopc_per_s);
 

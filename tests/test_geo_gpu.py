@@ -71,3 +71,12 @@ def test_world_coordinates(dunk, ctx):
     with pytest.raises(fd.NotFound):
         far.get_world_coordinates(10000.0, 10000.0)
     g.close(); g0.close(); far.close()
+
+
+def test_gamma_threshold_table_is_exhaustively_exact(dunk, ctx):
+    """the 255-threshold table behind f32_to_u8 equals the direct pow formula on every f32 in [0, 1]"""
+    import ctypes as C
+    from cubesat_apds_b200._lib import check, load
+    bad = C.c_uint64(123)
+    check(load().dunk_selftest_gamma_lut(ctx.handle, C.byref(bad)))
+    assert bad.value == 0

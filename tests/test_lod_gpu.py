@@ -42,3 +42,30 @@ def test_build_from_bands_equals_tilewise_build(dunk, ctx, resample):
     top = db.read_keypoints_from_lod(lods - 1)
     assert len(top) > 0 and set(top["image_id"].tolist()) == {n_tiles}
     db.close(); ref.close()
+
+
+def test_build_from_device_bands_and_clear(dunk, ctx):
+    """dunk_db_build_from_bands_dev (bands already in HBM) gives the rows of the host-band call; dunk_db_clear
+    empties keypoint + ref_image and a rebuild into the same buffers reproduces them."""
+    import ctypes as C
+    import torch
+    from cubesat_apds_b200._lib import check, load
+    fd = dunk.feature_database
+    r, g, b, mm = scene_bands()
+    db = fd.DescriptorDatabase(ctx, capacity=200000)
+    n_tiles, _ = db.build_from_bands(r, g, b, mm, 3)
+    want = db.rows().tobytes()
+    images = [db.read_image_from_id(i + 1).tolist() for i in range(n_tiles)]
+    db.clear()
+    assert len(db) == 0
+    with pytest.raises(fd.NotFound):
+        db.read_image_from_id(1)
+    dev = [torch.from_numpy(x).cuda() for x in (r, g, b)]
+    m = np.ascontiguousarray(mm, dtype=np.float64)
+    n, tw, th = C.c_int(0), C.c_int(0), C.c_int(0)
+    check(load().dunk_db_build_from_bands_dev(db.handle, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), 1024, 1024,
+                                              m.ctypes.data, 3, 0, 0, C.byref(n), C.byref(tw), C.byref(th)))
+    assert n.value == n_tiles and (tw.value, th.value) == (256, 256)
+    assert db.rows().tobytes() == want
+    assert [db.read_image_from_id(i + 1).tolist() for i in range(n_tiles)] == images
+    db.close()
