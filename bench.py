@@ -1014,10 +1014,63 @@ def cpu_baseline(scene, tiles, xo, yo, sc, frames, args, n_frames=4, db_tiles=8)
                       f"flatters the CPU); {dt * 1e3:.0f} ms/frame, tile extraction {t_extract * 1e3:.0f} ms/tile"}
 
 
+def run_reference_workload(args):
+    """reference arm of the secondary workloads: the same OpenCV calls on the host cores, bounded samples"""
+    cores = os.cpu_count() or 1
+    base = {"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "vs_baseline": None, "data": "synthetic"}
+    if args.workload == "extract":
+        B = args.extract_frames
+        frames = config2_frames(min(B, 16))
+        dt, ver = extract_cpu(frames, max(8, 4 * args.steps))
+        val, unit, metric, ms = 1.0 / dt, UNIT, "extract_frames_per_s", dt * 1e3 * B
+        cfg = {"workload": f"config2-extract on the host CPU: cv2 {ver} AKAZE.detectAndCompute on {FRAME}x{FRAME} u8 frames",
+               "frames_per_step_per_gpu": B}
+        sample = f"{max(8, 4 * args.steps)} frames, {dt * 1e3:.0f} ms/frame, scaled linearly to {B} frames per step"
+        dtype, scaling = "f32 (OpenCV)", "weak"
+    elif args.workload == "build":
+        r, g, b, mm = config4_bands(args.build_scene)
+        dt, ver, (tw, th) = build_cpu((r, g, b), mm, 4, 6)
+        val, unit, metric, ms = 1.0 / dt, "tiles/s", "db_build_tiles_per_s", dt * 1e3 * 85
+        cfg = {"workload": f"config4-build on the host CPU: {args.build_scene}^2 scene, tiles of {tw}x{th}: numpy band_merger + "
+                           f"cv2 {ver} INTER_AREA + AKAZE per tile", "tiles": 85}
+        sample = f"5 LoD-0 tiles + the top-LoD tile, {dt * 1e3:.0f} ms/tile, scaled linearly to 85 tiles per step"
+        dtype, scaling = "f32 (OpenCV)", "weak"
+    else:
+        import cv2
+        cv2.setNumThreads(cores)
+        nq, rows = args.queries, 1_000_000
+        rng = np.random.default_rng(0)
+        q = rng.integers(0, 256, (nq, 61), dtype=np.uint8)
+        t = np.random.default_rng(7).integers(0, 256, (rows, 61), dtype=np.uint8)
+        bf, chunk = cv2.BFMatcher(cv2.NORM_HAMMING, False), (1 << 18) - 1
+        t0 = time.perf_counter()
+        for a in range(0, rows, chunk):
+            bf.knnMatch(q, t[a:a + chunk], 2)
+        dt = time.perf_counter() - t0
+        gp = nq * rows / dt / 1e9
+        ms = dt * 1e3 * args.db_rows / rows
+        val, unit, metric = 1e3 / ms, UNIT, METRIC
+        cfg = {"workload": f"config3-match on the host CPU: cv2 {cv2.__version__} BFMatcher(HAMMING).knnMatch k=2 in <= 262 143-row chunks",
+               "db_rows": args.db_rows, "queries_per_frame": nq, "matcher_gpairs_per_s": gp}
+        sample = f"{nq} queries x {rows} rows ({gp:.2f} Gpairs/s), scaled linearly to {args.db_rows} rows"
+        dtype, scaling = "u8 popcnt (OpenCV)", "strong"
+    out = dict(base, metric=metric, value=val, unit=unit, ms_per_step=ms, scaling=scaling, dtype=dtype, config=cfg,
+               cpu_baseline={"value": val, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+               e2e={"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(out), flush=True)
+
+
 def run_reference(args):
     rank, _, world = env_rank()
     if rank != 0:
         return
+    if args.workload != "pipeline":
+        try:
+            return run_reference_workload(args)
+        except ImportError as e:
+            print(json.dumps({"impl": "reference", "unavailable": f"cv2 (OpenCV) not importable: {e}"}))
+            return
     scene = build_scene(args.scene)
     tiles, xo, yo, sc = scene_tiles(scene)
     B = args.frames
