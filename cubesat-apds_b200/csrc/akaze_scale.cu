@@ -8,6 +8,7 @@
 // (no FMA contraction) because 166 dependent steps amplify reassociation noise.
 #include "akaze.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace dunk {
 
@@ -23,6 +24,12 @@ __device__ __forceinline__ int reflect101(int v, int n) {
     if (n == 1) return 0;
     while (v < 0 || v >= n) v = v < 0 ? -v : 2 * (n - 1) - v;
     return v;
+}
+
+// one reflection is enough when the overshoot is smaller than the extent (callers guarantee it)
+__device__ __forceinline__ int reflect101_once(int v, int n) {
+    v = v < 0 ? -v : v;
+    return v >= n ? 2 * (n - 1) - v : v;
 }
 
 struct Gauss9 { float k[5]; };   // k[0] = centre
@@ -656,6 +663,137 @@ k_hessian(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, float w
     }
 }
 
+// Register-window version of k_hessian<S> for even W >= 128, H >= 32: no shared memory, no block barrier.
+// A warp owns a span of 64 adjacent columns (two per lane, interleaved: lane t holds columns 2t, 2t + 1 of
+// the span) and walks down R output rows.  Horizontal neighbours at distance S come from warp shuffles,
+// vertical ones from rolling register windows of depth 2S + 1 (statically indexed: the row loop is unrolled
+// by the window period).  Per input row a lane computes the row filters rd = L(x+S) - L(x-S) and
+// cs = [w0 w1 w0] . L(x-S, x, x+S); S rows later Lx / Ly of that row exist (column filters over the windows),
+// are stored, shuffled and row-filtered again; another S rows later Lxx, Lxy, Lyy and Ldet follow.  The span
+// carries 2S halo columns either side (outputs: 64 - 4S columns) and the walk 2S rows above and below.
+// Arithmetic: exactly the operations k_hessian<S> compiles to (t = w1 * mid; t = fma(w0, first, t);
+// t = fma(w0, last, t)), so both kernels give the same bits.
+template <int S>
+struct HessWin {
+    static constexpr int P = 2 * S + 1;
+    float rd[2][P], cs[2][P], rdx[2][P], csx[2][P], csy[2][P];
+};
+
+// One round = P consecutive input rows (walk indices base .. base + P - 1).  FAST: all 64 columns and all P
+// rows lie inside the image and every store of the round targets an output row, so the loads are plain
+// float2 loads off a running pointer and the stores are predicated on the lane's column only.
+template <int S, bool FAST>
+__device__ __forceinline__ void hess_round(HessWin<S>& w, const float* __restrict__ src, float* __restrict__ ox,
+                                           float* __restrict__ oy, float* __restrict__ od, int W, int H, int base,
+                                           int r_start, int n_rows, int y0, int y_end, int c0, int ca, int cb,
+                                           bool interior, bool col_ok, float w0, float w1, float sigma_quat) {
+    constexpr int P = 2 * S + 1;
+    constexpr int DA = (S + 1) / 2, DB = S / 2;            // shuffle distances (lanes) for the two columns
+    auto tri = [&](float a, float b, float c) { return __fmaf_rn(w0, c, __fmaf_rn(w0, a, __fmul_rn(w1, b))); };
+    auto left = [&](float v0, float v1, int which) {       // value at column - S for column `which` of the pair
+        return which == 0 ? __shfl_up_sync(0xffffffffu, (S & 1) ? v1 : v0, DA)
+                          : __shfl_up_sync(0xffffffffu, (S & 1) ? v0 : v1, DB);
+    };
+    auto right = [&](float v0, float v1, int which) {      // value at column + S
+        return which == 0 ? __shfl_down_sync(0xffffffffu, (S & 1) ? v1 : v0, DB)
+                          : __shfl_down_sync(0xffffffffu, (S & 1) ? v0 : v1, DA);
+    };
+    // the P input rows of this round, loaded up front so that their latencies overlap
+    float2 cur[P];
+    if (FAST) {
+        const float* rowp = src + (size_t)(r_start + base) * W + c0;
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) cur[ph] = __ldg((const float2*)(rowp + (size_t)ph * W));
+    } else {
+#pragma unroll
+        for (int ph = 0; ph < P; ++ph) {
+            const float* row = src + (size_t)reflect101_once(r_start + min(base + ph, n_rows - 1), H) * W;
+            if (interior) cur[ph] = __ldg((const float2*)(row + c0));
+            else cur[ph] = make_float2(row[ca], row[cb]);
+        }
+    }
+    // output offsets of row q = r - S (Lx, Ly) for ph = 0; Ldet goes S rows further up
+    const long long oq = (long long)(r_start + base - S) * W + c0;
+#pragma unroll
+    for (int ph = 0; ph < P; ++ph) {
+        const int pm = (ph + P - S) % P, pu = (ph + 1) % P;          // rows S and 2S earlier in the windows
+        const float l0 = cur[ph].x, l1 = cur[ph].y;
+        {
+            const float m0 = left(l0, l1, 0), p0 = right(l0, l1, 0), m1 = left(l0, l1, 1), p1 = right(l0, l1, 1);
+            w.rd[0][ph] = p0 - m0; w.cs[0][ph] = tri(m0, l0, p0);
+            w.rd[1][ph] = p1 - m1; w.cs[1][ph] = tri(m1, l1, p1);
+        }
+        // first derivatives of row q = r - S
+        const float lx0 = tri(w.rd[0][pu], w.rd[0][pm], w.rd[0][ph]), lx1 = tri(w.rd[1][pu], w.rd[1][pm], w.rd[1][ph]);
+        const float ly0 = w.cs[0][ph] - w.cs[0][pu], ly1 = w.cs[1][ph] - w.cs[1][pu];
+        const int i = base + ph, q = r_start + i - S;
+        const long long o = oq + (long long)ph * W;
+        const bool st1 = FAST ? col_ok : (col_ok && q >= y0 && q < y_end && i < n_rows);
+        if (st1) *(float2*)(ox + o) = make_float2(lx0, lx1);
+        if (st1) *(float2*)(oy + o) = make_float2(ly0, ly1);
+        {
+            const float m0 = left(lx0, lx1, 0), p0 = right(lx0, lx1, 0), m1 = left(lx0, lx1, 1), p1 = right(lx0, lx1, 1);
+            w.rdx[0][ph] = p0 - m0; w.csx[0][ph] = tri(m0, lx0, p0);
+            w.rdx[1][ph] = p1 - m1; w.csx[1][ph] = tri(m1, lx1, p1);
+        }
+        {
+            const float m0 = left(ly0, ly1, 0), p0 = right(ly0, ly1, 0), m1 = left(ly0, ly1, 1), p1 = right(ly0, ly1, 1);
+            w.csy[0][ph] = tri(m0, ly0, p0);
+            w.csy[1][ph] = tri(m1, ly1, p1);
+        }
+        // second derivatives of row p = r - 2S
+        const int pr = q - S;
+        float det[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const float lxx = tri(w.rdx[c][pu], w.rdx[c][pm], w.rdx[c][ph]);
+            const float lxy = w.csx[c][ph] - w.csx[c][pu];
+            const float lyy = w.csy[c][ph] - w.csy[c][pu];
+            det[c] = __fmul_rn(__fsub_rn(__fmul_rn(lxx, lyy), __fmul_rn(lxy, lxy)), sigma_quat);
+        }
+        if (FAST ? col_ok : (col_ok && pr >= y0 && pr < y_end && i < n_rows))
+            *(float2*)(od + o - (long long)S * W) = make_float2(det[0], det[1]);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(32, S == 4 ? 16 : (S == 3 ? 20 : 24))
+k_hessian_reg(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, int R, int nspans, float w0, float w1,
+              float sigma_quat, float* __restrict__ Lx, float* __restrict__ Ly, float* __restrict__ Ldet,
+              size_t pyr_stride) {
+    constexpr int P = 2 * S + 1;
+    constexpr int OUTW = 64 - 4 * S;
+    // one warp per block: every branch below depends on block-uniform values only, so the compiler keeps the
+    // shuffles free of divergence checks and can interleave the P independent row steps of a round
+    const int lane = threadIdx.x;
+    const int span = blockIdx.x;
+    const int f = blockIdx.z;
+    const int cx0 = span * OUTW, y0 = blockIdx.y * R;
+    const int c0 = cx0 - 2 * S + 2 * lane;                 // this lane's first column (may be outside the image)
+    const float* src = Lsm + (size_t)f * sm_stride;
+    float* ox = Lx + (size_t)f * pyr_stride;
+    float* oy = Ly + (size_t)f * pyr_stride;
+    float* od = Ldet + (size_t)f * pyr_stride;
+    const int r_start = y0 - 2 * S;
+    const int y_end = min(y0 + R, H);                      // output rows [y0, y_end)
+    const int n_rows = y_end - y0 + 4 * S;                 // input rows walked
+    const bool interior = cx0 - 2 * S >= 0 && cx0 - 2 * S + 64 <= W;      // all 64 columns inside the image
+    const bool col_ok = lane >= S && lane < 32 - S && c0 < W;
+    // border spans: reflected column indices, fixed over the walk
+    const int ca = reflect101_once(c0, W), cb = reflect101_once(c0 + 1, W);
+    HessWin<S> w;
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) w.rd[c][k] = w.cs[c][k] = w.rdx[c][k] = w.csx[c][k] = w.csy[c][k] = 0.f;
+    for (int base = 0; base < n_rows; base += P) {
+        // Lx / Ly stores are valid for walk indices [3S, n_rows - S), Ldet stores for [4S, n_rows)
+        const bool fast = interior && base >= 4 * S && base + P <= n_rows - S && r_start + base >= 0 && r_start + base + P <= H;
+        if (fast) hess_round<S, true>(w, src, ox, oy, od, W, H, base, r_start, n_rows, y0, y_end, c0, ca, cb, interior, col_ok, w0, w1, sigma_quat);
+        else hess_round<S, false>(w, src, ox, oy, od, W, H, base, r_start, n_rows, y0, y_end, c0, ca, cb, interior, col_ok, w0, w1, sigma_quat);
+    }
+}
+
 bool is_prime(int n) {
     if (n < 2) return false;
     for (int d = 2; d * d <= n; ++d)
@@ -813,6 +951,20 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             float* ly = ws.Ly + e.plane_off;
             float* ld = ws.Ldet + e.plane_off;
             const float sq = (float)(s * s * s * s);
+            // debug switch for tools/ab_hessian.py (bit-for-bit comparison of the two kernels)
+            static const bool use_old = getenv("DUNK_HESSIAN_OLD") != nullptr;
+            const bool reg_ok = !use_old && s >= 2 && s <= 4 && e.w % 2 == 0 && e.w >= 128 && e.h >= 32 && lsm_stride % 2 == 0 &&
+                                pyr % 2 == 0 && e.plane_off % 2 == 0;
+            if (reg_ok) {
+                const int outw = 64 - 4 * s, nspans = div_up(e.w, outw);
+                // rows per warp: long walks amortise the 4S halo rows, short ones keep small levels parallel
+                int R = 128;
+                while (R > 16 && (long long)nspans * div_up(e.h, R) * frames < 4096) R /= 2;
+                const dim3 g2(nspans, div_up(e.h, R), frames);
+                if (s == 2) k_hessian_reg<2><<<g2, 32, 0, st>>>(lsm, lsm_stride, e.w, e.h, R, nspans, w0, w1, sq, lx, ly, ld, pyr);
+                else if (s == 3) k_hessian_reg<3><<<g2, 32, 0, st>>>(lsm, lsm_stride, e.w, e.h, R, nspans, w0, w1, sq, lx, ly, ld, pyr);
+                else k_hessian_reg<4><<<g2, 32, 0, st>>>(lsm, lsm_stride, e.w, e.h, R, nspans, w0, w1, sq, lx, ly, ld, pyr);
+            } else
             if (s == 2) k_hessian<2><<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, w0, w1, sq, lx, ly, ld, pyr);
             else if (s == 3) k_hessian<3><<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, w0, w1, sq, lx, ly, ld, pyr);
             else if (s == 4) k_hessian<4><<<grid, blk, smem, st>>>(lsm, lsm_stride, e.w, e.h, w0, w1, sq, lx, ly, ld, pyr);
