@@ -8,6 +8,7 @@
 // (no FMA contraction) because 166 dependent steps amplify reassociation noise.
 #include "akaze.h"
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 
 namespace dunk {
@@ -324,6 +325,118 @@ k_prep_level(const float* __restrict__ Lt, size_t lt_stride, int W, int H, Gauss
         ul = ml; uc = mc; ur = mr;
         ml = bl; mc = b; mr = br;
         }
+    }
+}
+
+// Register-window version of k_prep_level for even W >= 128, H >= 16, in the style of k_hessian_reg: one warp per
+// block owns a span of 64 adjacent columns (two per lane, interleaved) and walks down R output rows (+6 halo rows).
+// The row loop is unrolled by the window period 5, so the Gauss5 row-filter window (5 rows) and the window of
+// smoothed rows with their outer neighbours (3 live rows, 5 slots) are statically indexed registers; a lane's own
+// two columns are each other's +-1 neighbours, so a row costs 8 shuffles for 2 pixels.  Outputs: span columns
+// 4 .. 59 (halo 2 for the Gaussian + 1 for Scharr, rounded up to keep the float2 accesses aligned).
+// Expressions are those of k_prep_level above, term for term.
+struct PrepWin {
+    float t[2][5];                    // row-filtered input rows
+    float b[2][5], bl0[5], br1[5];    // Gauss5 rows: both columns, left neighbour of column 0, right neighbour of column 1
+};
+
+template <bool FAST>
+__device__ __forceinline__ void prep_round(PrepWin& w, const float* __restrict__ src, float* __restrict__ sm,
+                                           float* __restrict__ fl, int W, int H, int base, int r_start, int n_rows,
+                                           int y0, int c0, int ca, int cb, bool interior, bool col_ok, bool le0,
+                                           bool re1, const Gauss5& g, float inv_k) {
+    const unsigned full = 0xffffffffu;
+    // the operation sequences k_prep_level compiles to (checked in its SASS), pinned here with intrinsics
+    auto gauss = [&](float c, float s1, float s2) { return __fmaf_rn(g.k[2], s2, __fmaf_rn(g.k[0], c, __fmul_rn(g.k[1], s1))); };
+    auto scharr = [](float a, float b, float c) { return __fmaf_rn(3.f, c, __fmaf_rn(10.f, b, __fmul_rn(3.f, a))); };
+    float2 cur[5];
+    if (FAST) {
+        const float* rowp = src + (size_t)(r_start + base) * W + c0;
+#pragma unroll
+        for (int ph = 0; ph < 5; ++ph) cur[ph] = __ldg((const float2*)(rowp + (size_t)ph * W));
+    } else {
+#pragma unroll
+        for (int ph = 0; ph < 5; ++ph) {
+            const float* row = src + (size_t)clampi(r_start + min(base + ph, n_rows - 1), 0, H - 1) * W;   // BORDER_REPLICATE
+            if (interior) cur[ph] = __ldg((const float2*)(row + c0));
+            else cur[ph] = make_float2(row[ca], row[cb]);
+        }
+    }
+    const long long oy = (long long)(r_start + base - 3) * W + c0;      // output row y = r - 3 at ph = 0
+#pragma unroll
+    for (int ph = 0; ph < 5; ++ph) {
+        const int p1 = (ph + 4) % 5, p2 = (ph + 3) % 5, p3 = (ph + 2) % 5, p4 = (ph + 1) % 5;   // 1 .. 4 rows earlier
+        const float a0 = cur[ph].x, a1 = cur[ph].y;
+        {   // Gauss5 along the row: neighbours at +-1 and +-2 columns
+            const float a0m1 = __shfl_up_sync(full, a1, 1), a1p1 = __shfl_down_sync(full, a0, 1);
+            const float a0m2 = __shfl_up_sync(full, a0, 1), a0p2 = __shfl_down_sync(full, a0, 1);
+            const float a1m2 = __shfl_up_sync(full, a1, 1), a1p2 = __shfl_down_sync(full, a1, 1);
+            w.t[0][ph] = gauss(a0, __fadd_rn(a0m1, a1), __fadd_rn(a0m2, a0p2));
+            w.t[1][ph] = gauss(a1, __fadd_rn(a0, a1p1), __fadd_rn(a1m2, a1p2));
+        }
+        // Gauss5 row yb = r - 2 is complete: rows yb-2 .. yb+2 sit in slots p4, p3, p2, p1, ph
+        const float b0 = gauss(w.t[0][p2], __fadd_rn(w.t[0][p3], w.t[0][p1]), __fadd_rn(w.t[0][p4], w.t[0][ph]));
+        const float b1 = gauss(w.t[1][p2], __fadd_rn(w.t[1][p3], w.t[1][p1]), __fadd_rn(w.t[1][p4], w.t[1][ph]));
+        float l0 = __shfl_up_sync(full, b1, 1), r1 = __shfl_down_sync(full, b0, 1);
+        if (!FAST) {                  // reflect-101 of the smoothed image (Scharr's border)
+            if (le0) l0 = b1;
+            if (re1) r1 = b0;
+        }
+        w.b[0][ph] = b0; w.b[1][ph] = b1; w.bl0[ph] = l0; w.br1[ph] = r1;
+        // output row y = yb - 1: Gauss5 rows u = y-1 (slot p2), m = y (slot p1), d = y+1 (slot ph)
+        const int i = base + ph, y = r_start + i - 3;
+        int su = p2, sd = ph;
+        float ul0, uc0, ur0, ul1, uc1, ur1, dl0, dc0, dr0, dl1, dc1, dr1;
+        ul0 = w.bl0[su]; uc0 = w.b[0][su]; ur0 = w.b[1][su]; ul1 = w.b[0][su]; uc1 = w.b[1][su]; ur1 = w.br1[su];
+        dl0 = w.bl0[sd]; dc0 = w.b[0][sd]; dr0 = w.b[1][sd]; dl1 = w.b[0][sd]; dc1 = w.b[1][sd]; dr1 = w.br1[sd];
+        if (!FAST) {
+            // rows outside the image are replaced by their reflection: row -1 -> row 1, row H -> row H-2
+            if (y - 1 < 0) { ul0 = dl0; uc0 = dc0; ur0 = dr0; ul1 = dl1; uc1 = dc1; ur1 = dr1; }
+            else if (y + 1 >= H) { dl0 = ul0; dc0 = uc0; dr0 = ur0; dl1 = ul1; dc1 = uc1; dr1 = ur1; }
+        }
+        const float ml0 = w.bl0[p1], mc0 = w.b[0][p1], mr0 = w.b[1][p1], ml1 = w.b[0][p1], mc1 = w.b[1][p1], mr1 = w.br1[p1];
+        const float lx0 = scharr(__fsub_rn(ur0, ul0), __fsub_rn(mr0, ml0), __fsub_rn(dr0, dl0));
+        const float ly0 = scharr(__fsub_rn(dl0, ul0), __fsub_rn(dc0, uc0), __fsub_rn(dr0, ur0));
+        const float lx1 = scharr(__fsub_rn(ur1, ul1), __fsub_rn(mr1, ml1), __fsub_rn(dr1, dl1));
+        const float ly1 = scharr(__fsub_rn(dl1, ul1), __fsub_rn(dc1, uc1), __fsub_rn(dr1, ur1));
+        const float f0 = __fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(inv_k, __fadd_rn(__fmul_rn(lx0, lx0), __fmul_rn(ly0, ly0)))));
+        const float f1 = __fdiv_rn(1.f, __fadd_rn(1.f, __fmul_rn(inv_k, __fadd_rn(__fmul_rn(lx1, lx1), __fmul_rn(ly1, ly1)))));
+        const bool ok = FAST ? col_ok : (col_ok && i >= 6 && i < n_rows);
+        const long long o = oy + (long long)ph * W;
+        if (ok) *(float2*)(sm + o) = make_float2(mc0, mc1);
+        if (ok) *(float2*)(fl + o) = make_float2(f0, f1);
+    }
+}
+
+__global__ void __launch_bounds__(32, 20)
+k_prep_level_reg(const float* __restrict__ Lt, size_t lt_stride, int W, int H, int R, Gauss5 g,
+                 const float* __restrict__ kcontrast, float kscale, float* __restrict__ Lsmooth,
+                 float* __restrict__ Lflow, size_t plane_stride) {
+    const int f = blockIdx.z, lane = threadIdx.x;
+    const int xs = blockIdx.x * 56 - 4, y0 = blockIdx.y * R;     // span start (even), first output row
+    const int c0 = xs + 2 * lane;
+    const float* src = Lt + (size_t)f * lt_stride;
+    float* sm = Lsmooth + (size_t)f * plane_stride;
+    float* fl = Lflow + (size_t)f * plane_stride;
+    const float k = __fmul_rn(kcontrast[f], kscale);
+    const float inv_k = __fdiv_rn(1.f, __fmul_rn(k, k));
+    const int y_end = min(y0 + R, H);
+    const int r_start = y0 - 3, n_rows = y_end - y0 + 6;
+    const bool interior = xs >= 0 && xs + 64 <= W;
+    const bool col_ok = lane >= 2 && lane < 30 && c0 < W;
+    const bool le0 = c0 == 0, re1 = c0 + 1 == W - 1;
+    const int ca = clampi(c0, 0, W - 1), cb = clampi(c0 + 1, 0, W - 1);
+    PrepWin w;
+#pragma unroll
+    for (int k5 = 0; k5 < 5; ++k5) {
+        w.t[0][k5] = w.t[1][k5] = w.b[0][k5] = w.b[1][k5] = w.bl0[k5] = w.br1[k5] = 0.f;
+    }
+    for (int base = 0; base < n_rows; base += 5) {
+        // outputs exist for walk indices [6, n_rows); FAST additionally needs all rows of the round, and the rows
+        // above / below every output row, inside the image
+        const bool fast = interior && base >= 6 && base + 5 <= n_rows && r_start + base >= 4 && r_start + base + 5 <= H;
+        if (fast) prep_round<true>(w, src, sm, fl, W, H, base, r_start, n_rows, y0, c0, ca, cb, interior, col_ok, le0, re1, g, inv_k);
+        else prep_round<false>(w, src, sm, fl, W, H, base, r_start, n_rows, y0, c0, ca, cb, interior, col_ok, le0, re1, g, inv_k);
     }
 }
 
@@ -951,7 +1064,7 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             float* ly = ws.Ly + e.plane_off;
             float* ld = ws.Ldet + e.plane_off;
             const float sq = (float)(s * s * s * s);
-            // debug switch for tools/ab_hessian.py (bit-for-bit comparison of the two kernels)
+            // debug switch for tools/ab_kernels.py (bit-for-bit comparison of the two kernels)
             static const bool use_old = getenv("DUNK_HESSIAN_OLD") != nullptr;
             const bool reg_ok = !use_old && s >= 2 && s <= 4 && e.w % 2 == 0 && e.w >= 128 && e.h >= 32 && lsm_stride % 2 == 0 &&
                                 pyr % 2 == 0 && e.plane_off % 2 == 0;
@@ -1007,6 +1120,16 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
         const dim3 grid(div_up(e.w, kTW), div_up(e.h, kTH), frames);
         {
             ProfScope ps(ctx, st, "scale.prep_level", (double)frames * e.w * e.h * 12);
+            // debug switch for tools/ab_kernels.py (bit-for-bit comparison of the two kernels)
+            static const bool prep_old = getenv("DUNK_PREP_OLD") != nullptr;
+            if (!prep_old && e.w % 2 == 0 && e.w >= 128 && e.h >= 16 && init_stride % 2 == 0 && plane % 2 == 0 &&
+                ((uintptr_t)init & 7) == 0) {
+                const int nspans = div_up(e.w, 56);
+                int R = 128;
+                while (R > 16 && (long long)nspans * div_up(e.h, R) * frames < 4096) R /= 2;
+                k_prep_level_reg<<<dim3(nspans, div_up(e.h, R), frames), 32, 0, st>>>(
+                    init, init_stride, e.w, e.h, R, g5, ws.kcontrast, kscale, ws.Lsmooth, ws.Lflow, plane);
+            } else
             k_prep_level<<<dim3(div_up(e.w, 8 * kPrepCols), div_up(e.h, kPrepRows), frames), 256, 0, st>>>(
                 init, init_stride, e.w, e.h, g5, ws.kcontrast, kscale, ws.Lsmooth, ws.Lflow, plane);
             DUNK_KERNEL_CHECK(ctx);

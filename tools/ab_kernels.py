@@ -1,5 +1,6 @@
-"""A/B: planes of every level with the register-window Hessian kernel vs the shared-memory one
-(DUNK_HESSIAN_OLD=1), compared bit for bit.  Usage: python tools/ab_hessian.py  (spawns itself twice)"""
+"""A/B: planes of every level, keypoints and descriptors with the register-window k_hessian_reg / k_prep_level_reg
+kernels vs their predecessors (DUNK_HESSIAN_OLD=1 DUNK_PREP_OLD=1), compared bit for bit.
+Usage: python tools/ab_kernels.py  (spawns itself twice)"""
 import os
 import subprocess
 import sys
@@ -21,7 +22,7 @@ def dump(path):
         i = 0
         while i < n:
             Lt, Lx, Ly, Ldet, k, n = dunk._extract.debug_level(img, i, ctx)
-            out[f"{name}_{i}_Lx"], out[f"{name}_{i}_Ly"], out[f"{name}_{i}_Ldet"] = Lx, Ly, Ldet
+            out[f"{name}_{i}_Lx"], out[f"{name}_{i}_Ly"], out[f"{name}_{i}_Ldet"], out[f"{name}_{i}_Lt"] = Lx, Ly, Ldet, Lt
             i += 1
         r = dunk.feature_extraction.akaze_keypoint_descriptor_extraction_def(img, None, ctx)
         out[f"{name}_kps"], out[f"{name}_desc"] = r.keypoints, r.descriptors
@@ -35,7 +36,7 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     a, b = os.path.join(ROOT, "gpurun_out", "ab_new.npz"), os.path.join(ROOT, "gpurun_out", "ab_old.npz")
     subprocess.check_call([sys.executable, __file__, a], env={**os.environ})
-    subprocess.check_call([sys.executable, __file__, b], env={**os.environ, "DUNK_HESSIAN_OLD": "1"})
+    subprocess.check_call([sys.executable, __file__, b], env={**os.environ, "DUNK_HESSIAN_OLD": "1", "DUNK_PREP_OLD": "1"})
     A, B = np.load(a), np.load(b)
     bad = 0
     for k in A.files:
