@@ -645,6 +645,136 @@ k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout,
     }
 }
 
+// ---- FED without shared memory: a cascade of K stages in registers ---------------------------------
+// One warp per block owns a span of 64 adjacent columns (two per lane, interleaved) and walks down the rows.
+// Stage s (1..K) turns rows of the field after s-1 steps into rows after s steps: when the stage receives row
+// rho it forms the horizontal fluxes of that row, the vertical flux between rho-1 and rho, and emits row rho-1,
+// which is the next stage's input in the same walk step - so stage s trails the loads by s rows and keeps only
+// its previous row (value, horizontal flux difference, vertical flux above): 6 registers per stage.  The
+// conductivity sums of a row are formed once when the Lflow row is loaded and kept in a K-deep delay line
+// (statically indexed: the walk loop is unrolled by K), since stage s needs the sums of the row s-1 steps back.
+// Horizontal neighbours: one shuffle for the left value, one for the flux through the right boundary (the next
+// lane's left flux), i.e. every boundary flux is computed exactly once.  The span loses Kh = K rounded up to even
+// columns either side (garbage creeps in one column per step from the span edges), the walk K rows above and
+// below.  Same operations as k_fed: CE = c_left + c_right, CS = c_up + c_down (0 across the image border),
+// flux = C * (L_b - L_a), L += (((fE_r - fE_l) + fS_d) - fS_u) * step, image corners unchanged.
+template <int K>
+struct FedWin {
+    float L[K][2], hs[K][2], fv[K][2];     // per stage: previous input row, its fE_r - fE_l, the flux above it
+    float ce0[K], ce1[K], cs0[K], cs1[K];  // delay lines: CE(left|c0), CE(c0|c1), CS(row-1|row) for both columns
+    float cp0, cp1;                        // previous conductivity row
+};
+
+template <int K, int ROUND, bool FAST>
+__device__ __forceinline__ void fed_round(FedWin<K>& w, const float* __restrict__ lin, const float* __restrict__ lfl,
+                                          float* __restrict__ lout, int W, int H, int base, int r_start, int n_rows,
+                                          int y0, int y_end, int c0, int ca, int cb, bool interior, bool col_ok,
+                                          const FedSteps& fs) {
+    const unsigned full = 0xffffffffu;
+    float2 cl[ROUND], cc[ROUND];
+    if (FAST) {
+        const size_t o = (size_t)(r_start + base) * W + c0;
+#pragma unroll
+        for (int ph = 0; ph < ROUND; ++ph) {
+            cl[ph] = __ldg((const float2*)(lin + o + (size_t)ph * W));
+            cc[ph] = __ldg((const float2*)(lfl + o + (size_t)ph * W));
+        }
+    } else {
+#pragma unroll
+        for (int ph = 0; ph < ROUND; ++ph) {
+            const size_t ro = (size_t)clampi(r_start + min(base + ph, n_rows - 1), 0, H - 1) * W;
+            if (interior) {
+                cl[ph] = __ldg((const float2*)(lin + ro + c0));
+                cc[ph] = __ldg((const float2*)(lfl + ro + c0));
+            } else {
+                cl[ph] = make_float2(lin[ro + ca], lin[ro + cb]);
+                cc[ph] = make_float2(lfl[ro + ca], lfl[ro + cb]);
+            }
+        }
+    }
+    const long long oy = (long long)(r_start + base - K) * W + c0;      // output row r - K at ph = 0
+#pragma unroll
+    for (int ph = 0; ph < ROUND; ++ph) {
+        const int slot = ph % K;                                        // base is a multiple of K
+        const int i = base + ph, r = r_start + i;
+        {   // conductivity sums of row r
+            const float c0v = cc[ph].x, c1v = cc[ph].y;
+            const float cleft = __shfl_up_sync(full, c1v, 1);
+            float e0 = __fadd_rn(cleft, c0v), e1 = __fadd_rn(c0v, c1v);
+            float s0 = __fadd_rn(w.cp0, c0v), s1 = __fadd_rn(w.cp1, c1v);
+            if (!FAST) {
+                const bool row_in = r >= 0 && r < H, up_in = r - 1 >= 0 && r < H;
+                const bool in0 = c0 >= 0 && c0 < W, in1 = c0 + 1 >= 0 && c0 + 1 < W;
+                if (!(row_in && in0 && c0 - 1 >= 0)) e0 = 0.f;
+                if (!(row_in && in0 && in1)) e1 = 0.f;
+                if (!(up_in && in0)) s0 = 0.f;
+                if (!(up_in && in1)) s1 = 0.f;
+            }
+            w.ce0[slot] = e0; w.ce1[slot] = e1; w.cs0[slot] = s0; w.cs1[slot] = s1;
+            w.cp0 = c0v; w.cp1 = c1v;
+        }
+        float in0 = cl[ph].x, in1 = cl[ph].y;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {                                   // stage s + 1: input row rho = r - s
+            const int sl = (slot + K - s) % K;
+            const float left = __shfl_up_sync(full, in1, 1);
+            const float f01 = __fmul_rn(w.ce1[sl], __fsub_rn(in1, in0));
+            const float fl0 = __fmul_rn(w.ce0[sl], __fsub_rn(in0, left));
+            const float f1r = __shfl_down_sync(full, fl0, 1);
+            const float h0 = __fsub_rn(f01, fl0), h1 = __fsub_rn(f1r, f01);
+            const float v0 = __fmul_rn(w.cs0[sl], __fsub_rn(in0, w.L[s][0]));
+            const float v1 = __fmul_rn(w.cs1[sl], __fsub_rn(in1, w.L[s][1]));
+            float d0 = __fmul_rn(__fsub_rn(__fadd_rn(w.hs[s][0], v0), w.fv[s][0]), fs.step[s]);
+            float d1 = __fmul_rn(__fsub_rn(__fadd_rn(w.hs[s][1], v1), w.fv[s][1]), fs.step[s]);
+            if (!FAST) {                                                // the four image corners are left unchanged
+                const int ro = r - s - 1;
+                if ((ro == 0 || ro == H - 1) && c0 == 0) d0 = 0.f;
+                if ((ro == 0 || ro == H - 1) && c0 + 1 == W - 1) d1 = 0.f;
+            }
+            const float o0 = __fadd_rn(w.L[s][0], d0), o1 = __fadd_rn(w.L[s][1], d1);
+            w.L[s][0] = in0; w.L[s][1] = in1; w.hs[s][0] = h0; w.hs[s][1] = h1; w.fv[s][0] = v0; w.fv[s][1] = v1;
+            in0 = o0; in1 = o1;
+        }
+        const int y = r - K;
+        if (FAST ? col_ok : (col_ok && y >= y0 && y < y_end && i < n_rows))
+            *(float2*)(lout + oy + (long long)ph * W) = make_float2(in0, in1);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(32, K >= 7 ? 12 : (K >= 5 ? 16 : 20))
+k_fed_reg(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout, size_t out_stride,
+          const float* __restrict__ Lflow, size_t flow_stride, int W, int H, int R, FedSteps fs) {
+    constexpr int KH = (K + 1) / 2 * 2;                                 // column halo, even
+    constexpr int OUTW = 64 - 2 * KH;
+    constexpr int ROUND = K * (K <= 2 ? 4 : (K <= 4 ? 2 : 1));          // rows loaded per round, a multiple of K
+    const int f = blockIdx.z, lane = threadIdx.x;
+    const int xs = blockIdx.x * OUTW - KH, y0 = blockIdx.y * R;
+    const int c0 = xs + 2 * lane;
+    const float* lin = Lin + (size_t)f * in_stride;
+    const float* lfl = Lflow + (size_t)f * flow_stride;
+    float* lout = Lout + (size_t)f * out_stride;
+    const int y_end = min(y0 + R, H);
+    const int r_start = y0 - K, n_rows = y_end - y0 + 2 * K;
+    const bool interior = xs >= 0 && xs + 64 <= W;
+    const bool col_ok = lane >= KH / 2 && lane < 32 - KH / 2 && c0 < W;
+    const int ca = clampi(c0, 0, W - 1), cb = clampi(c0 + 1, 0, W - 1);
+    FedWin<K> w;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        w.L[s][0] = w.L[s][1] = w.hs[s][0] = w.hs[s][1] = w.fv[s][0] = w.fv[s][1] = 0.f;
+        w.ce0[s] = w.ce1[s] = w.cs0[s] = w.cs1[s] = 0.f;
+    }
+    w.cp0 = w.cp1 = 0.f;
+    for (int base = 0; base < n_rows; base += ROUND) {
+        // outputs exist for walk indices [2K, n_rows); FAST also needs every input row of the round, the row above
+        // the first one, and all stage rows inside the image
+        const bool fast = interior && base >= 2 * K && base + ROUND <= n_rows && r_start + base - K >= 1 && r_start + base + ROUND <= H;
+        if (fast) fed_round<K, ROUND, true>(w, lin, lfl, lout, W, H, base, r_start, n_rows, y0, y_end, c0, ca, cb, interior, col_ok, fs);
+        else fed_round<K, ROUND, false>(w, lin, lfl, lout, W, H, base, r_start, n_rows, y0, y_end, c0, ca, cb, interior, col_ok, fs);
+    }
+}
+
 // ---- fused Hessian: Lsmooth -> Lx, Ly (kept for orientation/descriptor) and Ldet ------------------
 // kernels of compute_derivative_kernels(scale s): taps at -s, 0, +s: smoothing [w0, w1, w0],
 // derivative [-1, 0, 1]; sepFilter2D = row pass (kx) then column pass (ky), BORDER_REFLECT_101.
@@ -1150,6 +1280,23 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             const dim3 fgrid(div_up(e.w, T), div_up(e.h, T), frames);
             {
                 ProfScope ps(ctx, st, "scale.fed", (double)frames * e.w * e.h * 12);
+                // debug switch for tools/ab_kernels.py (bit-for-bit comparison of the two kernels)
+                static const bool fed_old = getenv("DUNK_FED_OLD") != nullptr;
+                // the row-walking cascade needs many spans x bands x frames to fill the GPU: measured faster than the
+                // tiled kernel at 1024^2 and 512^2 (1.6x / 1.3x), slower at 256^2 and below (0.8x)
+                if (!fed_old && e.w % 2 == 0 && e.w >= 384 && e.h >= 192 && in_stride % 2 == 0 && out_stride % 2 == 0 && plane % 2 == 0 &&
+                    ((uintptr_t)in & 7) == 0 && ((uintptr_t)out & 7) == 0) {
+                    const int kh = (fs.k + 1) / 2 * 2, nspans = div_up(e.w, 64 - 2 * kh);
+                    int R = 128;
+                    while (R > 16 && (long long)nspans * div_up(e.h, R) * frames < 4096) R /= 2;
+                    const dim3 g3(nspans, div_up(e.h, R), frames);
+#define DUNK_FED_CASE(KK) case KK: k_fed_reg<KK><<<g3, 32, 0, st>>>(in, in_stride, out, out_stride, ws.Lflow, plane, e.w, e.h, R, fs); break;
+                    switch (fs.k) {
+                        DUNK_FED_CASE(1) DUNK_FED_CASE(2) DUNK_FED_CASE(3) DUNK_FED_CASE(4)
+                        DUNK_FED_CASE(5) DUNK_FED_CASE(6) DUNK_FED_CASE(7) DUNK_FED_CASE(8)
+                    }
+#undef DUNK_FED_CASE
+                } else
                 k_fed<<<fgrid, dim3(16, 16), (size_t)2 * kFedS * kFedS * 4, st>>>(in, in_stride, out, out_stride, ws.Lflow, plane,
                                                                                  e.w, e.h, fs);
                 DUNK_KERNEL_CHECK(ctx);

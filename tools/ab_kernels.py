@@ -1,5 +1,5 @@
-"""A/B: planes of every level, keypoints and descriptors with the register-window k_hessian_reg / k_prep_level_reg
-kernels vs their predecessors (DUNK_HESSIAN_OLD=1 DUNK_PREP_OLD=1), compared bit for bit.
+"""A/B: planes of every level, keypoints and descriptors with the register-window k_hessian_reg / k_prep_level_reg / k_fed_reg
+kernels vs their predecessors (DUNK_HESSIAN_OLD=1 DUNK_PREP_OLD=1 DUNK_FED_OLD=1), compared bit for bit.
 Usage: python tools/ab_kernels.py  (spawns itself twice)"""
 import os
 import subprocess
@@ -36,7 +36,7 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     a, b = os.path.join(ROOT, "gpurun_out", "ab_new.npz"), os.path.join(ROOT, "gpurun_out", "ab_old.npz")
     subprocess.check_call([sys.executable, __file__, a], env={**os.environ})
-    subprocess.check_call([sys.executable, __file__, b], env={**os.environ, "DUNK_HESSIAN_OLD": "1", "DUNK_PREP_OLD": "1"})
+    subprocess.check_call([sys.executable, __file__, b], env={**os.environ, "DUNK_HESSIAN_OLD": "1", "DUNK_PREP_OLD": "1", "DUNK_FED_OLD": "1"})
     A, B = np.load(a), np.load(b)
     bad = 0
     for k in A.files:
