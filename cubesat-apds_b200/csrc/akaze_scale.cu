@@ -645,6 +645,221 @@ k_fed(const float* __restrict__ Lin, size_t in_stride, float* __restrict__ Lout,
     }
 }
 
+// ---- level 0 in the register-window style (one warp per block, 64-column span, two columns per lane) --------
+// Both kernels read the u8 frame directly (gray conversion + 1/255 in registers) and keep the separable filter's
+// row-filtered rows in statically indexed register windows; FP sequences are the ones k_gray_gauss9 /
+// k_contrast_modg compile to (checked in their SASS), pinned with intrinsics.
+__device__ __forceinline__ float gray_value(int b, int g, int r) {
+    return __fmul_rn((float)((b * 3735 + g * 19235 + r * 9798 + 16384) >> 15), (float)(1.0 / 255.0));
+}
+
+// Raw pixel pairs: the loads of a round are issued back to back and only converted when the round is processed
+// (a conversion right behind its load would serialise the load latencies).  MODE 0: gray, 2-byte aligned pair in
+// .x; MODE 1: BGRA, 8-byte aligned pair in .x / .y; MODE 2: anything else - the two 8-bit gray values in .x.
+template <int MODE>
+__device__ __forceinline__ uint2 raw_pair(const unsigned char* __restrict__ img, int row_stride, int channels, int y, int c0) {
+    const unsigned char* p = img + (size_t)y * row_stride + (size_t)c0 * channels;
+    if (MODE == 0) return make_uint2(__ldg((const unsigned short*)p), 0u);
+    if (MODE == 1) return __ldg((const uint2*)p);
+    if (channels == 1) return make_uint2((unsigned)p[0] | (unsigned)p[1] << 8, 0u);
+    const unsigned v0 = (p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15;
+    const unsigned v1 = (p[channels] * 3735 + p[channels + 1] * 19235 + p[channels + 2] * 9798 + 16384) >> 15;
+    return make_uint2(v0 | v1 << 8, 0u);
+}
+
+// border spans: the two columns are clamped independently
+__device__ __forceinline__ uint2 raw_pair_clamped(const unsigned char* __restrict__ img, int row_stride, int channels, int y,
+                                                  int ca, int cb) {
+    const unsigned char* p = img + (size_t)y * row_stride;
+    unsigned v0, v1;
+    if (channels == 1) {
+        v0 = p[ca]; v1 = p[cb];
+    } else {
+        const unsigned char* a = p + (size_t)ca * channels;
+        const unsigned char* b = p + (size_t)cb * channels;
+        v0 = (a[0] * 3735 + a[1] * 19235 + a[2] * 9798 + 16384) >> 15;
+        v1 = (b[0] * 3735 + b[1] * 19235 + b[2] * 9798 + 16384) >> 15;
+    }
+    return make_uint2(v0 | v1 << 8, 0u);
+}
+
+template <int MODE>
+__device__ __forceinline__ float2 raw_to_gray(uint2 q, bool interior) {
+    if (MODE == 1 && interior)
+        return make_float2(gray_value(q.x & 255, q.x >> 8 & 255, q.x >> 16 & 255), gray_value(q.y & 255, q.y >> 8 & 255, q.y >> 16 & 255));
+    return make_float2(__fmul_rn((float)(q.x & 255), (float)(1.0 / 255.0)), __fmul_rn((float)(q.x >> 8 & 255), (float)(1.0 / 255.0)));
+}
+
+// the P rows of one round (walk indices base .. base + P - 1), rows replicated beyond the image
+template <int P, int MODE>
+__device__ __forceinline__ void gray_round_load(uint2 (&dst)[P], const unsigned char* __restrict__ img, int row_stride,
+                                                int channels, int H, int base, int r_start, int n_rows, int c0, int ca,
+                                                int cb, bool interior) {
+#pragma unroll
+    for (int ph = 0; ph < P; ++ph) {
+        const int y = clampi(r_start + min(base + ph, n_rows - 1), 0, H - 1);
+        dst[ph] = interior ? raw_pair<MODE>(img, row_stride, channels, y, c0) : raw_pair_clamped(img, row_stride, channels, y, ca, cb);
+    }
+}
+
+template <bool FAST, int MODE>
+__device__ __forceinline__ void gauss9_round(float (&t)[2][9], const uint2 (&raw)[9], bool interior, float* __restrict__ out,
+                                             int W, int base, int r_start, int n_rows, int c0, bool col_ok, const Gauss9& g) {
+    const unsigned full = 0xffffffffu;
+    auto gauss = [&](float c, float s1, float s2, float s3, float s4) {
+        return __fmaf_rn(g.k[4], s4, __fmaf_rn(g.k[3], s3, __fmaf_rn(g.k[2], s2, __fmaf_rn(g.k[0], c, __fmul_rn(g.k[1], s1)))));
+    };
+    const long long oy = (long long)(r_start + base - 4) * W + c0;      // output row r - 4 at ph = 0
+#pragma unroll
+    for (int ph = 0; ph < 9; ++ph) {
+        const float2 px = raw_to_gray<MODE>(raw[ph], interior);
+        const float a0 = px.x, a1 = px.y;
+        const float u1a0 = __shfl_up_sync(full, a0, 1), u1a1 = __shfl_up_sync(full, a1, 1);
+        const float d1a0 = __shfl_down_sync(full, a0, 1), d1a1 = __shfl_down_sync(full, a1, 1);
+        const float u2a0 = __shfl_up_sync(full, a0, 2), u2a1 = __shfl_up_sync(full, a1, 2);
+        const float d2a0 = __shfl_down_sync(full, a0, 2), d2a1 = __shfl_down_sync(full, a1, 2);
+        // column 0 (span index 2t): -1 = u1a1, +1 = a1, -2 = u1a0, +2 = d1a0, -3 = u2a1, +3 = d1a1, -4 = u2a0, +4 = d2a0
+        t[0][ph] = gauss(a0, __fadd_rn(u1a1, a1), __fadd_rn(u1a0, d1a0), __fadd_rn(u2a1, d1a1), __fadd_rn(u2a0, d2a0));
+        // column 1 (2t + 1): -1 = a0, +1 = d1a0, -2 = u1a1, +2 = d1a1, -3 = u1a0, +3 = d2a0, -4 = u2a1, +4 = d2a1
+        t[1][ph] = gauss(a1, __fadd_rn(a0, d1a0), __fadd_rn(u1a1, d1a1), __fadd_rn(u1a0, d2a0), __fadd_rn(u2a1, d2a1));
+        // output row y = r - 4: row-filtered rows y-4 .. y+4 sit in slots ph+1 .. ph (mod 9)
+        const int m4 = (ph + 1) % 9, m3 = (ph + 2) % 9, m2 = (ph + 3) % 9, m1 = (ph + 4) % 9, c = (ph + 5) % 9, p1 = (ph + 6) % 9,
+                  p2 = (ph + 7) % 9, p3 = (ph + 8) % 9;
+        const float o0 = gauss(t[0][c], __fadd_rn(t[0][m1], t[0][p1]), __fadd_rn(t[0][m2], t[0][p2]), __fadd_rn(t[0][m3], t[0][p3]),
+                               __fadd_rn(t[0][m4], t[0][ph]));
+        const float o1 = gauss(t[1][c], __fadd_rn(t[1][m1], t[1][p1]), __fadd_rn(t[1][m2], t[1][p2]), __fadd_rn(t[1][m3], t[1][p3]),
+                               __fadd_rn(t[1][m4], t[1][ph]));
+        const int i = base + ph;
+        if (FAST ? col_ok : (col_ok && i >= 8 && i < n_rows)) *(float2*)(out + oy + (long long)ph * W) = make_float2(o0, o1);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32, 24)
+k_gray_gauss9_reg(const unsigned char* __restrict__ images, size_t image_stride, int row_stride, int channels,
+                  int W, int H, int R, Gauss9 g, float* __restrict__ Lt0, size_t pyr_stride) {
+    const int f = blockIdx.z, lane = threadIdx.x;
+    const int xs = blockIdx.x * 56 - 4, y0 = blockIdx.y * R;     // span start (even), first output row
+    const int c0 = xs + 2 * lane;
+    const unsigned char* img = images + (size_t)f * image_stride;
+    float* out = Lt0 + (size_t)f * pyr_stride;
+    const int y_end = min(y0 + R, H);
+    const int r_start = y0 - 4, n_rows = y_end - y0 + 8;
+    const bool interior = xs >= 0 && xs + 64 <= W;
+    const bool col_ok = lane >= 2 && lane < 30 && c0 < W;
+    const int ca = clampi(c0, 0, W - 1), cb = clampi(c0 + 1, 0, W - 1);
+    float t[2][9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) t[0][k] = t[1][k] = 0.f;
+    // software pipeline: the next round's 9 rows are in flight while this round is filtered
+    uint2 nxt[9];
+    gray_round_load<9, MODE>(nxt, img, row_stride, channels, H, 0, r_start, n_rows, c0, ca, cb, interior);
+    for (int base = 0; base < n_rows; base += 9) {
+        uint2 cur[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) cur[k] = nxt[k];
+        if (base + 9 < n_rows) gray_round_load<9, MODE>(nxt, img, row_stride, channels, H, base + 9, r_start, n_rows, c0, ca, cb, interior);
+        const bool fast = interior && base >= 8 && base + 9 <= n_rows;
+        if (fast) gauss9_round<true, MODE>(t, cur, interior, out, W, base, r_start, n_rows, c0, col_ok, g);
+        else gauss9_round<false, MODE>(t, cur, interior, out, W, base, r_start, n_rows, c0, col_ok, g);
+    }
+}
+
+// k-contrast pass 1: Gauss5(sigma 1) -> Scharr -> |grad| plane + per-frame max; structure of k_prep_level_reg
+template <bool FAST, int MODE>
+__device__ __forceinline__ void modg_round(PrepWin& w, float& mx, const uint2 (&raw)[5], bool interior, float* __restrict__ out,
+                                           int W, int H, int base, int r_start, int n_rows, int c0, bool col_ok, bool le0,
+                                           bool re1, const Gauss5& g) {
+    const unsigned full = 0xffffffffu;
+    auto gauss = [&](float c, float s1, float s2) { return __fmaf_rn(g.k[2], s2, __fmaf_rn(g.k[0], c, __fmul_rn(g.k[1], s1))); };
+    // k_contrast_modg contracts Scharr differently from k_prep_level: the multiply sits on the middle term
+    auto scharr = [](float a, float b, float c) { return __fmaf_rn(3.f, c, __fmaf_rn(3.f, a, __fmul_rn(10.f, b))); };
+    const long long oy = (long long)(r_start + base - 3) * W + c0;      // output row y = r - 3 at ph = 0
+#pragma unroll
+    for (int ph = 0; ph < 5; ++ph) {
+        const int p1 = (ph + 4) % 5, p2 = (ph + 3) % 5, p3 = (ph + 2) % 5, p4 = (ph + 1) % 5;   // 1 .. 4 rows earlier
+        const float2 px = raw_to_gray<MODE>(raw[ph], interior);
+        const float a0 = px.x, a1 = px.y;
+        {
+            const float a0m1 = __shfl_up_sync(full, a1, 1), a1p1 = __shfl_down_sync(full, a0, 1);
+            const float a0m2 = __shfl_up_sync(full, a0, 1), a1p2 = __shfl_down_sync(full, a1, 1);
+            w.t[0][ph] = gauss(a0, __fadd_rn(a0m1, a1), __fadd_rn(a0m2, a1p1));
+            w.t[1][ph] = gauss(a1, __fadd_rn(a0, a1p1), __fadd_rn(a0m1, a1p2));
+        }
+        const float b0 = gauss(w.t[0][p2], __fadd_rn(w.t[0][p3], w.t[0][p1]), __fadd_rn(w.t[0][p4], w.t[0][ph]));
+        const float b1 = gauss(w.t[1][p2], __fadd_rn(w.t[1][p3], w.t[1][p1]), __fadd_rn(w.t[1][p4], w.t[1][ph]));
+        float l0 = __shfl_up_sync(full, b1, 1), r1 = __shfl_down_sync(full, b0, 1);
+        if (!FAST) {                  // reflect-101 of the smoothed image (Scharr's border)
+            if (le0) l0 = b1;
+            if (re1) r1 = b0;
+        }
+        w.b[0][ph] = b0; w.b[1][ph] = b1; w.bl0[ph] = l0; w.br1[ph] = r1;
+        const int i = base + ph, y = r_start + i - 3;
+        const int su = p2, sd = ph;
+        float ul0 = w.bl0[su], uc0 = w.b[0][su], ur0 = w.b[1][su], ul1 = w.b[0][su], uc1 = w.b[1][su], ur1 = w.br1[su];
+        float dl0 = w.bl0[sd], dc0 = w.b[0][sd], dr0 = w.b[1][sd], dl1 = w.b[0][sd], dc1 = w.b[1][sd], dr1 = w.br1[sd];
+        if (!FAST) {
+            if (y - 1 < 0) { ul0 = dl0; uc0 = dc0; ur0 = dr0; ul1 = dl1; uc1 = dc1; ur1 = dr1; }
+            else if (y + 1 >= H) { dl0 = ul0; dc0 = uc0; dr0 = ur0; dl1 = ul1; dc1 = uc1; dr1 = ur1; }
+        }
+        const float ml0 = w.bl0[p1], mr0 = w.b[1][p1], ml1 = w.b[0][p1], mr1 = w.br1[p1];
+        const float lx0 = scharr(__fsub_rn(ur0, ul0), __fsub_rn(mr0, ml0), __fsub_rn(dr0, dl0));
+        const float ly0 = scharr(__fsub_rn(dl0, ul0), __fsub_rn(dc0, uc0), __fsub_rn(dr0, ur0));
+        const float lx1 = scharr(__fsub_rn(ur1, ul1), __fsub_rn(mr1, ml1), __fsub_rn(dr1, dl1));
+        const float ly1 = scharr(__fsub_rn(dl1, ul1), __fsub_rn(dc1, uc1), __fsub_rn(dr1, ur1));
+        const float v0 = sqrtf(__fadd_rn(__fmul_rn(lx0, lx0), __fmul_rn(ly0, ly0)));
+        const float v1 = sqrtf(__fadd_rn(__fmul_rn(lx1, lx1), __fmul_rn(ly1, ly1)));
+        const bool ok = FAST ? col_ok : (col_ok && i >= 6 && i < n_rows);
+        if (ok) *(float2*)(out + oy + (long long)ph * W) = make_float2(v0, v1);
+        // maximum over the interior pixels only (1 <= x < W-1, 1 <= y < H-1)
+        if (FAST) {
+            if (ok) mx = fmaxf(mx, fmaxf(v0, v1));
+        } else {
+            const bool yin = y >= 1 && y < H - 1;
+            if (ok && yin && c0 >= 1 && c0 < W - 1) mx = fmaxf(mx, v0);
+            if (ok && yin && c0 + 1 >= 1 && c0 + 1 < W - 1) mx = fmaxf(mx, v1);
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32, 20)
+k_contrast_modg_reg(const unsigned char* __restrict__ images, size_t image_stride, int row_stride, int channels,
+                    int W, int H, int R, Gauss5 g, float* __restrict__ modg, size_t plane_stride, float* __restrict__ hmax) {
+    const int f = blockIdx.z, lane = threadIdx.x;
+    const int xs = blockIdx.x * 56 - 4, y0 = blockIdx.y * R;
+    const int c0 = xs + 2 * lane;
+    const unsigned char* img = images + (size_t)f * image_stride;
+    float* out = modg + (size_t)f * plane_stride;
+    const int y_end = min(y0 + R, H);
+    const int r_start = y0 - 3, n_rows = y_end - y0 + 6;
+    const bool interior = xs >= 0 && xs + 64 <= W;
+    const bool col_ok = lane >= 2 && lane < 30 && c0 < W;
+    const bool le0 = c0 == 0, re1 = c0 + 1 == W - 1;
+    const int ca = clampi(c0, 0, W - 1), cb = clampi(c0 + 1, 0, W - 1);
+    PrepWin w;
+#pragma unroll
+    for (int k5 = 0; k5 < 5; ++k5) w.t[0][k5] = w.t[1][k5] = w.b[0][k5] = w.b[1][k5] = w.bl0[k5] = w.br1[k5] = 0.f;
+    float mx = 0.f;
+    // software pipeline: the next round's 5 rows are in flight while this round is processed
+    uint2 nxt[5];
+    gray_round_load<5, MODE>(nxt, img, row_stride, channels, H, 0, r_start, n_rows, c0, ca, cb, interior);
+    for (int base = 0; base < n_rows; base += 5) {
+        uint2 cur[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) cur[k] = nxt[k];
+        if (base + 5 < n_rows) gray_round_load<5, MODE>(nxt, img, row_stride, channels, H, base + 5, r_start, n_rows, c0, ca, cb, interior);
+        // FAST: every output of the round is stored, the rows around every output row lie strictly inside the image
+        // (so the outputs are interior pixels of the maximum too: y >= 1, y + 1 < H) and the span is interior
+        const bool fast = interior && base >= 6 && base + 5 <= n_rows && r_start + base >= 4 && r_start + base + 5 <= H;
+        if (fast) modg_round<true, MODE>(w, mx, cur, interior, out, W, H, base, r_start, n_rows, c0, col_ok, le0, re1, g);
+        else modg_round<false, MODE>(w, mx, cur, interior, out, W, H, base, r_start, n_rows, c0, col_ok, le0, re1, g);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx > 0.f) atomicMax((int*)&hmax[f], __float_as_int(mx));   // non-negative floats order like ints
+}
+
 // ---- FED without shared memory: a cascade of K stages in registers ---------------------------------
 // One warp per block owns a span of 64 adjacent columns (two per lane, interleaved) and walks down the rows.
 // Stage s (1..K) turns rows of the field after s-1 steps into rows after s steps: when the stage receives row
@@ -1147,8 +1362,26 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
     // level 0
     {
         const dim3 grid(div_up(W, kTW), div_up(H, kTH), frames);
+        // debug switch for tools/ab_kernels.py (bit-for-bit comparison of the two kernel generations)
+        static const bool l0_old = getenv("DUNK_LEVEL0_OLD") != nullptr;
+        const bool l0_reg = !l0_old && W % 2 == 0 && W >= 128 && H >= 16 && pyr % 2 == 0 && plane % 2 == 0 && lt.lv[0].plane_off % 2 == 0;
+        // vector loads of a pixel pair: 2 bytes (gray) or 8 bytes (BGRA)
+        const int pair_bytes = channels == 1 ? 2 : 8;
+        const bool l0_aligned = (channels == 1 || channels == 4) && ((uintptr_t)images % pair_bytes) == 0 &&
+                                image_stride_bytes % pair_bytes == 0 && row_stride % pair_bytes == 0;
+        const int l0_mode = !l0_aligned ? 2 : (channels == 1 ? 0 : 1);
+        const int l0_spans = div_up(W, 56);
+        int l0_R = 128;
+        while (l0_R > 16 && (long long)l0_spans * div_up(H, l0_R) * frames < 4096) l0_R /= 2;
         {
             ProfScope ps(ctx, st, "scale.gray_gauss9", (double)frames * plane * (channels + 4));
+            if (l0_reg) {
+                const dim3 g0(l0_spans, div_up(H, l0_R), frames);
+                float* lt0 = ws.Lt + lt.lv[0].plane_off;
+                if (l0_mode == 0) k_gray_gauss9_reg<0><<<g0, 32, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, l0_R, g9, lt0, pyr);
+                else if (l0_mode == 1) k_gray_gauss9_reg<1><<<g0, 32, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, l0_R, g9, lt0, pyr);
+                else k_gray_gauss9_reg<2><<<g0, 32, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, l0_R, g9, lt0, pyr);
+            } else
             k_gray_gauss9<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g9,
                                                 ws.Lt + lt.lv[0].plane_off, pyr);
             DUNK_KERNEL_CHECK(ctx);
@@ -1158,6 +1391,12 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             DUNK_CUDA(cudaMemsetAsync(ws.hist, 0, (size_t)frames * kNBins * 4, st));
             {
                 ProfScope ps(ctx, st, "scale.contrast_modg", (double)frames * plane * (channels + 4));
+                if (l0_reg) {
+                    const dim3 g0(l0_spans, div_up(H, l0_R), frames);
+                    if (l0_mode == 0) k_contrast_modg_reg<0><<<g0, 32, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, l0_R, g5, ws.Lflow, plane, ws.hmax);
+                    else if (l0_mode == 1) k_contrast_modg_reg<1><<<g0, 32, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, l0_R, g5, ws.Lflow, plane, ws.hmax);
+                    else k_contrast_modg_reg<2><<<g0, 32, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, l0_R, g5, ws.Lflow, plane, ws.hmax);
+                } else
                 k_contrast_modg<<<grid, blk, 0, st>>>(images, image_stride_bytes, row_stride, channels, W, H, g5,
                                                       ws.Lflow, plane, ws.hmax);
                 DUNK_KERNEL_CHECK(ctx);
