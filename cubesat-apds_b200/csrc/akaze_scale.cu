@@ -340,28 +340,25 @@ struct PrepWin {
     float b[2][5], bl0[5], br1[5];    // Gauss5 rows: both columns, left neighbour of column 0, right neighbour of column 1
 };
 
+// the 5 input rows of one round (walk indices base .. base + 4), rows replicated beyond the image
+__device__ __forceinline__ void prep_round_load(float2 (&dst)[5], const float* __restrict__ src, int W, int H, int base,
+                                                int r_start, int n_rows, int c0, int ca, int cb, bool interior) {
+#pragma unroll
+    for (int ph = 0; ph < 5; ++ph) {
+        const float* row = src + (size_t)clampi(r_start + min(base + ph, n_rows - 1), 0, H - 1) * W;   // BORDER_REPLICATE
+        if (interior) dst[ph] = __ldg((const float2*)(row + c0));
+        else dst[ph] = make_float2(row[ca], row[cb]);
+    }
+}
+
 template <bool FAST>
-__device__ __forceinline__ void prep_round(PrepWin& w, const float* __restrict__ src, float* __restrict__ sm,
+__device__ __forceinline__ void prep_round(PrepWin& w, const float2 (&cur)[5], float* __restrict__ sm,
                                            float* __restrict__ fl, int W, int H, int base, int r_start, int n_rows,
-                                           int y0, int c0, int ca, int cb, bool interior, bool col_ok, bool le0,
-                                           bool re1, const Gauss5& g, float inv_k) {
+                                           int y0, int c0, bool col_ok, bool le0, bool re1, const Gauss5& g, float inv_k) {
     const unsigned full = 0xffffffffu;
     // the operation sequences k_prep_level compiles to (checked in its SASS), pinned here with intrinsics
     auto gauss = [&](float c, float s1, float s2) { return __fmaf_rn(g.k[2], s2, __fmaf_rn(g.k[0], c, __fmul_rn(g.k[1], s1))); };
     auto scharr = [](float a, float b, float c) { return __fmaf_rn(3.f, c, __fmaf_rn(10.f, b, __fmul_rn(3.f, a))); };
-    float2 cur[5];
-    if (FAST) {
-        const float* rowp = src + (size_t)(r_start + base) * W + c0;
-#pragma unroll
-        for (int ph = 0; ph < 5; ++ph) cur[ph] = __ldg((const float2*)(rowp + (size_t)ph * W));
-    } else {
-#pragma unroll
-        for (int ph = 0; ph < 5; ++ph) {
-            const float* row = src + (size_t)clampi(r_start + min(base + ph, n_rows - 1), 0, H - 1) * W;   // BORDER_REPLICATE
-            if (interior) cur[ph] = __ldg((const float2*)(row + c0));
-            else cur[ph] = make_float2(row[ca], row[cb]);
-        }
-    }
     const long long oy = (long long)(r_start + base - 3) * W + c0;      // output row y = r - 3 at ph = 0
 #pragma unroll
     for (int ph = 0; ph < 5; ++ph) {
@@ -431,12 +428,19 @@ k_prep_level_reg(const float* __restrict__ Lt, size_t lt_stride, int W, int H, i
     for (int k5 = 0; k5 < 5; ++k5) {
         w.t[0][k5] = w.t[1][k5] = w.b[0][k5] = w.b[1][k5] = w.bl0[k5] = w.br1[k5] = 0.f;
     }
+    // software pipeline: the next round's 5 rows are in flight while this round is processed
+    float2 nxt[5];
+    prep_round_load(nxt, src, W, H, 0, r_start, n_rows, c0, ca, cb, interior);
     for (int base = 0; base < n_rows; base += 5) {
-        // outputs exist for walk indices [6, n_rows); FAST additionally needs all rows of the round, and the rows
-        // above / below every output row, inside the image
+        float2 cur[5];
+#pragma unroll
+        for (int k5 = 0; k5 < 5; ++k5) cur[k5] = nxt[k5];
+        if (base + 5 < n_rows) prep_round_load(nxt, src, W, H, base + 5, r_start, n_rows, c0, ca, cb, interior);
+        // outputs exist for walk indices [6, n_rows); FAST additionally needs the rows above / below every output row
+        // inside the image and an interior span
         const bool fast = interior && base >= 6 && base + 5 <= n_rows && r_start + base >= 4 && r_start + base + 5 <= H;
-        if (fast) prep_round<true>(w, src, sm, fl, W, H, base, r_start, n_rows, y0, c0, ca, cb, interior, col_ok, le0, re1, g, inv_k);
-        else prep_round<false>(w, src, sm, fl, W, H, base, r_start, n_rows, y0, c0, ca, cb, interior, col_ok, le0, re1, g, inv_k);
+        if (fast) prep_round<true>(w, cur, sm, fl, W, H, base, r_start, n_rows, y0, c0, col_ok, le0, re1, g, inv_k);
+        else prep_round<false>(w, cur, sm, fl, W, H, base, r_start, n_rows, y0, c0, col_ok, le0, re1, g, inv_k);
     }
 }
 
@@ -1140,11 +1144,23 @@ struct HessWin {
 // One round = P consecutive input rows (walk indices base .. base + P - 1).  FAST: all 64 columns and all P
 // rows lie inside the image and every store of the round targets an output row, so the loads are plain
 // float2 loads off a running pointer and the stores are predicated on the lane's column only.
+// the P input rows of one round (walk indices base .. base + P - 1), reflect-101 beyond the image
+template <int P>
+__device__ __forceinline__ void hess_round_load(float2 (&dst)[P], const float* __restrict__ src, int W, int H, int base,
+                                                int r_start, int n_rows, int c0, int ca, int cb, bool interior) {
+#pragma unroll
+    for (int ph = 0; ph < P; ++ph) {
+        const float* row = src + (size_t)reflect101_once(r_start + min(base + ph, n_rows - 1), H) * W;
+        if (interior) dst[ph] = __ldg((const float2*)(row + c0));
+        else dst[ph] = make_float2(row[ca], row[cb]);
+    }
+}
+
 template <int S, bool FAST>
-__device__ __forceinline__ void hess_round(HessWin<S>& w, const float* __restrict__ src, float* __restrict__ ox,
+__device__ __forceinline__ void hess_round(HessWin<S>& w, const float2 (&cur)[2 * S + 1], float* __restrict__ ox,
                                            float* __restrict__ oy, float* __restrict__ od, int W, int H, int base,
-                                           int r_start, int n_rows, int y0, int y_end, int c0, int ca, int cb,
-                                           bool interior, bool col_ok, float w0, float w1, float sigma_quat) {
+                                           int r_start, int n_rows, int y0, int y_end, int c0, bool col_ok, float w0,
+                                           float w1, float sigma_quat) {
     constexpr int P = 2 * S + 1;
     constexpr int DA = (S + 1) / 2, DB = S / 2;            // shuffle distances (lanes) for the two columns
     auto tri = [&](float a, float b, float c) { return __fmaf_rn(w0, c, __fmaf_rn(w0, a, __fmul_rn(w1, b))); };
@@ -1156,20 +1172,6 @@ __device__ __forceinline__ void hess_round(HessWin<S>& w, const float* __restric
         return which == 0 ? __shfl_down_sync(0xffffffffu, (S & 1) ? v1 : v0, DB)
                           : __shfl_down_sync(0xffffffffu, (S & 1) ? v0 : v1, DA);
     };
-    // the P input rows of this round, loaded up front so that their latencies overlap
-    float2 cur[P];
-    if (FAST) {
-        const float* rowp = src + (size_t)(r_start + base) * W + c0;
-#pragma unroll
-        for (int ph = 0; ph < P; ++ph) cur[ph] = __ldg((const float2*)(rowp + (size_t)ph * W));
-    } else {
-#pragma unroll
-        for (int ph = 0; ph < P; ++ph) {
-            const float* row = src + (size_t)reflect101_once(r_start + min(base + ph, n_rows - 1), H) * W;
-            if (interior) cur[ph] = __ldg((const float2*)(row + c0));
-            else cur[ph] = make_float2(row[ca], row[cb]);
-        }
-    }
     // output offsets of row q = r - S (Lx, Ly) for ph = 0; Ldet goes S rows further up
     const long long oq = (long long)(r_start + base - S) * W + c0;
 #pragma unroll
@@ -1215,7 +1217,7 @@ __device__ __forceinline__ void hess_round(HessWin<S>& w, const float* __restric
 }
 
 template <int S>
-__global__ void __launch_bounds__(32, S == 4 ? 16 : (S == 3 ? 20 : 24))
+__global__ void __launch_bounds__(32, S == 4 ? 12 : (S == 3 ? 16 : 20))
 k_hessian_reg(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, int R, int nspans, float w0, float w1,
               float sigma_quat, float* __restrict__ Lx, float* __restrict__ Ly, float* __restrict__ Ldet,
               size_t pyr_stride) {
@@ -1244,11 +1246,18 @@ k_hessian_reg(const float* __restrict__ Lsm, size_t sm_stride, int W, int H, int
     for (int k = 0; k < P; ++k)
 #pragma unroll
         for (int c = 0; c < 2; ++c) w.rd[c][k] = w.cs[c][k] = w.rdx[c][k] = w.csx[c][k] = w.csy[c][k] = 0.f;
+    // software pipeline: the next round's P rows are in flight while this round is processed
+    float2 nxt[P];
+    hess_round_load<P>(nxt, src, W, H, 0, r_start, n_rows, c0, ca, cb, interior);
     for (int base = 0; base < n_rows; base += P) {
+        float2 cur[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) cur[k] = nxt[k];
+        if (base + P < n_rows) hess_round_load<P>(nxt, src, W, H, base + P, r_start, n_rows, c0, ca, cb, interior);
         // Lx / Ly stores are valid for walk indices [3S, n_rows - S), Ldet stores for [4S, n_rows)
-        const bool fast = interior && base >= 4 * S && base + P <= n_rows - S && r_start + base >= 0 && r_start + base + P <= H;
-        if (fast) hess_round<S, true>(w, src, ox, oy, od, W, H, base, r_start, n_rows, y0, y_end, c0, ca, cb, interior, col_ok, w0, w1, sigma_quat);
-        else hess_round<S, false>(w, src, ox, oy, od, W, H, base, r_start, n_rows, y0, y_end, c0, ca, cb, interior, col_ok, w0, w1, sigma_quat);
+        const bool fast = base >= 4 * S && base + P <= n_rows - S;
+        if (fast) hess_round<S, true>(w, cur, ox, oy, od, W, H, base, r_start, n_rows, y0, y_end, c0, col_ok, w0, w1, sigma_quat);
+        else hess_round<S, false>(w, cur, ox, oy, od, W, H, base, r_start, n_rows, y0, y_end, c0, col_ok, w0, w1, sigma_quat);
     }
 }
 
