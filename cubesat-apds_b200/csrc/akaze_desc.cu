@@ -49,7 +49,8 @@ constexpr int kSlices = 42, kWin = 7, kAng = 109;
 
 struct OriShared {
     float rx[kAng], ry[kAng];
-    unsigned char bin[kAng], sorted[kAng];
+    unsigned char sorted[kAng];
+    unsigned char run[kSlices];
     int cum[kSlices + 1];
 };
 
@@ -71,27 +72,71 @@ k_orientation(DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restr
     const float* lx = Lx + (size_t)f * pyr_stride + e.plane_off;
     const float* ly = Ly + (size_t)f * pyr_stride + e.plane_off;
     const float ang_step = (float)(2.0 * M_PI / kSlices);
-    for (int s = lane; s < kAng; s += 32) {
+    // all 8 gathers of a lane are issued before any of them is used (4 samples x Lx, Ly)
+    constexpr int kIt = (kAng + 31) / 32;
+    float gx[kIt], gy[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int s = min(lane + 32 * it, kAng - 1);
         const int y = min(max(y0 + __ldg(&c_ori.yi[s]) * scale, 0), e.h - 1);
         const int x = min(max(x0 + __ldg(&c_ori.xi[s]) * scale, 0), e.w - 1);
-        const float w = __ldg(&c_ori.w[s]);
-        const float rx = __fmul_rn(w, lx[(size_t)y * e.w + x]);
-        const float ry = __fmul_rn(w, ly[(size_t)y * e.w + x]);
-        sh.rx[s] = rx;
-        sh.ry[s] = ry;
-        const float ang = __fmul_rn(fast_atan2_deg(ry, rx), (float)(M_PI / 180.0));
-        int b = (int)__fdiv_rn(ang, ang_step);
-        if (b < 0 || b >= kSlices) b = 0;
-        sh.bin[s] = (unsigned char)b;
+        gx[it] = __ldg(lx + (size_t)y * e.w + x);
+        gy[it] = __ldg(ly + (size_t)y * e.w + x);
+    }
+    for (int b = lane; b <= kSlices; b += 32) sh.cum[b] = 0;
+    if (lane < kSlices) sh.run[lane] = 0;
+    if (lane + 32 < kSlices) sh.run[lane + 32] = 0;
+    __syncwarp();
+    int bins[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+        const int s = lane + 32 * it;
+        bins[it] = 255;
+        if (s < kAng) {
+            const float w = __ldg(&c_ori.w[s]);
+            const float rx = __fmul_rn(w, gx[it]);
+            const float ry = __fmul_rn(w, gy[it]);
+            sh.rx[s] = rx;
+            sh.ry[s] = ry;
+            const float ang = __fmul_rn(fast_atan2_deg(ry, rx), (float)(M_PI / 180.0));
+            int b = (int)__fdiv_rn(ang, ang_step);
+            if (b < 0 || b >= kSlices) b = 0;
+            bins[it] = b;
+            atomicAdd(&sh.cum[b + 1], 1);                  // slice populations
+        }
     }
     __syncwarp();
-    if (lane == 0) {   // quantized_counting_sort (unstable: descending index inside a slice)
-        for (int i = 0; i <= kSlices; ++i) sh.cum[i] = 0;
-        for (int i = 0; i < kAng; ++i) sh.cum[sh.bin[i]]++;
-        for (int i = 1; i <= kSlices; ++i) sh.cum[i] += sh.cum[i - 1];
-        for (int i = 0; i < kAng; ++i) sh.sorted[--sh.cum[sh.bin[i]]] = (unsigned char)i;
+    {   // inclusive scan of the 43 counters: cum[b] = first position of slice b, cum[kSlices] = kAng
+        int v0 = sh.cum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v0, o);
+            if (lane >= o) v0 += t;
+        }
+        const int tot = __shfl_sync(0xffffffffu, v0, 31);
+        int v1 = lane + 32 <= kSlices ? sh.cum[lane + 32] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v1, o);
+            if (lane >= o) v1 += t;
+        }
+        __syncwarp();
+        sh.cum[lane] = v0;
+        if (lane + 32 <= kSlices) sh.cum[lane + 32] = v1 + tot;
     }
     __syncwarp();
+    // quantized_counting_sort places sample i at (end of its slice) - 1 - (same-slice samples before i), i.e. a slice
+    // reads in DESCENDING sample index: position = slice start + number of same-slice samples with a larger index
+#pragma unroll
+    for (int it = kIt - 1; it >= 0; --it) {
+        const int s = lane + 32 * it;
+        const int b = bins[it];
+        const unsigned m = __match_any_sync(0xffffffffu, b);
+        if (b != 255) sh.sorted[sh.cum[b] + sh.run[b] + __popc(m & (0xfffffffeu << lane))] = (unsigned char)s;
+        __syncwarp();
+        if (b != 255 && (m & ((1u << lane) - 1)) == 0) sh.run[b] += (unsigned char)__popc(m);   // lowest lane of the group
+        __syncwarp();
+    }
     float bestN = -1.f, bestX = 0.f, bestY = 0.f;
     int bestW = 1 << 30;
     for (int sn = lane; sn < kSlices; sn += 32) {
