@@ -45,6 +45,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 constexpr int kWarpsPerBlock = 8;
+constexpr int kMldbWarps = 4;          // 128-thread blocks: the kernel needs ~150 registers, small blocks pack the register file better
 constexpr int kSlices = 42, kWin = 7, kAng = 109;
 
 struct OriShared {
@@ -177,19 +178,19 @@ __device__ __forceinline__ int toggle_flt(float v) {
     return x ^ ((x < 0) ? 0x7fffffff : 0);   // CV_TOGGLE_FLT
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kMldbWarps * 32)
 k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restrict__ kp_count,
        const float* __restrict__ Lt, const float* __restrict__ Lx, const float* __restrict__ Ly, size_t pyr_stride,
        LevelsDev lv, uint4* __restrict__ desc64_all) {
-    __shared__ int vals_all[kWarpsPerBlock][29 * 3];
-    __shared__ float pri_all[kWarpsPerBlock][441];     // Lt at the lattice points (NaN = outside the image)
-    __shared__ float2 pxy_all[kWarpsPerBlock][441];    // rotated (Lx, Ly)
+    __shared__ int vals_all[kMldbWarps][29 * 3];
+    __shared__ float pri_all[kMldbWarps][441];     // Lt at the lattice points (NaN = outside the image)
+    __shared__ float2 pxy_all[kMldbWarps][441];    // rotated (Lx, Ly)
     const int f = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // a fixed, small grid strides over the frame's keypoints: a grid sized for the keypoint CAPACITY is > 90 %
     // empty blocks whose turnover (45 KB of shared memory each) would dominate the kernel
     const int count = kp_count[f];
-    for (int ki = blockIdx.x * kWarpsPerBlock + warp; ki < count; ki += gridDim.x * kWarpsPerBlock) {
+    for (int ki = blockIdx.x * kMldbWarps + warp; ki < count; ki += gridDim.x * kMldbWarps) {
     int* vals = vals_all[warp];
     const DunkKeyPoint kp = kps_all[(size_t)f * kp_cap + ki];
     const LevelDev& e = lv.lv[kp.class_id];
@@ -359,8 +360,8 @@ int akaze_describe(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const A
     }
     {
         ProfScope ps(ctx, st, "describe.mldb", 0.0);
-        const dim3 mgrid(std::min(div_up(ws.kp_cap, kWarpsPerBlock), 64), frames);
-        k_mldb<<<mgrid, kWarpsPerBlock * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lt, ws.Lx, ws.Ly, lt.pyramid_floats, lv,
+        const dim3 mgrid(std::min(div_up(ws.kp_cap, kMldbWarps), 128), frames);
+        k_mldb<<<mgrid, kMldbWarps * 32, 0, st>>>(ws.kps, ws.kp_cap, ws.kp_count, ws.Lt, ws.Lx, ws.Ly, lt.pyramid_floats, lv,
                                                       ws.desc64);
         DUNK_KERNEL_CHECK(ctx);
     }

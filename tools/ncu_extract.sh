@@ -4,7 +4,7 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_fed|k_hessian|k_prep_level" --launch-skip 116 -c 13 \
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_fed|k_hessian|k_prep_level|k_gray_gauss9|k_contrast_modg" --launch-skip 120 -c 17 \
   -o gpurun_out/prof_scale -f python tools/bench_extract.py 16 16 1 > gpurun_out/ncu_scale.log 2>&1
 ncu -i gpurun_out/prof_scale.ncu-rep --page raw --csv > gpurun_out/prof_scale_raw.csv 2>/dev/null
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"k_mldb|k_orientation|k_extrema" --launch-skip 36 -c 18 \
