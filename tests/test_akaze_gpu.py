@@ -71,6 +71,22 @@ def test_extract_odd_size_bgr_vs_oracle(dunk, ctx):
     assert_parity(rep)
 
 
+@pytest.mark.parametrize("h,w,channels", [(210, 386, 4), (128, 130, 1), (200, 770, 1)])
+def test_extract_even_awkward_shapes_vs_oracle(dunk, ctx, h, w, channels):
+    """even widths take the register-window kernels (spans of 64 columns, bands of <= 128 rows): shapes whose last span
+    and band are partial, a level just above the FED cascade's size threshold (386 x 210), a level just above the
+    kernels' minimum (130 x 128), and a wide flat one; checked against the oracle like the odd-size case"""
+    import synthdata
+    g = synthdata.synth_image(h, w, 21 + w)
+    img = g if channels == 1 else np.dstack([g, np.roll(g, 2, 1), np.roll(g, -3, 0), np.full_like(g, 255)]).copy()
+    kps, desc = ao.detect_and_compute(img)
+    r = dunk.feature_extraction.akaze_keypoint_descriptor_extraction_def(img, None, ctx)
+    rep = compare(kps, desc, r.keypoints, r.descriptors)
+    print(rep)
+    assert len(kps) >= 5
+    assert_parity(rep)
+
+
 def test_gray_bgr_bgra_identical(dunk, ctx):
     g = G["a_img"][:200, :240]
     fe = dunk.feature_extraction
