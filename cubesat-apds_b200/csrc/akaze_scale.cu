@@ -171,14 +171,20 @@ k_contrast_hist(const float* __restrict__ modg, size_t plane_stride, int W, int 
     if (hm > 0.f) {
         const float scale = __fdiv_rn((float)(kNBins - 1), hm);
         const float* src = modg + (size_t)f * plane_stride;
-        const int iw = W - 2, ih = H - 2;
-        const long long total = (long long)iw * ih;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-             i += (long long)gridDim.x * blockDim.x) {
-            const int y = (int)(i / iw) + 1, x = (int)(i % iw) + 1;
-            int b = (int)__fmul_rn(src[(size_t)y * W + x], scale);
-            b = min(max(b, 0), kNBins - 1);
-            atomicAdd(&sh[b], 1);
+        // interior rows 1 .. H-2 are dealt to the blocks round-robin, two rows per pass so that a thread has
+        // 2 x ceil((W-2)/256) independent loads in flight (no per-element division)
+        for (int y = 1 + 2 * blockIdx.x; y < H - 1; y += 2 * gridDim.x) {
+            const float* r0 = src + (size_t)y * W;
+            const bool two = y + 1 < H - 1;
+            const float* r1 = r0 + (two ? W : 0);
+            for (int x = 1 + threadIdx.x; x < W - 1; x += blockDim.x) {
+                const float v0 = r0[x], v1 = r1[x];
+                int b0 = (int)__fmul_rn(v0, scale), b1 = (int)__fmul_rn(v1, scale);
+                b0 = min(max(b0, 0), kNBins - 1);
+                b1 = min(max(b1, 0), kNBins - 1);
+                atomicAdd(&sh[b0], 1);
+                if (two) atomicAdd(&sh[b1], 1);
+            }
         }
     }
     __syncthreads();
