@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ by running the reference's OpenCV entry
 points (through cv2, the same C++ library the `opencv` crate binds) with the reference's exact
-arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|akaze|pnp|warp|l2|all]
+arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|lmeds|akaze|pnp|warp|l2|all]
 The OpenCV version is recorded in every file (parity is defined against that version)."""
 import os
 import sys
@@ -83,6 +83,25 @@ def make_ransac():
         out[f"c{i}_H"], out[f"c{i}_mask"] = H, mask.ravel().astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, "ransac_golden.npz"), **out)
     print("ransac_golden.npz:", len(cases), "cases")
+
+
+LMEDS_CASES = [(50, 0.2, 0.5), (200, 0.4, 0.5), (1000, 0.3, 1.0), (2000, 0.4, 2.0), (100, 0.0, 0.1), (300, 0.45, 1.5),
+               (1500, 0.1, 3.0), (777, 0.25, 4.0), (5, 0.0, 0.0), (4, 0.0, 0.0)]
+
+
+def make_lmeds():
+    """cv2.findHomography(src, dst, LMEDS, thr) — HomographyMethod::LMEDS, mod.rs:25-31,243-250.  Noise levels up to
+    4 px make sigma, the sigma-inlier set and the returned (thr-based) mask differ, so the mask rule is pinned."""
+    out = {"opencv_version": np.array(cv2.__version__), "n_cases": np.array(len(LMEDS_CASES) + 1)}
+    cases = [ransac_case(n, of, sg, 100 + seed) + (3.0,) for seed, (n, of, sg) in enumerate(LMEDS_CASES)]
+    grid = np.array([(i, j) for i in range(1, 11) for j in range(1, 11)], dtype=np.float32)
+    cases.append((grid, grid.copy(), 1.0))
+    for i, (src, dst, thr) in enumerate(cases):
+        H, mask = cv2.findHomography(src, dst, cv2.LMEDS, thr)
+        out[f"c{i}_src"], out[f"c{i}_dst"], out[f"c{i}_thr"] = src, dst, np.array(thr)
+        out[f"c{i}_H"], out[f"c{i}_mask"] = H, mask.ravel().astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "lmeds_golden.npz"), **out)
+    print("lmeds_golden.npz:", len(cases), "cases")
 
 
 def synth(n, seed, m=None):
@@ -255,6 +274,8 @@ if __name__ == "__main__":
         make_match()
     if what in ("ransac", "all") and "make_ransac" in globals():
         make_ransac()
+    if what in ("lmeds", "all") and "make_lmeds" in globals():
+        make_lmeds()
     if what in ("akaze", "all") and "make_akaze" in globals():
         make_akaze()
     if what in ("pnp", "all") and "make_pnp" in globals():

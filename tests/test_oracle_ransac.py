@@ -52,3 +52,27 @@ def test_update_num_iters():
     assert ro.ransac_update_num_iters(0.995, 0.0, 4, 2000) == 0
     assert ro.ransac_update_num_iters(0.995, 1.0, 4, 2000) == 2000
     assert ro.ransac_update_num_iters(0.995, 0.5, 4, 2000) == ro.cv_round(np.log(0.005) / np.log(1 - 0.5 ** 4))
+
+
+# ---- LMEDS (HomographyMethod::LMEDS, homographier mod.rs:25-31) ------------------------------------------------
+GL = np.load(os.path.join(os.path.dirname(__file__), "golden", "lmeds_golden.npz"))
+NL = int(GL["n_cases"])
+
+
+@pytest.mark.parametrize("i", range(NL))
+def test_find_homography_lmeds_matches_cv2(i):
+    src, dst, thr = GL[f"c{i}_src"], GL[f"c{i}_dst"], float(GL[f"c{i}_thr"])
+    H, mask = ro.find_homography_lmeds(src, dst, thr)
+    assert np.array_equal(mask, GL[f"c{i}_mask"])
+    assert rel_err(H, GL[f"c{i}_H"]) < H_RTOL
+
+
+def test_lmeds_iteration_count_and_mask_rule():
+    """55 iterations for confidence 0.995 (outlier ratio 0.45); on a noisy case sigma is far from the caller's
+    threshold, so the sigma-inliers (used for the refit) and the returned mask (thr on the refined H) differ"""
+    assert max(ro.ransac_update_num_iters(0.995, 0.45, 4, 2000), 3) == 55
+    i = 7
+    src, dst = GL[f"c{i}_src"], GL[f"c{i}_dst"]
+    _, sig_mask, sigma, iters = ro.lmeds_loop(src, dst)
+    assert iters == 55 and sigma > 6.0
+    assert int(sig_mask.sum()) > int(GL[f"c{i}_mask"].sum())
