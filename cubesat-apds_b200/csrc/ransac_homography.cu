@@ -157,6 +157,27 @@ __device__ int warp_count_inliers(const double* H, const float2* __restrict__ sr
     return c;
 }
 
+// LMEDS score: bit pattern of the (n / 2)-th smallest f32 reprojection error (what std::nth_element at count / 2
+// leaves there in ptsetreg.cpp).  Non-negative floats order like their bit patterns, so the answer is the
+// smallest v with #{err bits <= v} >= n / 2 + 1: 32 bisection steps, each a pass over the points (errors are
+// recomputed instead of stored: 55 hypotheses per problem, the path is not throughput critical).
+__device__ unsigned warp_median_error_bits(const double* H, const float2* __restrict__ src,
+                                           const float2* __restrict__ dst, int n, int lane) {
+    float Hf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Hf[i] = (float)H[i];
+    const int need = n / 2 + 1;
+    unsigned lo = 0u, hi = 0xffffffffu;
+    while (lo < hi) {
+        const unsigned mid = lo + (hi - lo) / 2u;
+        int c = 0;
+        for (int i = lane; i < n; i += 32) c += (__float_as_uint(reproj_err(Hf, src[i], dst[i])) <= mid);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= need) hi = mid; else lo = mid + 1u;
+    }
+    return lo;
+}
+
 __device__ int update_num_iters(double p, double ep, int model_points, int max_iters) {
     p = fmin(fmax(p, 0.), 1.);
     ep = fmin(fmax(ep, 0.), 1.);
@@ -250,6 +271,9 @@ struct Shared {
     int counts[kMaxHyp];
     double Hs[kMaxHyp][9];
     double bestH[9];
+    double min_median;   // LMEDS
+    float fit_thr2;      // squared inlier threshold of the refit (RANSAC: thr^2, LMEDS: sigma^2)
+    int have_best;
     // refit / LM
     double red_buf[kWarps * 46];
     double red[46];
@@ -509,7 +533,7 @@ __device__ void lm_refine(Shared& sh, const float2* __restrict__ src, const floa
     __syncthreads();
 }
 
-// method: 8 = RANSAC, 0 = all points least squares (+LM)
+// method: 8 = RANSAC, 4 = LMEDS, 0 = all points least squares (+LM)
 __global__ void __launch_bounds__(kThreads)
 find_homography_kernel(const float2* __restrict__ src_all, const float2* __restrict__ dst_all,
                        const int* __restrict__ starts, const int* __restrict__ counts, int method, float thr, int max_iters,
@@ -539,7 +563,8 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
     }
     auto all_points = [](int) { return true; };
 
-    if (method != 8 || n == 4) {
+    const bool lmeds = method == 4;
+    if ((method != 8 && !lmeds) || n == 4) {
         // Default(0): least-squares DLT on all points (+ LM if n > 4); RANSAC with exactly 4 points:
         // single model, mask all ones (ptsetreg.cpp count == modelPoints)
         const bool ok = dlt_refit(sh, src, dst, n, all_points);
@@ -552,8 +577,11 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
 
     if (tid == 0) {
         sh.rng_state = ~0ull;
-        sh.niters = max_iters; sh.iter = 0; sh.best_count = 0; sh.rejects = 0;
+        // LMeDSPointSetRegistrator: a fixed number of iterations from an assumed outlier ratio of 0.45, at least 3
+        sh.niters = lmeds ? max(update_num_iters(confidence, 0.45, 4, max_iters), 3) : max_iters;
+        sh.iter = 0; sh.best_count = 0; sh.rejects = 0;
         sh.exhausted = 0; sh.done = 0; sh.nh = 0;
+        sh.min_median = DBL_MAX; sh.have_best = 0; sh.fit_thr2 = thr2;
     }
     __syncthreads();
     int total_hyp = 0;
@@ -616,7 +644,8 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
             for (int i = 0; i < 4; ++i) { s[i] = src[sh.hyp[h][i]]; d[i] = dst[sh.hyp[h][i]]; }
             double H[9];
             const bool ok = homography_4pt(s, d, H);
-            const int c = ok ? warp_count_inliers(H, src, dst, n, thr2, lane) : -1;
+            const int c = !ok ? -1 : lmeds ? (int)warp_median_error_bits(H, src, dst, n, lane)
+                                           : warp_count_inliers(H, src, dst, n, thr2, lane);
             if (lane == 0) sh.counts[h] = c;
             if (lane < 9) sh.Hs[h][lane] = H[lane];
         }
@@ -625,7 +654,14 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
         if (tid == 0) {
             for (int h = 0; h < nh && sh.iter < sh.niters; ++h) {
                 const int good = sh.counts[h];
-                if (good > max(sh.best_count, 3)) {
+                if (lmeds) {
+                    // median < minMedian, strict, in stream order; a failed minimal solve is skipped
+                    if (good != -1 && (double)__int_as_float(good) < sh.min_median) {
+                        sh.min_median = (double)__int_as_float(good);
+                        sh.have_best = 1;
+                        for (int i = 0; i < 9; ++i) sh.bestH[i] = sh.Hs[h][i];
+                    }
+                } else if (good > max(sh.best_count, 3)) {
                     sh.best_count = good;
                     for (int i = 0; i < 9; ++i) sh.bestH[i] = sh.Hs[h][i];
                     sh.niters = update_num_iters(confidence, (double)(n - good) / n, 4, sh.niters);
@@ -640,6 +676,27 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
         if (sh.done) break;
     }
 
+    if (lmeds) {
+        // sigma = 2.5 * 1.4826 * (1 + 5 / (count - modelPoints)) * sqrt(minMedian), at least 0.001; the model stands
+        // if at least 4 points lie within sigma (findInliers: err <= (float)(sigma * sigma))
+        if (tid == 0 && sh.have_best) {
+            double sigma = 2.5 * 1.4826 * (1.0 + 5.0 / (double)(n - 4)) * sqrt(sh.min_median);
+            sigma = fmax(sigma, 0.001);
+            sh.fit_thr2 = (float)(sigma * sigma);
+        }
+        __syncthreads();
+        double cnt[1] = {0};
+        if (sh.have_best) {
+            float Hb[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Hb[i] = (float)sh.bestH[i];
+            const float t2 = sh.fit_thr2;
+            for (int i = tid; i < n; i += kThreads) cnt[0] += (reproj_err(Hb, src[i], dst[i]) <= t2);
+        }
+        block_reduce<1>(cnt, sh.red_buf, sh.red);
+        if (tid == 0) sh.best_count = sh.have_best && sh.red[0] >= 4.0 ? (int)sh.red[0] : 0;
+        __syncthreads();
+    }
     if (sh.best_count == 0) {
         for (int i = tid; i < n && mask; i += kThreads) mask[i] = 0;
         __syncthreads();
@@ -651,7 +708,8 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
 #pragma unroll
     for (int i = 0; i < 8; ++i) Hf[i] = (float)sh.bestH[i];
     __syncthreads();
-    auto inlier = [&](int i) { return reproj_err(Hf, src[i], dst[i]) <= thr2; };
+    const float fit2 = sh.fit_thr2;
+    auto inlier = [&](int i) { return reproj_err(Hf, src[i], dst[i]) <= fit2; };
     dlt_refit(sh, src, dst, n, inlier);   // on failure keeps the minimal-sample model
     lm_refine(sh, src, dst, n, inlier);
     // ---- (5) returned mask = inliers of the final H (cv2 4.13) ------
@@ -711,8 +769,8 @@ int dunk_find_homography_batch(dunk_ctx* ctx, const float* src, const float* dst
     DUNK_REQUIRE(ctx && offsets && H && info && n_problems >= 0, DUNK_ERR_BAD_ARG,
                  "dunk_find_homography_batch: NULL argument");
     if (n_problems == 0) return DUNK_OK;
-    DUNK_REQUIRE(method == DUNK_H_RANSAC || method == DUNK_H_DEFAULT, DUNK_ERR_BAD_ARG,
-                 "dunk_find_homography: method %d not implemented (RANSAC=8 and Default=0 are)", method);
+    DUNK_REQUIRE(method == DUNK_H_RANSAC || method == DUNK_H_LMEDS || method == DUNK_H_DEFAULT, DUNK_ERR_BAD_ARG,
+                 "dunk_find_homography: method %d not implemented (RANSAC=8, LMEDS=4 and Default=0 are)", method);
     const int total = offsets[n_problems];
     for (int b = 0; b < n_problems; ++b) {
         const int n = offsets[b + 1] - offsets[b];

@@ -108,3 +108,28 @@ def test_random_cases_vs_oracle(dunk, ctx):
         H, mask = hg.find_homography_mat(src, dst, hg.HomographyMethod.RANSAC, 3.0, ctx)
         assert np.array_equal(mask.mat.ravel(), mo)
         assert rel_err(H.mat, Ho) < H_RTOL
+
+
+# ---- LMEDS (HomographyMethod::LMEDS, homographier mod.rs:25-31,243-250) ----------------------------------------
+GL = np.load(os.path.join(os.path.dirname(__file__), "golden", "lmeds_golden.npz"))
+NL = int(GL["n_cases"])
+
+
+@pytest.mark.parametrize("i", range(NL))
+def test_find_homography_lmeds_vs_cv2_golden(dunk, ctx, i):
+    hg = dunk.homographier
+    src, dst, thr = GL[f"c{i}_src"], GL[f"c{i}_dst"], float(GL[f"c{i}_thr"])
+    H, mask = hg.find_homography_mat(src, dst, hg.HomographyMethod.LMEDS, thr, ctx)
+    assert np.array_equal(mask.mat.ravel(), GL[f"c{i}_mask"])
+    assert rel_err(H.mat, GL[f"c{i}_H"]) < H_RTOL
+
+
+def test_lmeds_batch_runs_55_iterations(dunk, ctx):
+    hg = dunk.homographier
+    ids = [0, 2, 3, 7]
+    Hb, masks, info = hg.find_homography_batch([GL[f"c{i}_src"] for i in ids], [GL[f"c{i}_dst"] for i in ids], 3.0,
+                                               hg.HomographyMethod.LMEDS, ctx)
+    for k, i in enumerate(ids):
+        assert np.array_equal(masks[k], GL[f"c{i}_mask"]) and info[k, 0] == 1
+        assert info[k, 2] == 55                       # LMeDS iteration count for confidence 0.995
+        assert rel_err(Hb[k].reshape(3, 3), GL[f"c{i}_H"]) < H_RTOL
