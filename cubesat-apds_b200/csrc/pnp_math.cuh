@@ -702,5 +702,134 @@ DUNK_HD inline float reproj_err_f32(const double* R2, const double* t, const Cam
     return DUNK_FADD(DUNK_FMUL(dx, dx), DUNK_FMUL(dy, dy));
 }
 
+// SOLVEPNP_ITERATIVE's final answer: the minimum of the squared reprojection error over the used points
+// (calib3d solvePnP -> Levenberg-Marquardt on (rvec, tvec); cv2 4.13.0's result agrees with the minimiser to
+// ~1e-8).  Levenberg-Marquardt from the given pose with a local rotation update R <- exp([dw]x) R, so the
+// Jacobian needs no Rodrigues derivative: d(RX + t)/dw = -[RX]x, d/dt = I.  One pass over the points per
+// iteration accumulates J^T J (21), J^T r (6) and the cost; the 6 x 6 solve runs redundantly in every thread of
+// the executor (all see the same sums), exactly like epnp_solve's scalar part.  Returns the final RMS error.
+template <class Exec>
+DUNK_HD double pnp_refine(const Exec& ex, const Camera& cam, double (&R)[9], double (&t)[3], int max_iters = 50) {
+    double lambda = 1e-3, prev_cost = -1.0;
+    double Rp[9], tp[3];          // last accepted pose
+    for (int i = 0; i < 9; ++i) Rp[i] = R[i];
+    for (int i = 0; i < 3; ++i) tp[i] = t[i];
+    double JtJp[21], Jtrp[6];     // normal equations at the last accepted pose
+    for (int i = 0; i < 21; ++i) JtJp[i] = 0;
+    for (int i = 0; i < 6; ++i) Jtrp[i] = 0;
+    const double n = ex.count();
+    for (int it = 0; it < max_iters; ++it) {
+        double s[28];
+        const double r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6], r7 = R[7], r8 = R[8];
+        const double t0 = t[0], t1 = t[1], t2 = t[2];
+        const double fu = cam.fu, fv = cam.fv, uc = cam.uc, vc = cam.vc;
+        ex.template sum<28>(
+            [=](const Point& p, double (&a)[28]) {
+                const double ax = r0 * p.X + r1 * p.Y + r2 * p.Z, ay = r3 * p.X + r4 * p.Y + r5 * p.Z,
+                             az = r6 * p.X + r7 * p.Y + r8 * p.Z;          // R X
+                const double x = ax + t0, y = ay + t1, z = az + t2, iz = 1.0 / z;
+                const double ru = fu * x * iz + uc - p.u, rv = fv * y * iz + vc - p.v;
+                // d(u, v)/d(x, y, z)
+                const double ux = fu * iz, uz = -fu * x * iz * iz, vy = fv * iz, vz = -fv * y * iz * iz;
+                // columns: dw (x' = x + dw x a: dx/dw = (0, az, -ay), dy/dw = (-az, 0, ax), dz/dw = (ay, -ax, 0)), dt
+                double ju[6], jv[6];
+                ju[0] = uz * ay;            ju[1] = ux * az - uz * ax;  ju[2] = -ux * ay;
+                jv[0] = -vy * az + vz * ay; jv[1] = -vz * ax;           jv[2] = vy * ax;
+                ju[3] = ux; ju[4] = 0.0; ju[5] = uz;
+                jv[3] = 0.0; jv[4] = vy; jv[5] = vz;
+                int k = 0;
+                for (int r = 0; r < 6; ++r)
+                    for (int c = r; c < 6; ++c) a[k++] += ju[r] * ju[c] + jv[r] * jv[c];
+                for (int r = 0; r < 6; ++r) a[21 + r] += ju[r] * ru + jv[r] * rv;
+                a[27] += ru * ru + rv * rv;
+            },
+            s);
+        const double cost = s[27];
+        bool accepted = true;
+        if (prev_cost >= 0.0 && !(cost <= prev_cost)) {
+            // worse (or not finite): back to the last accepted pose, more damping
+            accepted = false;
+            lambda *= 10.0;
+            for (int i = 0; i < 9; ++i) R[i] = Rp[i];
+            for (int i = 0; i < 3; ++i) t[i] = tp[i];
+        } else {
+            if (prev_cost >= 0.0) lambda = lambda * 0.1 > 1e-12 ? lambda * 0.1 : 1e-12;
+            prev_cost = cost;
+            for (int i = 0; i < 9; ++i) Rp[i] = R[i];
+            for (int i = 0; i < 3; ++i) tp[i] = t[i];
+            for (int i = 0; i < 21; ++i) JtJp[i] = s[i];
+            for (int i = 0; i < 6; ++i) Jtrp[i] = s[21 + i];
+        }
+        // (J^T J + lambda diag) d = -J^T r by Cholesky
+        double A[36], b[6], d[6];
+        {
+            int k = 0;
+            for (int r = 0; r < 6; ++r)
+                for (int c = r; c < 6; ++c) { A[r * 6 + c] = A[c * 6 + r] = JtJp[k++]; }
+            for (int r = 0; r < 6; ++r) { A[r * 6 + r] *= 1.0 + lambda; b[r] = -Jtrp[r]; }
+        }
+        bool spd = true;
+        for (int c = 0; c < 6 && spd; ++c) {
+            double diag = A[c * 6 + c];
+            for (int k = 0; k < c; ++k) diag -= A[c * 6 + k] * A[c * 6 + k];
+            if (!(diag > 0.0)) { spd = false; break; }
+            const double l = sqrt(diag);
+            A[c * 6 + c] = l;
+            for (int r = c + 1; r < 6; ++r) {
+                double v = A[r * 6 + c];
+                for (int k = 0; k < c; ++k) v -= A[r * 6 + k] * A[c * 6 + k];
+                A[r * 6 + c] = v / l;
+            }
+        }
+        if (!spd) break;
+        for (int r = 0; r < 6; ++r) {
+            double v = b[r];
+            for (int k = 0; k < r; ++k) v -= A[r * 6 + k] * d[k];
+            d[r] = v / A[r * 6 + r];
+        }
+        for (int r = 5; r >= 0; --r) {
+            double v = d[r];
+            for (int k = r + 1; k < 6; ++k) v -= A[k * 6 + r] * d[k];
+            d[r] = v / A[r * 6 + r];
+        }
+        // R <- exp([dw]x) R, t <- t + dt (from the last accepted pose)
+        double dR[9], Rn[9];
+        rodrigues_to_matrix(d, dR);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) Rn[r * 3 + c] = dR[r * 3] * Rp[c] + dR[r * 3 + 1] * Rp[3 + c] + dR[r * 3 + 2] * Rp[6 + c];
+        for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+        for (int i = 0; i < 3; ++i) t[i] = tp[i] + d[3 + i];
+        double step = 0.0, scale = 1.0;
+        for (int i = 0; i < 3; ++i) {
+            step = fmax(step, fabs(d[i]));
+            scale = fmax(scale, fabs(tp[i]));
+        }
+        for (int i = 3; i < 6; ++i) step = fmax(step, fabs(d[i]) / scale);
+        if (accepted && step < 1e-13) break;
+    }
+    // the loop may end on a trial pose: keep the last accepted one unless the trial is at least as good
+    {
+        double s[1];
+        const double r0 = R[0], r1 = R[1], r2 = R[2], r3 = R[3], r4 = R[4], r5 = R[5], r6 = R[6], r7 = R[7], r8 = R[8];
+        const double t0 = t[0], t1 = t[1], t2 = t[2];
+        const double fu = cam.fu, fv = cam.fv, uc = cam.uc, vc = cam.vc;
+        ex.template sum<1>(
+            [=](const Point& p, double (&a)[1]) {
+                const double x = r0 * p.X + r1 * p.Y + r2 * p.Z + t0, y = r3 * p.X + r4 * p.Y + r5 * p.Z + t1,
+                             z = r6 * p.X + r7 * p.Y + r8 * p.Z + t2;
+                const double ru = fu * x / z + uc - p.u, rv = fv * y / z + vc - p.v;
+                a[0] += ru * ru + rv * rv;
+            },
+            s);
+        if (!(s[0] <= prev_cost)) {
+            for (int i = 0; i < 9; ++i) R[i] = Rp[i];
+            for (int i = 0; i < 3; ++i) t[i] = tp[i];
+        } else {
+            prev_cost = s[0];
+        }
+    }
+    return sqrt(prev_cost / (n > 0 ? n : 1.0));
+}
+
 }  // namespace pnp
 }  // namespace dunk

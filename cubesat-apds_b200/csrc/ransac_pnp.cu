@@ -280,6 +280,9 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
     BlockExec ex{obj, img, mask, n, sh.n_inliers, sh.first_inlier, cam, &sh};
     double R[9], t[3], r[3];
     epnp_solve(ex, cam, R, t);
+    // SOLVEPNP_ITERATIVE: same RANSAC stage, then the Levenberg-Marquardt minimum over the inliers (solvepnp.cpp calls
+    // solvePnP(inliers, flags); with exactly model_points points OpenCV returns the kernel's pose unrefined)
+    if (method == DUNK_PNP_ITERATIVE && n > mp) pnp_refine(ex, cam, R, t);
     rodrigues_to_vector(R, r);
     bool ok = true;
     for (int i = 0; i < 3; ++i) ok = ok && isfinite(r[i]) && isfinite(t[i]);
@@ -331,8 +334,9 @@ int dunk_pnp_ransac_batch(dunk_ctx* ctx, const double* obj, const double* img, c
     DUNK_REQUIRE(ctx && offsets && K && rvecs && tvecs && info && n_problems >= 0, DUNK_ERR_BAD_ARG,
                  "dunk_pnp_ransac_batch: NULL argument");
     if (n_problems == 0) return DUNK_OK;
-    DUNK_REQUIRE(method == DUNK_PNP_EPNP || method == DUNK_PNP_P3P, DUNK_ERR_BAD_ARG,
-                 "dunk_pnp_ransac: method %d not implemented (SOLVEPNP_EPNP = 1, the reference's default, and SOLVEPNP_P3P = 2 are)",
+    DUNK_REQUIRE(method == DUNK_PNP_EPNP || method == DUNK_PNP_P3P || method == DUNK_PNP_ITERATIVE, DUNK_ERR_BAD_ARG,
+                 "dunk_pnp_ransac: method %d not implemented (SOLVEPNP_ITERATIVE = 0, SOLVEPNP_EPNP = 1, the reference's default, "
+                 "and SOLVEPNP_P3P = 2 are)",
                  method);
     const int total = offsets[n_problems];
     for (int b = 0; b < n_problems; ++b) {

@@ -365,6 +365,45 @@ def solve_pnp_ransac(obj, img, K, iters=100, thr=8.0, confidence=0.99):
     return True, sol[0], sol[1], np.nonzero(mask)[0].astype(np.int32)
 
 
+def refine_pose_lm(obj, img, K, rvec, tvec, max_iters=100):
+    """SOLVEPNP_ITERATIVE's answer: the minimum of the squared reprojection error (calib3d solvePnP ->
+    Levenberg-Marquardt over (rvec, tvec); cv2 4.13.0 agrees with the minimiser to ~1e-8).  Gauss-Newton with a
+    local rotation update R <- exp([dw]x) R; stops when the step is below 1e-14."""
+    obj = np.asarray(obj, np.float64).reshape(-1, 3)
+    img = np.asarray(img, np.float64).reshape(-1, 2)
+    K = np.asarray(K, np.float64).reshape(3, 3)
+    fu, fv, uc, vc = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    R, t = rodrigues_to_matrix(np.asarray(rvec, np.float64)), np.asarray(tvec, np.float64).copy()
+    for _ in range(max_iters):
+        a = obj @ R.T
+        x, y, z = (a + t).T
+        ru, rv = fu * x / z + uc - img[:, 0], fv * y / z + vc - img[:, 1]
+        ux, uz, vy, vz = fu / z, -fu * x / z ** 2, fv / z, -fv * y / z ** 2
+        zero = np.zeros_like(z)
+        ju = np.stack([uz * a[:, 1], ux * a[:, 2] - uz * a[:, 0], -ux * a[:, 1], ux, zero, uz], 1)
+        jv = np.stack([-vy * a[:, 2] + vz * a[:, 1], -vz * a[:, 0], vy * a[:, 0], zero, vy, vz], 1)
+        J = np.concatenate([ju, jv])
+        d = np.linalg.solve(J.T @ J, -J.T @ np.concatenate([ru, rv]))
+        R = rodrigues_to_matrix(d[:3]) @ R
+        t = t + d[3:]
+        if np.abs(d[:3]).max() < 1e-14 and np.abs(d[3:]).max() < 1e-14 * max(1.0, np.abs(t).max()):
+            break
+    return rodrigues_to_vector(R), t
+
+
+def solve_pnp_ransac_iterative(obj, img, K, iters=100, thr=8.0, confidence=0.99):
+    """cv::solvePnPRansac(..., flags=SOLVEPNP_ITERATIVE): the RANSAC stage is the EPnP one (5-point samples); when
+    there are more points than the minimal sample the final pose over the inliers is the LM minimum."""
+    found, rv, tv, inl = solve_pnp_ransac(obj, img, K, iters, thr, confidence)
+    n = np.asarray(obj).reshape(-1, 3).shape[0]
+    if not found or n <= 5:
+        return found, rv, tv, inl
+    obj32 = np.asarray(obj, np.float64).reshape(-1, 3).astype(np.float32).astype(np.float64)
+    img32 = np.asarray(img, np.float64).reshape(-1, 2).astype(np.float32).astype(np.float64)
+    rv, tv = refine_pose_lm(obj32[inl], img32[inl], K, rv, tv)
+    return True, rv, tv, inl
+
+
 # ----------------------------------------------------------------------------- P3P (SOLVEPNP_P3P)
 # OpenCV's p3p.cpp (Gao et al.) solves a quartic for the ratio of two depths and aligns the three
 # camera-frame points with Horn's quaternion method.  The restatement below uses the same unknowns

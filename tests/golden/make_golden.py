@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ by running the reference's OpenCV entry
 points (through cv2, the same C++ library the `opencv` crate binds) with the reference's exact
-arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|lmeds|akaze|pnp|warp|l2|all]
+arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|lmeds|akaze|pnp|pnp_iter|warp|l2|all]
 The OpenCV version is recorded in every file (parity is defined against that version)."""
 import os
 import sys
@@ -83,6 +83,23 @@ def make_ransac():
         out[f"c{i}_H"], out[f"c{i}_mask"] = H, mask.ravel().astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, "ransac_golden.npz"), **out)
     print("ransac_golden.npz:", len(cases), "cases")
+
+
+def make_pnp_iter():
+    """cv2.solvePnPRansac(..., flags=SOLVEPNP_ITERATIVE) on the cases of pnp_golden.npz (same inputs, regenerated
+    by pnp_case): the RANSAC stage is the EPnP one, the final pose is the Levenberg-Marquardt minimum of the
+    reprojection error over the inliers."""
+    out = {"opencv_version": np.array(cv2.__version__), "n_cases": np.array(len(PNP_CASES))}
+    for i, (n, of, noise, iters, thr, conf, relief) in enumerate(PNP_CASES):
+        obj, img = pnp_case(i, n, of, noise, relief)
+        ok, r, t, inl = cv2.solvePnPRansac(obj, img, PNP_K, np.zeros((4, 1)), None, None, False, iters, thr, conf, None,
+                                           cv2.SOLVEPNP_ITERATIVE)
+        out[f"c{i}_checksum"] = np.array([obj.sum(), img.sum()])
+        out[f"c{i}_found"] = np.array(bool(ok))
+        out[f"c{i}_rvec"], out[f"c{i}_tvec"] = r.ravel(), t.ravel()
+        out[f"c{i}_inliers"] = np.zeros(0, np.int32) if inl is None else inl.ravel().astype(np.int32)
+        print(f"pnp iterative case {i}: n={n} found={ok} inliers={len(out[f'c{i}_inliers'])}")
+    np.savez_compressed(os.path.join(HERE, "pnp_iter_golden.npz"), **out)
 
 
 LMEDS_CASES = [(50, 0.2, 0.5), (200, 0.4, 0.5), (1000, 0.3, 1.0), (2000, 0.4, 2.0), (100, 0.0, 0.1), (300, 0.45, 1.5),
@@ -280,6 +297,8 @@ if __name__ == "__main__":
         make_akaze()
     if what in ("pnp", "all") and "make_pnp" in globals():
         make_pnp()
+    if what in ("pnp_iter", "all") and "make_pnp_iter" in globals():
+        make_pnp_iter()
     if what in ("warp", "all") and "make_warp" in globals():
         make_warp()
     if what in ("l2", "all") and "make_l2" in globals():

@@ -31,6 +31,17 @@ double hc_epnp(const float* obj, const float* img, const int* idx, int n, const 
     return e;
 }
 
+double hc_refine(const float* obj, const float* img, const int* idx, int n, const double* K, double* rvec, double* tvec) {
+    Camera cam{K[0], K[4], K[2], K[5]};
+    SerialExec ex{obj, img, idx, n, cam, false};
+    double R[9], t[3] = {tvec[0], tvec[1], tvec[2]};
+    rodrigues_to_matrix(rvec, R);
+    const double e = pnp_refine(ex, cam, R, t);
+    rodrigues_to_vector(R, rvec);
+    for (int i = 0; i < 3; ++i) tvec[i] = t[i];
+    return e;
+}
+
 int hc_p3p(const float* obj, const float* img, const int* idx, const double* K, int f32n, double* rvec, double* tvec) {
     Camera cam{K[0], K[4], K[2], K[5]};
     double R[9], t[3];

@@ -91,3 +91,21 @@ def test_four_points_run_p3p_once():
         assert abs(e_ours[3] - e_cv[3]) <= 0.05 * max(e_cv[3], 1e-3)
         same += np.abs(np.r_[r, t] - G[f"q{j}_rt"]).max() < 1e-6
     assert same >= int(G["n_four"]) - 2
+
+
+# ---- SOLVEPNP_ITERATIVE ------------------------------------------------------------------------------------
+GI = np.load(os.path.join(os.path.dirname(__file__), "golden", "pnp_iter_golden.npz"))
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_solve_pnp_ransac_iterative_matches_cv2(i):
+    """same RANSAC stage (identical inlier lists), final pose = minimum of the reprojection error over the inliers;
+    cv2's own LM stops within ~1e-8 of it"""
+    assert np.allclose([G[f"c{i}_obj"].sum(), G[f"c{i}_img"].sum()], GI[f"c{i}_checksum"])
+    iters, thr, conf = G[f"c{i}_params"]
+    found, r, t, inl = po.solve_pnp_ransac_iterative(G[f"c{i}_obj"], G[f"c{i}_img"], K, int(iters), float(thr), float(conf))
+    assert found == bool(GI[f"c{i}_found"])
+    assert np.array_equal(inl, GI[f"c{i}_inliers"])
+    if found:
+        assert np.abs(r - GI[f"c{i}_rvec"]).max() < 1e-6
+        assert np.abs(t - GI[f"c{i}_tvec"]).max() < 1e-6 * max(1.0, np.abs(GI[f"c{i}_tvec"]).max())

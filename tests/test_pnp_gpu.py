@@ -69,7 +69,28 @@ def test_reference_test_too_few_points(dunk, ctx):
 def test_unsupported_methods_fail_loudly(dunk, ctx):
     hg = dunk.homographier
     with pytest.raises(hg.MatError):
-        hg.pnp_solver_ransac((G["c0_obj"], G["c0_img"]), K, 100, 8.0, 0.99, None, hg.SolvePnPMethod.SOLVEPNP_ITERATIVE, ctx)
+        hg.pnp_solver_ransac((G["c0_obj"], G["c0_img"]), K, 100, 8.0, 0.99, None, 8, ctx)   # SOLVEPNP_SQPNP
+
+
+GI = np.load(os.path.join(os.path.dirname(__file__), "golden", "pnp_iter_golden.npz"))
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_pnp_ransac_iterative_vs_cv2_golden(dunk, ctx, i):
+    """SOLVEPNP_ITERATIVE: EPnP RANSAC stage (same inliers), final pose = LM minimum over the inliers"""
+    hg = dunk.homographier
+    assert np.allclose([G[f"c{i}_obj"].sum(), G[f"c{i}_img"].sum()], GI[f"c{i}_checksum"])
+    iters, thr, conf = G[f"c{i}_params"]
+    sol = hg.pnp_solver_ransac((G[f"c{i}_obj"], G[f"c{i}_img"]), K, int(iters), float(thr), float(conf), None,
+                               hg.SolvePnPMethod.SOLVEPNP_ITERATIVE, ctx)
+    if not bool(GI[f"c{i}_found"]):
+        assert sol is None
+        return
+    assert sol is not None
+    assert np.array_equal(np.asarray(sol.inliers.mat).ravel(), GI[f"c{i}_inliers"])
+    rv, tv = np.asarray(sol.rvec.mat).ravel(), np.asarray(sol.tvec.mat).ravel()
+    assert np.abs(rv - GI[f"c{i}_rvec"]).max() < 1e-6
+    assert np.abs(tv - GI[f"c{i}_tvec"]).max() < 1e-6 * max(1.0, np.abs(GI[f"c{i}_tvec"]).max())
 
 
 @pytest.mark.parametrize("i", range(N))

@@ -119,3 +119,23 @@ def test_p3p_host_math_matches_oracle(hc):
             total += 1
             close += np.abs(np.r_[r, t] - np.r_[sol[0], sol[1]]).max() < 1e-6
     assert total > 150 and close >= 0.95 * total
+
+
+GI = np.load(os.path.join(HERE, "golden", "pnp_iter_golden.npz"))
+
+
+@pytest.mark.parametrize("i", range(int(G["n_cases"])))
+def test_iterative_refinement_on_golden_inliers(hc, i):
+    """pnp_refine (the code the GPU runs after the final EPnP when the method is SOLVEPNP_ITERATIVE), compiled for the
+    host: from the EPnP pose of cv2's inlier set to cv2's ITERATIVE pose"""
+    if not bool(GI[f"c{i}_found"]) or len(G[f"c{i}_obj"]) <= 5:
+        pytest.skip("no pose / minimal point set (OpenCV returns the kernel's pose unrefined)")
+    obj32 = np.ascontiguousarray(G[f"c{i}_obj"], np.float32)
+    img32 = np.ascontiguousarray(G[f"c{i}_img"], np.float32)
+    idx = np.ascontiguousarray(GI[f"c{i}_inliers"], np.int32)
+    r, t = host_epnp(hc, obj32, img32, idx, False)
+    hc.hc_refine.restype = C.c_double
+    rms = hc.hc_refine(ptr(obj32), ptr(img32), ptr(idx), len(idx), ptr(np.ascontiguousarray(K)), ptr(r), ptr(t))
+    assert np.isfinite(rms)
+    assert np.abs(r - GI[f"c{i}_rvec"]).max() < 1e-6
+    assert np.abs(t - GI[f"c{i}_tvec"]).max() < 1e-6 * max(1.0, np.abs(GI[f"c{i}_tvec"]).max())
