@@ -8,7 +8,8 @@ Sub-modules mirror the reference crates on the path:
 Everything numeric happens in libdunk_b200.so (csrc/, C ABI in include/dunk_b200.h).
 """
 from . import _lib
-from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, REGISTRATION_DTYPE, TOP2_DTYPE, Context, DunkError, default_context)
+from ._lib import (DMATCH_DTYPE, KEYPOINT_DTYPE, POSE_DTYPE, REGISTRATION_DTYPE, TOP2_DTYPE, Context, DeviceBuffer, DunkError,
+                   PinnedBuffer, default_context)
 from . import feature_extraction
 from . import _extract
 from . import feature_database
@@ -16,4 +17,4 @@ from . import homographier
 from . import image_extractor
 
 __all__ = ["_lib", "Context", "DunkError", "default_context", "feature_extraction", "feature_database", "homographier", "image_extractor",
-           "DMATCH_DTYPE", "KEYPOINT_DTYPE", "TOP2_DTYPE"]
+           "DMATCH_DTYPE", "KEYPOINT_DTYPE", "TOP2_DTYPE", "POSE_DTYPE", "REGISTRATION_DTYPE", "DeviceBuffer", "PinnedBuffer"]

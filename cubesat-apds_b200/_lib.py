@@ -50,6 +50,19 @@ class RowFilter(C.Structure):
 
 
 TOP2_DTYPE = np.dtype([("d1", "<u4"), ("i1", "<u4"), ("d2", "<u4"), ("i2", "<u4")])
+POSE_DTYPE = np.dtype([("rvec", "<f8", (3,)), ("tvec", "<f8", (3,)), ("found", "<i4"), ("inliers", "<i4"),
+                       ("ransac_iters", "<i4"), ("hypotheses", "<i4")])
+assert POSE_DTYPE.itemsize == 64
+SHARD_ID_BYTES = 128
+
+
+class PoseConfig(C.Structure):
+    """DunkPoseConfig (include/dunk_b200.h): the pose stage behind the homography — get_world_coordinates
+    (feature_database/src/elevationdb.rs:64-104) + pnp_solver_ransac (homographier/src/homographier/mod.rs:320-369)"""
+    _fields_ = [("elevation", C.c_void_p), ("K", C.c_double * 9), ("origin", C.c_double * 3), ("method", C.c_int32),
+                ("iters", C.c_int32), ("thr", C.c_float), ("confidence", C.c_double)]
+
+
 assert REGISTRATION_DTYPE.itemsize == 96 and KEYPOINT_DTYPE.itemsize == 28 and DMATCH_DTYPE.itemsize == 16 and TOP2_DTYPE.itemsize == 16
 
 
@@ -152,6 +165,29 @@ SIGNATURES = {
     "dunk_pnp_ransac": (_i, [_vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _i, _pi, _pi]),
     "dunk_pnp_ransac_batch": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _vp]),
     "dunk_pnp_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _d, _vp, _vp]),
+    "dunk_register_frames_pose": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _f, _d, _i, _vp, _vp, _vp]),
+    "dunk_register_frames_pose_dev": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, C.c_size_t, _f, _d, _i, _vp, _vp, C.c_size_t, _vp, _vp]),
+    "dunk_shard_unique_id": (_i, [_vp]),
+    "dunk_shard_group_create": (_i, [_vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "dunk_shard_group_destroy": (None, [_vp]),
+    "dunk_shard_group_rank": (_i, [_vp]),
+    "dunk_shard_group_world": (_i, [_vp]),
+    "dunk_nccl_version": (_i, []),
+    "dunk_shard_group_balance": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "dunk_shard_group_total_rows": (_i64, [_vp]),
+    "dunk_shard_group_base": (_i64, [_vp, _i]),
+    "dunk_db_match_sharded": (_i, [_vp, _vp, _vp, _i, _u32, _f, _vp, _i, _pi]),
+    "dunk_db_match_sharded_dev": (_i, [_vp, _vp, _i, _vp, _i, _u32, _f, _vp, _vp, _vp]),
+    "dunk_register_sharded_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
+    "dunk_register_frames_sharded_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, C.c_size_t, _f, _d, _i, _vp, _vp, C.c_size_t,
+                                              _vp, _vp]),
+    "dunk_memcpy_h2d": (_i, [_vp, _i, _vp, _vp, C.c_size_t]),
+    "dunk_memcpy_d2h": (_i, [_vp, _i, _vp, _vp, C.c_size_t]),
+    "dunk_dev_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "dunk_dev_free": (_i, [_vp, _vp]),
+    "dunk_host_alloc": (_i, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "dunk_host_free": (_i, [_vp, _vp]),
+    "dunk_db_desc_bytes": (_i, [_vp]),
 }
 
 
@@ -246,6 +282,59 @@ class Context:
         ms = C.c_float()
         check(load().dunk_timer_end(self.handle, slot, C.byref(ms)))
         return float(ms.value)
+
+
+class DeviceBuffer:
+    """`nbytes` of HBM owned by the caller (dunk_dev_alloc): what the `_dev` entry points take."""
+
+    def __init__(self, ctx: Context, nbytes: int):
+        p = C.c_void_p()
+        check(load().dunk_dev_alloc(ctx.handle, int(nbytes), C.byref(p)))
+        self.ctx, self.ptr, self.nbytes = ctx, int(p.value), int(nbytes)
+
+    def free(self):
+        if getattr(self, "ptr", 0) and self.ctx._h is not None:
+            load().dunk_dev_free(self.ctx.handle, C.c_void_p(self.ptr))
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def upload(self, slot: int, host: np.ndarray, offset: int = 0):
+        """async H2D on the slot's stream (truly asynchronous only from a PinnedBuffer's array)"""
+        check(load().dunk_memcpy_h2d(self.ctx.handle, slot, C.c_void_p(self.ptr + offset), host.ctypes.data_as(C.c_void_p),
+                                     host.nbytes))
+
+    def download(self, slot: int, host: np.ndarray, offset: int = 0):
+        check(load().dunk_memcpy_d2h(self.ctx.handle, slot, host.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr + offset),
+                                     host.nbytes))
+
+
+class PinnedBuffer:
+    """page-locked host memory (dunk_host_alloc) exposed as a numpy array"""
+
+    def __init__(self, ctx: Context, shape, dtype=np.uint8):
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        check(load().dunk_host_alloc(ctx.handle, n, C.byref(p)))
+        self.ctx, self.ptr = ctx, int(p.value)
+        self.array = np.frombuffer((C.c_uint8 * max(n, 1)).from_address(self.ptr), dtype=np.uint8, count=n).view(dt).reshape(shape)
+
+    def free(self):
+        if getattr(self, "ptr", 0) and self.ctx._h is not None:
+            self.array = None
+            load().dunk_host_free(self.ctx.handle, C.c_void_p(self.ptr))
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 _default_ctx = None

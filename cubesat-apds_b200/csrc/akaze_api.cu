@@ -84,6 +84,42 @@ int akaze_run(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeW
     return akaze_describe(ctx, st, lt, ws, frames);
 }
 
+namespace {
+// exclusive scan of the per-frame keypoint counts (frames <= 64 per sub-batch) + the largest raw-extrema count
+__global__ void k_out_offsets(const int* __restrict__ counts, const int* __restrict__ cand_count, int frames, int* __restrict__ off) {
+    if (threadIdx.x == 0) {
+        int acc = 0, cmax = 0;
+        for (int f = 0; f < frames; ++f) {
+            off[f] = acc;
+            acc += counts[f];
+            cmax = max(cmax, cand_count[f]);
+        }
+        off[frames] = acc;
+        off[frames + 1] = cmax;
+    }
+}
+// every frame's keypoints and 61-byte descriptor rows, packed back to back in frame order
+__global__ void __launch_bounds__(256)
+k_pack_outputs(const DunkKeyPoint* __restrict__ kps, const uint4* __restrict__ desc64, int kp_cap, const int* __restrict__ counts,
+               const int* __restrict__ off, DunkKeyPoint* __restrict__ out_kps, uint8_t* __restrict__ out_desc) {
+    const int f = blockIdx.y, n = counts[f];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // byte-quad index inside the frame's descriptor block
+    const size_t base = (size_t)off[f];
+    if (i < n) out_kps[base + i] = kps[(size_t)f * kp_cap + i];
+    const unsigned char* src = (const unsigned char*)(desc64 + (size_t)f * kp_cap * 4);
+    for (int k = i; k < n * 61; k += gridDim.x * blockDim.x) out_desc[base * 61 + k] = src[(size_t)(k / 61) * 64 + k % 61];
+}
+}  // namespace
+
+static int launch_pack_outputs(dunk_ctx* ctx, cudaStream_t st, const AkazeWorkspace& ws, int frames, int* d_off, DunkKeyPoint* d_kps,
+                               uint8_t* d_desc61) {
+    k_out_offsets<<<1, 32, 0, st>>>(ws.kp_count, ws.cand_count, frames, d_off);
+    DUNK_KERNEL_CHECK(ctx);
+    k_pack_outputs<<<dim3(div_up(ws.kp_cap, 256), frames), 256, 0, st>>>(ws.kps, ws.desc64, ws.kp_cap, ws.kp_count, d_off, d_kps, d_desc61);
+    DUNK_KERNEL_CHECK(ctx);
+    return DUNK_OK;
+}
+
 }  // namespace dunk
 
 using namespace dunk;
@@ -109,49 +145,109 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
     DUNK_REQUIRE(frame_stride_bytes >= img_bytes, DUNK_ERR_BAD_ARG, "dunk_akaze_extract: frame stride < frame bytes");
 
     const LevelTable lt = make_level_table(cols, rows);
-    const int cand_cap = default_cand_cap(cols, rows);
-    const int kp_cap = cand_cap;
+    int cand_cap = default_cand_cap(cols, rows);
     SlotGuard g(ctx);
     cudaStream_t st = g.stream();
-    // sub-batch so the workspace stays bounded (~100 MB per 1024^2 frame)
     size_t free_b = 0, total_b = 0;
     DUNK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t per_frame = akaze_workspace_bytes(lt, 1, cand_cap, kp_cap) + frame_stride_bytes + 4096;
-    size_t budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)8 << 30);
-    int sub = (int)std::max<size_t>(1, std::min<size_t>(n_frames, budget / per_frame));
-    sub = std::min(sub, 64);
-    const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cand_cap, kp_cap);
-    const size_t need = al(ws_bytes) + al((size_t)sub * frame_stride_bytes) + al((size_t)sub * kp_cap * 61);
-    void* scratch = ctx->dev_scratch(g.s, need);
-    if (!scratch) return DUNK_ERR_NO_MEM;
-    AkazeWorkspace ws;
-    akaze_carve_workspace(scratch, lt, sub, cand_cap, kp_cap, &ws);
-    unsigned char* d_img = (unsigned char*)scratch + al(ws_bytes);
-    uint8_t* d_desc61 = d_img + al((size_t)sub * frame_stride_bytes);
-    std::vector<int> h_counts(sub), h_cand(sub);
-    for (int f0 = 0; f0 < n_frames; f0 += sub) {
-        const int nf = std::min(sub, n_frames - f0);
-        DUNK_CUDA(cudaMemcpyAsync(d_img, images + (size_t)f0 * frame_stride_bytes, (size_t)nf * frame_stride_bytes,
-                                  cudaMemcpyHostToDevice, st));
-        int rc = akaze_run(ctx, st, lt, ws, d_img, frame_stride_bytes, row_stride_bytes, channels, nf, max_points);
-        if (rc) return rc;
-        DUNK_CUDA(cudaMemcpyAsync(h_counts.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-        DUNK_CUDA(cudaMemcpyAsync(h_cand.data(), ws.cand_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
-        DUNK_CUDA(cudaStreamSynchronize(st));
-        for (int f = 0; f < nf; ++f) {
-            DUNK_REQUIRE(h_cand[f] <= cand_cap, DUNK_ERR_NO_MEM,
-                         "dunk_akaze_extract: frame %d produced %d raw extrema, capacity %d", f0 + f, h_cand[f], cand_cap);
-            const int n = h_counts[f];
-            DUNK_REQUIRE(n <= cap_per_frame, DUNK_ERR_NO_MEM,
-                         "dunk_akaze_extract: frame %d has %d keypoints, output capacity %d", f0 + f, n, cap_per_frame);
-            counts[f0 + f] = n;
-            if (n == 0) continue;
-            rc = launch_unpad_rows(ctx, st, ws.desc64 + (size_t)f * kp_cap * 4, n, 61, d_desc61 + (size_t)f * kp_cap * 61);
+    const size_t budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)8 << 30);
+    cudaEvent_t done[2] = {g.slot().ev0, g.slot().ev1};
+    int f0 = 0;
+    // The raw-candidate capacity (w*h/32 by default) is exceeded only by pathological textures (random 4x4 blocks
+    // reach w*h/29); k_extrema keeps counting past the capacity, so on overflow the sub-batch is simply re-run
+    // with a workspace carved for the observed maximum — the result never depends on which candidates were dropped.
+    while (f0 < n_frames) {
+        const int kp_cap = cand_cap;
+        // sub-batch so the workspace stays bounded (~100 MB per 1024^2 frame)
+        const size_t per_frame = akaze_workspace_bytes(lt, 1, cand_cap, kp_cap) + 2 * frame_stride_bytes + 4096;
+        int sub = (int)std::max<size_t>(1, std::min<size_t>(n_frames - f0, budget / per_frame));
+        sub = std::min(sub, 64);
+        const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cand_cap, kp_cap);
+        // Two-deep software pipeline over sub-batches (one stream): while the device works on sub-batch i the calling
+        // thread stages sub-batch i + 1 into the other pinned half (pageable caller memory would otherwise go through
+        // the driver's blocking staged copy at ~11 GB/s) and unpacks the results of sub-batch i - 1.  The packed
+        // outputs of a sub-batch leave in ONE D2H copy each (keypoints, descriptors).
+        const size_t in_half = al((size_t)sub * frame_stride_bytes);
+        const size_t out_rows = (size_t)sub * kp_cap;
+        const size_t out_half = al(out_rows * 61) + al(out_rows * sizeof(DunkKeyPoint)) + al((size_t)(sub + 2) * 4);
+        void* scratch = ctx->dev_scratch(g.s, al(ws_bytes) + 2 * in_half + 2 * out_half);
+        if (!scratch) return DUNK_ERR_NO_MEM;
+        // pinned: two input halves, two offset blocks, one output block sized for the typical density (grown on demand)
+        const size_t pin_off = 2 * in_half, pin_out = pin_off + 2 * al((size_t)(sub + 2) * 4);
+        size_t pin_out_cap = std::max<size_t>((size_t)sub * 4096 * 89, 1 << 20);
+        unsigned char* pin = (unsigned char*)ctx->pin_scratch(g.s, pin_out + pin_out_cap);
+        if (!pin) return DUNK_ERR_NO_MEM;
+        AkazeWorkspace ws;
+        akaze_carve_workspace(scratch, lt, sub, cand_cap, kp_cap, &ws);
+        unsigned char* d_in = (unsigned char*)scratch + al(ws_bytes);
+        unsigned char* d_out = d_in + 2 * in_half;
+        auto d_desc61 = [&](int h) { return (uint8_t*)(d_out + h * out_half); };
+        auto d_kps = [&](int h) { return (DunkKeyPoint*)(d_out + h * out_half + al(out_rows * 61)); };
+        auto d_off = [&](int h) { return (int*)(d_out + h * out_half + al(out_rows * 61) + al(out_rows * sizeof(DunkKeyPoint))); };
+        auto h_off = [&](int h) { return (int*)(pin + pin_off + h * al((size_t)(sub + 2) * 4)); };
+        bool overflow = false;
+        // stage sub-batch starting at frame `fs` into half h (asynchronous after the host memcpy)
+        auto stage = [&](int fs, int h) -> int {
+            const int nf = std::min(sub, n_frames - fs);
+            const size_t in_bytes = (size_t)nf * frame_stride_bytes;
+            par_memcpy(pin + h * in_half, images + (size_t)fs * frame_stride_bytes, in_bytes);
+            DUNK_CUDA(cudaMemcpyAsync(d_in + h * in_half, pin + h * in_half, in_bytes, cudaMemcpyHostToDevice, st));
+            int rc = akaze_run(ctx, st, lt, ws, d_in + h * in_half, frame_stride_bytes, row_stride_bytes, channels, nf, max_points);
             if (rc) return rc;
-            DUNK_CUDA(cudaMemcpyAsync(kps + (size_t)(f0 + f) * cap_per_frame, ws.kps + (size_t)f * kp_cap,
-                                      (size_t)n * sizeof(DunkKeyPoint), cudaMemcpyDeviceToHost, st));
-            DUNK_CUDA(cudaMemcpyAsync(desc + (size_t)(f0 + f) * cap_per_frame * 61, d_desc61 + (size_t)f * kp_cap * 61,
-                                      (size_t)n * 61, cudaMemcpyDeviceToHost, st));
+            if ((rc = launch_pack_outputs(ctx, st, ws, nf, d_off(h), d_kps(h), d_desc61(h)))) return rc;
+            DUNK_CUDA(cudaMemcpyAsync(h_off(h), d_off(h), (size_t)(nf + 2) * 4, cudaMemcpyDeviceToHost, st));
+            DUNK_CUDA(cudaEventRecord(done[h], st));
+            return DUNK_OK;
+        };
+        int rc = stage(f0, 0);
+        if (rc) return rc;
+        cudaStream_t st2 = g.slot().stream2;      // output copies run beside the next sub-batch's kernels
+        for (int h = 0; f0 < n_frames && !overflow; h ^= 1) {
+            const int nf = std::min(sub, n_frames - f0);
+            const int next = f0 + nf;
+            // host stages sub-batch i + 1 while the device runs sub-batch i (its pinned half and packed-output half
+            // were released when sub-batch i - 1 was unpacked)
+            if (next < n_frames && (rc = stage(next, h ^ 1))) return rc;
+            DUNK_CUDA(cudaEventSynchronize(done[h]));
+            const int* off = h_off(h);
+            if (off[nf + 1] > cand_cap) {              // re-run from this sub-batch with a larger candidate capacity
+                DUNK_REQUIRE(off[nf + 1] <= (1 << 22), DUNK_ERR_NO_MEM, "dunk_akaze_extract: %d raw extrema in one frame", off[nf + 1]);
+                DUNK_CUDA(cudaStreamSynchronize(st));
+                cand_cap = off[nf + 1] + off[nf + 1] / 4;
+                overflow = true;
+                break;
+            }
+            const int total = off[nf];
+            for (int f = 0; f < nf; ++f) {
+                const int n = off[f + 1] - off[f];
+                DUNK_REQUIRE(n <= cap_per_frame, DUNK_ERR_NO_MEM,
+                             "dunk_akaze_extract: frame %d has %d keypoints, output capacity %d", f0 + f, n, cap_per_frame);
+                counts[f0 + f] = n;
+            }
+            if (total > 0) {
+                if ((size_t)total * 89 > pin_out_cap) {     // denser than typical: grow the pinned block (rare, slow path)
+                    DUNK_CUDA(cudaStreamSynchronize(st));
+                    std::vector<int> keep0(h_off(0), h_off(0) + sub + 2), keep1(h_off(1), h_off(1) + sub + 2);
+                    pin_out_cap = (size_t)total * 89 * 2;
+                    pin = (unsigned char*)ctx->pin_scratch(g.s, pin_out + pin_out_cap);
+                    if (!pin) return DUNK_ERR_NO_MEM;
+                    memcpy(h_off(0), keep0.data(), keep0.size() * 4);
+                    memcpy(h_off(1), keep1.data(), keep1.size() * 4);
+                    off = h_off(h);
+                }
+                DunkKeyPoint* p_kps = (DunkKeyPoint*)(pin + pin_out);
+                uint8_t* p_desc = (uint8_t*)(p_kps + total);
+                DUNK_CUDA(cudaMemcpyAsync(p_kps, d_kps(h), (size_t)total * sizeof(DunkKeyPoint), cudaMemcpyDeviceToHost, st2));
+                DUNK_CUDA(cudaMemcpyAsync(p_desc, d_desc61(h), (size_t)total * 61, cudaMemcpyDeviceToHost, st2));
+                DUNK_CUDA(cudaStreamSynchronize(st2));
+                for (int f = 0; f < nf; ++f) {
+                    const int n = off[f + 1] - off[f];
+                    if (n == 0) continue;
+                    memcpy(kps + (size_t)(f0 + f) * cap_per_frame, p_kps + off[f], (size_t)n * sizeof(DunkKeyPoint));
+                    memcpy(desc + (size_t)(f0 + f) * cap_per_frame * 61, p_desc + (size_t)off[f] * 61, (size_t)n * 61);
+                }
+            }
+            f0 = next;
         }
         DUNK_CUDA(cudaStreamSynchronize(st));
     }

@@ -1355,6 +1355,17 @@ LevelsDev make_levels_dev(const LevelTable& lt) {
     return d;
 }
 
+// per-device shared-memory opt-ins of the tiled kernels (run by dunk_ctx_create on the context's device)
+static int scale_device_init(dunk_ctx*) {
+    DUNK_CUDA(cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFedS * kFedS * 4));
+    DUNK_CUDA(cudaFuncSetAttribute(k_hessian_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DUNK_CUDA(cudaFuncSetAttribute(k_hessian<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DUNK_CUDA(cudaFuncSetAttribute(k_hessian<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    DUNK_CUDA(cudaFuncSetAttribute(k_hessian<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    return DUNK_OK;
+}
+static DeviceInitReg scale_device_init_reg(scale_device_init);
+
 int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeWorkspace& ws,
                             const unsigned char* images, size_t image_stride_bytes, int row_stride, int channels,
                             int frames) {
@@ -1365,15 +1376,6 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
     Gauss5 g5;
     gaussian_kernel(9, 1.6, g9.k);
     gaussian_kernel(5, 1.0, g5.k);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kFedS * kFedS * 4);
-        cudaFuncSetAttribute(k_hessian_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(k_hessian<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(k_hessian<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(k_hessian<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
-    }
     // level 0
     {
         const dim3 grid(div_up(W, kTW), div_up(H, kTH), frames);

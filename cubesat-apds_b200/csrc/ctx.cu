@@ -1,7 +1,10 @@
 // Context / slot pool / error string / timers.
 #include "ctx.h"
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <thread>
 
 namespace dunk {
 
@@ -15,6 +18,30 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
     g_err = buf;
 }
+
+void par_memcpy(void* dst, const void* src, size_t n) {
+    const size_t kMin = (size_t)8 << 20;
+    const int parts = (int)std::min<size_t>(4, n / kMin);
+    if (parts <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t chunk = ((n / parts) + 4095) & ~size_t(4095);
+    for (int i = 1; i < parts; ++i) {
+        const size_t o = (size_t)i * chunk;
+        if (o >= n) break;
+        th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, std::min(chunk, n - o)); });
+    }
+    memcpy(dst, src, std::min(chunk, n));
+    for (auto& t : th) t.join();
+}
+
+static std::vector<DeviceInitFn>& device_init_hooks() {
+    static std::vector<DeviceInitFn> hooks;
+    return hooks;
+}
+DeviceInitReg::DeviceInitReg(DeviceInitFn fn) { device_init_hooks().push_back(fn); }
 
 }  // namespace dunk
 
@@ -77,6 +104,35 @@ void* dunk_ctx::pin_scratch(int s, size_t bytes) {
     return sl.pin;
 }
 
+int dunk_ctx::upload_pageable(int s, void* dst_dev, const void* src_host, size_t nbytes) {
+    dunk::Slot& sl = slots[s];
+    const size_t half = (size_t)64 << 20;
+    if (nbytes < ((size_t)1 << 20)) {
+        DUNK_CUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, sl.stream));
+        return DUNK_OK;
+    }
+    // a dedicated pinned ring (the slot's pin scratch may hold the caller's other staging data)
+    if (!sl.ring) {
+        if (cudaMallocHost(&sl.ring, 2 * half) != cudaSuccess) {
+            cudaGetLastError();
+            sl.ring = nullptr;
+            dunk::set_error("upload ring allocation failed");
+            return DUNK_ERR_NO_MEM;
+        }
+    }
+    cudaEvent_t ev[2] = {sl.ev0, sl.ev1};
+    int h = 0;
+    for (size_t off = 0; off < nbytes; off += half, h ^= 1) {
+        const size_t n = std::min(half, nbytes - off);
+        // the half's previous copy (of this or an earlier call) must have left it; a never-recorded event is complete
+        DUNK_CUDA(cudaEventSynchronize(ev[h]));
+        dunk::par_memcpy((char*)sl.ring + h * half, (const char*)src_host + off, n);
+        DUNK_CUDA(cudaMemcpyAsync((char*)dst_dev + off, (char*)sl.ring + h * half, n, cudaMemcpyHostToDevice, sl.stream));
+        DUNK_CUDA(cudaEventRecord(ev[h], sl.stream));
+    }
+    return DUNK_OK;
+}
+
 extern "C" {
 
 const char* dunk_last_error(void) { return dunk::g_err.c_str(); }
@@ -111,6 +167,14 @@ int dunk_ctx_create(int device, int n_slots, dunk_ctx** out) {
         DUNK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         DUNK_CUDA(cudaEventCreate(&s.ev0));
         DUNK_CUDA(cudaEventCreate(&s.ev1));
+        DUNK_CUDA(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+    }
+    for (dunk::DeviceInitFn fn : dunk::device_init_hooks()) {
+        const int rc = fn(c);
+        if (rc != DUNK_OK) {
+            dunk_ctx_destroy(c);
+            return rc;
+        }
     }
     *out = c;
     return DUNK_OK;
@@ -123,8 +187,10 @@ void dunk_ctx_destroy(dunk_ctx* c) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.dev) cudaFree(s.dev);
         if (s.pin) cudaFreeHost(s.pin);
+        if (s.ring) cudaFreeHost(s.ring);
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.stream2) { cudaStreamSynchronize(s.stream2); cudaStreamDestroy(s.stream2); }
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     delete c;
@@ -200,6 +266,59 @@ int dunk_profile_end(dunk_ctx* c, char* names, int names_cap, double* ms, int* l
     c->prof.clear();
     snprintf(names, names_cap, "%s", all.c_str());
     return n;
+}
+
+int dunk_memcpy_h2d(dunk_ctx* c, int slot, void* dst_dev, const void* src_host, size_t nbytes) {
+    DUNK_REQUIRE(c && slot >= 0 && slot < (int)c->slots.size(), DUNK_ERR_BAD_ARG, "dunk_memcpy_h2d: bad ctx / slot");
+    if (nbytes == 0) return DUNK_OK;
+    DUNK_REQUIRE(dst_dev && src_host, DUNK_ERR_BAD_ARG, "dunk_memcpy_h2d: NULL pointer");
+    DUNK_CUDA(cudaSetDevice(c->device));
+    DUNK_CUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, c->slots[slot].stream));
+    return DUNK_OK;
+}
+int dunk_memcpy_d2h(dunk_ctx* c, int slot, void* dst_host, const void* src_dev, size_t nbytes) {
+    DUNK_REQUIRE(c && slot >= 0 && slot < (int)c->slots.size(), DUNK_ERR_BAD_ARG, "dunk_memcpy_d2h: bad ctx / slot");
+    if (nbytes == 0) return DUNK_OK;
+    DUNK_REQUIRE(dst_host && src_dev, DUNK_ERR_BAD_ARG, "dunk_memcpy_d2h: NULL pointer");
+    DUNK_CUDA(cudaSetDevice(c->device));
+    DUNK_CUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, c->slots[slot].stream));
+    return DUNK_OK;
+}
+int dunk_dev_alloc(dunk_ctx* c, size_t nbytes, void** out_dev) {
+    DUNK_REQUIRE(c && out_dev, DUNK_ERR_BAD_ARG, "dunk_dev_alloc: NULL argument");
+    *out_dev = nullptr;
+    DUNK_CUDA(cudaSetDevice(c->device));
+    if (cudaMalloc(out_dev, nbytes ? nbytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        dunk::set_error("dunk_dev_alloc: %zu bytes", nbytes);
+        return DUNK_ERR_NO_MEM;
+    }
+    return DUNK_OK;
+}
+int dunk_dev_free(dunk_ctx* c, void* dev) {
+    DUNK_REQUIRE(c, DUNK_ERR_BAD_ARG, "dunk_dev_free: ctx is NULL");
+    if (!dev) return DUNK_OK;
+    DUNK_CUDA(cudaSetDevice(c->device));
+    DUNK_CUDA(cudaFree(dev));
+    return DUNK_OK;
+}
+int dunk_host_alloc(dunk_ctx* c, size_t nbytes, void** out_host) {
+    DUNK_REQUIRE(c && out_host, DUNK_ERR_BAD_ARG, "dunk_host_alloc: NULL argument");
+    *out_host = nullptr;
+    DUNK_CUDA(cudaSetDevice(c->device));
+    if (cudaMallocHost(out_host, nbytes ? nbytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        dunk::set_error("dunk_host_alloc: %zu pinned bytes", nbytes);
+        return DUNK_ERR_NO_MEM;
+    }
+    return DUNK_OK;
+}
+int dunk_host_free(dunk_ctx* c, void* host) {
+    DUNK_REQUIRE(c, DUNK_ERR_BAD_ARG, "dunk_host_free: ctx is NULL");
+    if (!host) return DUNK_OK;
+    DUNK_CUDA(cudaSetDevice(c->device));
+    DUNK_CUDA(cudaFreeHost(host));
+    return DUNK_OK;
 }
 
 int dunk_ctx_reserve_slot(dunk_ctx* c) {

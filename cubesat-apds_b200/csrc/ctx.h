@@ -12,15 +12,19 @@
 namespace dunk {
 
 void set_error(const char* fmt, ...);
+// host memcpy on up to 4 threads (a single core moves ~10 GB/s, less than PCIe 5 or the kernels consume)
+void par_memcpy(void* dst, const void* src, size_t n);
 
 // One stream + growable device / pinned-host scratch.  A host-API call owns exactly one
 // slot for its duration (SURVEY 8b "Threading").
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // copy stream of the pipelined host-buffer calls (ordered against `stream` by events)
     void* dev = nullptr;
     size_t dev_bytes = 0;
     void* pin = nullptr;
     size_t pin_bytes = 0;
+    void* ring = nullptr;             // 2 x 64 MB pinned halves of upload_pageable
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool busy = false;
 };
@@ -44,6 +48,7 @@ struct dunk_ctx {
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<uint64_t> launches{0};
+    int hamming_occ = 1;    // resident CTAs per SM of the Hamming matcher on THIS device (set by its device-init hook)
     bool prof_on = false;
     std::vector<dunk::ProfAccum> prof;
     std::mutex prof_mu;
@@ -53,9 +58,21 @@ struct dunk_ctx {
     // grow-only scratch; returns nullptr (and sets error) on failure
     void* dev_scratch(int s, size_t bytes);
     void* pin_scratch(int s, size_t bytes);
+    // H2D copy of PAGEABLE caller memory at pinned speed: multi-threaded memcpy into two pinned halves of the slot,
+    // each shipped with an async copy while the other half is being filled.  Asynchronous on the slot's stream for
+    // the last chunk only (callers order later work on the same stream).  Uses stream2-free events ev0 / ev1.
+    int upload_pageable(int s, void* dst_dev, const void* src_host, size_t nbytes);
 };
 
 namespace dunk {
+
+// Per-device kernel set-up (cudaFuncSetAttribute opt-ins, occupancy queries).  Function attributes are per
+// DEVICE, so every translation unit registers a hook and dunk_ctx_create runs all of them on the context's
+// device (a process may hold contexts on several GPUs).
+using DeviceInitFn = int (*)(dunk_ctx*);
+struct DeviceInitReg {
+    explicit DeviceInitReg(DeviceInitFn fn);
+};
 
 struct SlotGuard {
     dunk_ctx* ctx;

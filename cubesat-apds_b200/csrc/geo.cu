@@ -11,23 +11,10 @@
 #include <mutex>
 #include "ctx.h"
 #include "gamma_lut.cuh"
-
-struct dunk_elevation {
-    dunk_ctx* ctx = nullptr;
-    double gt_dataset[6];
-    double gt_elev_inv[6];
-    int has_elevation = 0;
-    int x_size = 0, y_size = 0;
-    double* heights = nullptr;   // device, y_size x x_size (the `elevation` table in row-id order)
-};
+#include "geo.cuh"
 
 namespace dunk {
 namespace {
-
-constexpr double kWgs84A = 6378137.0;
-constexpr double kWgs84F = 1.0 / 298.257223563;
-constexpr double kWgs84Es = 2 * kWgs84F - kWgs84F * kWgs84F;
-constexpr double kDegToRad = 0.017453292519943296;
 
 __device__ float g_gamma_thr[256];
 
@@ -84,41 +71,16 @@ __global__ void __launch_bounds__(256) k_swizzle_rb(const uchar4* __restrict__ s
     dst[i] = make_uchar4(v.z, v.y, v.x, v.w);
 }
 
-struct GeoParams {
-    double gt[6], inv[6];
-    int has_elev, x_size, y_size;
-};
-
-__device__ __forceinline__ double round_half_away(double v) { return v >= 0 ? floor(v + 0.5) : ceil(v - 0.5); }
-
 __global__ void __launch_bounds__(256)
 k_world_coordinates(const double* __restrict__ px, const double* __restrict__ py, long long n, GeoParams p,
                     const double* __restrict__ heights, double* __restrict__ xyz, int* __restrict__ n_missing) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double x = px[i], y = py[i];
-    // GeoTransform::apply (no FMA contraction: GDAL is built without it on x86-64)
-    const double gx = __dadd_rn(__dadd_rn(p.gt[0], __dmul_rn(x, p.gt[1])), __dmul_rn(y, p.gt[2]));
-    const double gy = __dadd_rn(__dadd_rn(p.gt[3], __dmul_rn(x, p.gt[4])), __dmul_rn(y, p.gt[5]));
-    double h = 0.0;
-    if (p.has_elev) {
-        const double ex = __dadd_rn(__dadd_rn(p.inv[0], __dmul_rn(gx, p.inv[1])), __dmul_rn(gy, p.inv[2]));
-        const double ey = __dadd_rn(__dadd_rn(p.inv[3], __dmul_rn(gx, p.inv[4])), __dmul_rn(gy, p.inv[5]));
-        // elevation::get_elevation: row id = round(y) * x_size + round(x) + 1 (f64::round, i32 arithmetic)
-        const long long idx = (long long)round_half_away(ey) * p.x_size + (long long)round_half_away(ex);
-        if (idx >= 0 && idx < (long long)p.x_size * p.y_size) h = heights[idx];
-        else {
-            h = nan("");
-            atomicAdd(n_missing, 1);
-        }
-    }
-    // convert_coordinates(coordinates.1, coordinates.0, height): EPSG:4326 (lat, lon) -> EPSG:4978
-    const double phi = gy * kDegToRad, lam = gx * kDegToRad;
-    const double s = sin(phi), c = cos(phi);
-    const double N = kWgs84A / sqrt(1.0 - kWgs84Es * s * s);
-    xyz[3 * i + 0] = (N + h) * c * cos(lam);
-    xyz[3 * i + 1] = (N + h) * c * sin(lam);
-    xyz[3 * i + 2] = (N * (1.0 - kWgs84Es) + h) * s;
+    double o[3];
+    if (!world_point(p, heights, px[i], py[i], o)) atomicAdd(n_missing, 1);
+    xyz[3 * i + 0] = o[0];
+    xyz[3 * i + 1] = o[1];
+    xyz[3 * i + 2] = o[2];
 }
 
 // GDALInvGeoTransform
@@ -325,9 +287,7 @@ int dunk_world_coordinates(dunk_elevation* e, const double* px, const double* py
     DUNK_CUDA(cudaMemcpyAsync(d_x, px, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     DUNK_CUDA(cudaMemcpyAsync(d_y, py, (size_t)n * 8, cudaMemcpyHostToDevice, st));
     DUNK_CUDA(cudaMemsetAsync(d_miss, 0, 4, st));
-    GeoParams p;
-    for (int i = 0; i < 6; ++i) { p.gt[i] = e->gt_dataset[i]; p.inv[i] = e->gt_elev_inv[i]; }
-    p.has_elev = e->has_elevation; p.x_size = e->x_size; p.y_size = e->y_size;
+    const GeoParams p = make_geo_params(e);
     {
         ProfScope ps(ctx, st, "geo.world_coordinates", (double)n * 40.0);
         k_world_coordinates<<<div_up(n, 256), 256, 0, st>>>(d_x, d_y, n, p, e->heights, d_o, d_miss);

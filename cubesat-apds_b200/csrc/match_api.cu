@@ -216,6 +216,7 @@ void dunk_db_destroy(dunk_db* db) {
 }
 
 int64_t dunk_db_size(dunk_db* db) { return db ? db->size : 0; }
+int dunk_db_desc_bytes(dunk_db* db) { return db ? db->desc_bytes : 0; }
 
 int dunk_db_clear(dunk_db* db) {
     DUNK_REQUIRE(db, DUNK_ERR_BAD_ARG, "dunk_db_clear: db is NULL");

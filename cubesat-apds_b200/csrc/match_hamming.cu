@@ -346,18 +346,25 @@ __global__ void fill_random_rows_kernel(uint2* __restrict__ dst, long long n, un
 
 }  // namespace
 
+static constexpr size_t kHammingSmem = (size_t)kWarpsPerCta * kStages * kTileRows * 64 + kWarpsPerCta * kStages * sizeof(uint64_t);
+
+// per-device opt-in to ~96 KB of dynamic shared memory + the occupancy the planner sizes its rounds with
+static int hamming_device_init(dunk_ctx* ctx) {
+    DUNK_CUDA(cudaFuncSetAttribute(hamming_top2_kernel<kQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHammingSmem));
+    int occ = 0;
+    DUNK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<kQT>, kWarpsPerCta * 32, kHammingSmem));
+    ctx->hamming_occ = std::max(occ, 1);
+    return DUNK_OK;
+}
+static DeviceInitReg hamming_device_init_reg(hamming_device_init);
+
 KnnPlan plan_knn2(dunk_ctx* ctx, int nq, uint32_t nt) {
     KnnPlan p;
     p.threads = kWarpsPerCta * 32;
     p.gy = div_up(nq, 32 * kQT);          // query groups (one warp each)
     p.smem = (size_t)kWarpsPerCta * kStages * kTileRows * 64 + kWarpsPerCta * kStages * sizeof(uint64_t);
     const int total_tiles = div_up(nt, kTileRows);
-    static int occ = 0;
-    if (occ == 0) {
-        cudaFuncSetAttribute(hamming_top2_kernel<kQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<kQT>, p.threads, p.smem);
-        if (occ < 1) occ = 1;
-    }
+    const int occ = std::max(1, ctx->hamming_occ);      // per device, set by hamming_device_init
     // equal-sized slabs: (query groups x slabs) work items on `slots` resident warps.  All items cost the same,
     // so the launch takes ceil(items / slots) rounds; pick the slab count whose last round is fullest
     // (e.g. 1233 query groups x 4 slabs would be 2.08 rounds = 69 % efficiency, x 19 slabs is 9.9 rounds = 99 %).
@@ -387,10 +394,7 @@ KnnPlan plan_knn2(dunk_ctx* ctx, int nq, uint32_t nt) {
 // upper bound of plan.gx * nq * 16 over every query count <= nq_max (callers that size a workspace before the
 // query count is known): the planner never creates more than max(query groups, 16 * resident warps) work items
 size_t knn2_partial_bound(dunk_ctx* ctx, size_t nq_max) {
-    const KnnPlan probe = plan_knn2(ctx, 1, 1);   // initialises the occupancy query
-    (void)probe;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hamming_top2_kernel<kQT>, kWarpsPerCta * 32, probe.smem);
+    const int occ = ctx->hamming_occ;
     const size_t slots = (size_t)ctx->sm_count * (size_t)std::max(occ, 1) * kWarpsPerCta;
     const size_t groups = (nq_max + 32 * kQT - 1) / (32 * kQT);
     return std::max(groups, 16 * slots + groups) * (32 * kQT) * 16;

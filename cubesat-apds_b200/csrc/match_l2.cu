@@ -510,6 +510,14 @@ bool make_map(CUtensorMap* m, const float* base, uint64_t rows, int dim, int box
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// per-device opt-in to the kernels' dynamic shared memory (run by dunk_ctx_create on the context's device)
+static int l2_device_init(dunk_ctx*) {
+    DUNK_CUDA(cudaFuncSetAttribute(l2_candidates_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM));
+    DUNK_CUDA(cudaFuncSetAttribute(l2_candidates_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM));
+    return DUNK_OK;
+}
+static DeviceInitReg l2_device_init_reg(l2_device_init);
+
 template <int D>
 int launch_candidates(dunk_ctx* ctx, cudaStream_t st, const float* d_q, int nq, const float* d_t, uint32_t nt, const float* d_tnorm,
                       int total_tiles, int tiles_per_slab, int n_slabs, const float* d_tau, float4* cand_score, uint4* cand_idx, const char* label) {
@@ -518,11 +526,6 @@ int launch_candidates(dunk_ctx* ctx, cudaStream_t st, const float* d_q, int nq, 
     if (!make_map(&mq, d_q, (uint64_t)nq, D, kM) || !make_map(&mt, d_t, nt, D, C::N)) {
         set_error("dunk_knn2_l2: cuTensorMapEncodeTiled failed");
         return DUNK_ERR_CUDA;
-    }
-    static bool attr = false;
-    if (!attr) {
-        DUNK_CUDA(cudaFuncSetAttribute(l2_candidates_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr = true;
     }
     ProfScope ps(ctx, st, label, (double)nq * (double)std::min<long long>((long long)total_tiles * C::N, (long long)nt));
     l2_candidates_kernel<D><<<dim3(n_slabs, div_up(nq, kM)), kThreads, C::SMEM, st>>>(mq, mt, d_tnorm, nq, total_tiles, tiles_per_slab,

@@ -5,10 +5,13 @@
 // points) followed by find_homography_mat (homographier/src/homographier/mod.rs:231-259).
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include "akaze.h"
 #include "gamma_lut.cuh"
+#include "geo.cuh"
 #include "match.h"
 #include "pipeline.h"
+#include "shard.h"
 
 namespace dunk {
 
@@ -20,11 +23,18 @@ int akaze_run(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeW
 namespace {
 
 // exclusive scan of per-frame keypoint counts -> query offsets (frames <= 1024), one CTA
-__global__ void __launch_bounds__(1024) k_frame_offsets(const int* __restrict__ counts, int frames, int* __restrict__ offsets) {
+// offsets[frames + 1] = the largest raw-extrema count of the batch: k_extrema keeps counting past the
+// candidate capacity and drops the entry, so the caller compares it with cand_cap in the read-back it
+// already makes and fails loudly instead of returning an atomics-order-dependent keypoint subset
+__global__ void __launch_bounds__(1024) k_frame_offsets(const int* __restrict__ counts, int frames, int* __restrict__ offsets,
+                                                        const int* __restrict__ cand_count) {
     __shared__ int sh[1024];
+    __shared__ int cmax;
     const int t = threadIdx.x;
+    if (t == 0) cmax = 0;
     sh[t] = t < frames ? counts[t] : 0;
     __syncthreads();
+    if (t < frames) atomicMax(&cmax, cand_count[t]);
     for (int o = 1; o < 1024; o <<= 1) {
         const int v = t >= o ? sh[t - o] : 0;
         __syncthreads();
@@ -32,7 +42,10 @@ __global__ void __launch_bounds__(1024) k_frame_offsets(const int* __restrict__ 
         __syncthreads();
     }
     if (t < frames) offsets[t + 1] = sh[t];
-    if (t == 0) offsets[0] = 0;
+    if (t == 0) {
+        offsets[0] = 0;
+        offsets[frames + 1] = cmax;
+    }
 }
 
 // gather every frame's descriptor rows into one contiguous query array
@@ -114,6 +127,88 @@ __global__ void k_pack_results(const double* __restrict__ H, const int* __restri
     out[f] = r;
 }
 
+// ---- pose stage (stage 3b): homography inliers -> (object point, image point) pairs -> PnP-RANSAC -------------
+// What a caller of the reference composes by hand: get_world_coordinates (feature_database/src/elevationdb.rs:64-104)
+// for every matched reference keypoint, then pnp_solver_ransac (homographier/src/homographier/mod.rs:320-369).
+struct PoseParams {
+    GeoParams geo;
+    const double* heights;
+    double K[9];
+    double origin[3];
+};
+
+// per frame: ordered compaction of the pairs the homography kept (mask != 0) into the f32 point lists
+// solvePnPRansac works on (OpenCV rounds its f64 inputs to f32 first; the caller's origin is subtracted in f64
+// before that rounding so ECEF magnitudes of 6.4e6 m do not eat the mantissa).  Pairs whose elevation sample is
+// missing are dropped.  Block 0 also places the camera matrix in device memory for the PnP kernel.
+__global__ void __launch_bounds__(1024)
+k_pose_inputs(const float2* __restrict__ src, const float2* __restrict__ dst, const uint8_t* __restrict__ mask,
+              const int* __restrict__ offsets, const int* __restrict__ n_pairs, const int* __restrict__ h_info, PoseParams pp,
+              float* __restrict__ obj, float* __restrict__ img, int* __restrict__ pose_count, double* __restrict__ K_dev) {
+    __shared__ int wsum[32];
+    __shared__ int running, chunk_total;
+    const int f = blockIdx.x;
+    const int off = offsets[f];
+    const int n = h_info[f * 4 + 0] ? n_pairs[f] : 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (f == 0 && tid < 9) K_dev[tid] = pp.K[tid];
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        bool keep = i < n && mask[off + i] != 0;
+        double w[3] = {0, 0, 0};
+        float2 q = make_float2(0.f, 0.f);
+        if (keep) {
+            const float2 r = dst[off + i];
+            q = src[off + i];
+            keep = world_point(pp.geo, pp.heights, (double)r.x, (double)r.y, w);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const int x = wsum[lane];
+            int incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            wsum[lane] = incl - x;
+            if (lane == 31) chunk_total = incl;
+        }
+        __syncthreads();
+        if (keep) {
+            const size_t pos = (size_t)off + running + wsum[warp] + __popc(bal & ((1u << lane) - 1u));
+            obj[pos * 3 + 0] = (float)(w[0] - pp.origin[0]);
+            obj[pos * 3 + 1] = (float)(w[1] - pp.origin[1]);
+            obj[pos * 3 + 2] = (float)(w[2] - pp.origin[2]);
+            img[pos * 2 + 0] = q.x;
+            img[pos * 2 + 1] = q.y;
+        }
+        __syncthreads();
+        if (tid == 0) running += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) pose_count[f] = running;
+}
+
+__global__ void k_pack_poses(const double* __restrict__ rt, const int* __restrict__ info, int frames, DunkPose* __restrict__ out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= frames) return;
+    DunkPose p;
+    for (int i = 0; i < 3; ++i) {
+        p.rvec[i] = rt[f * 6 + i];
+        p.tvec[i] = rt[f * 6 + 3 + i];
+    }
+    p.found = info[f * 4 + 0];
+    p.inliers = info[f * 4 + 1];
+    p.ransac_iters = info[f * 4 + 2];
+    p.hypotheses = info[f * 4 + 3];
+    out[f] = p;
+}
+
 size_t al(size_t b) { return (b + 255) & ~size_t(255); }
 
 struct PipelineBuffers {
@@ -129,6 +224,15 @@ struct PipelineBuffers {
     uint8_t* mask;       // [frames * kp_cap]
     int* info;           // [frames * 4]
     DunkRegistration* results;  // [frames]
+    // pose stage
+    float* p_obj;        // [frames * kp_cap][3]
+    float* p_img;        // [frames * kp_cap][2]
+    int* p_count;        // [frames]
+    double* p_K;         // [9]
+    double* p_rt;        // [frames][6]
+    uint8_t* p_mask;     // [frames * kp_cap]
+    int* p_info;         // [frames][4]
+    DunkPose* poses;     // [frames]
 };
 
 }  // namespace
@@ -152,9 +256,11 @@ static PipelinePlan plan_pipeline(dunk_ctx* ctx, int rows, int cols, int frames,
     // worst-case slab count for the matcher: plan with the largest query count
     (void)db_rows;
     p.partial_bytes = knn2_partial_bound(ctx, nq_max);
-    p.total_bytes = al(p.ws_bytes) + al((frames + 1) * 4) + al(nq_max * 64) + al(nq_max * 16) + al(p.partial_bytes) +
+    p.total_bytes = al(p.ws_bytes) + al((frames + 2) * 4) + al(nq_max * 64) + al(nq_max * 16) + al(p.partial_bytes) +
                     2 * al(nq_max * 8) + al(nq_max * 16) + al(frames * 4) + al((size_t)frames * 72) + al(nq_max) +
-                    al((size_t)frames * 16) + al((size_t)frames * sizeof(DunkRegistration));
+                    al((size_t)frames * 16) + al((size_t)frames * sizeof(DunkRegistration)) +
+                    al(nq_max * 12) + al(nq_max * 8) + al(frames * 4) + al(72) + al((size_t)frames * 48) + al(nq_max) +
+                    al((size_t)frames * 16) + al((size_t)frames * sizeof(DunkPose));
     return p;
 }
 
@@ -163,7 +269,7 @@ static void carve_pipeline(void* base, const PipelinePlan& p, PipelineBuffers* b
     auto take = [&](size_t bytes) { void* r = ptr; ptr += al(bytes); return r; };
     akaze_carve_workspace(take(p.ws_bytes), p.lt, p.frames, p.cand_cap, p.kp_cap, &b->ws);
     const size_t nq_max = (size_t)p.frames * p.kp_cap;
-    b->q_off = (int*)take((p.frames + 1) * 4);
+    b->q_off = (int*)take((p.frames + 2) * 4);
     b->q64 = (uint4*)take(nq_max * 64);
     b->top2 = (uint4*)take(nq_max * 16);
     b->partial = (uint4*)take(p.partial_bytes);
@@ -175,22 +281,42 @@ static void carve_pipeline(void* base, const PipelinePlan& p, PipelineBuffers* b
     b->mask = (uint8_t*)take(nq_max);
     b->info = (int*)take((size_t)p.frames * 16);
     b->results = (DunkRegistration*)take((size_t)p.frames * sizeof(DunkRegistration));
+    b->p_obj = (float*)take(nq_max * 12);
+    b->p_img = (float*)take(nq_max * 8);
+    b->p_count = (int*)take(p.frames * 4);
+    b->p_K = (double*)take(72);
+    b->p_rt = (double*)take((size_t)p.frames * 48);
+    b->p_mask = (uint8_t*)take(nq_max);
+    b->p_info = (int*)take((size_t)p.frames * 16);
+    b->poses = (DunkPose*)take((size_t)p.frames * sizeof(DunkPose));
 }
 
 // stage 1 for `frames` device-resident images + packing of every frame's descriptors into one
 // query array; returns the total query count (one 4-byte read back: the matcher grid depends on it)
-static int pipeline_extract(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& p, const PipelineBuffers& b,
-                            const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
-                            int max_points, int* total_q) {
+static int pipeline_extract_async(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& p, const PipelineBuffers& b,
+                                  const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
+                                  int max_points) {
     int rc = akaze_run(ctx, st, p.lt, b.ws, images_dev, frame_stride, row_stride, channels, frames, max_points);
     if (rc) return rc;
-    k_frame_offsets<<<1, 1024, 0, st>>>(b.ws.kp_count, frames, b.q_off);
+    k_frame_offsets<<<1, 1024, 0, st>>>(b.ws.kp_count, frames, b.q_off, b.ws.cand_count);
     DUNK_KERNEL_CHECK(ctx);
     k_pack_queries<<<dim3(div_up((long long)p.kp_cap * 4, 256), frames), 256, 0, st>>>(b.ws.desc64, p.kp_cap, b.ws.kp_count,
                                                                                       b.q_off, b.q64);
     DUNK_KERNEL_CHECK(ctx);
-    DUNK_CUDA(cudaMemcpyAsync(total_q, b.q_off + frames, 4, cudaMemcpyDeviceToHost, st));
+    return DUNK_OK;
+}
+
+static int pipeline_extract(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& p, const PipelineBuffers& b,
+                            const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
+                            int max_points, int* total_q) {
+    int rc = pipeline_extract_async(ctx, st, p, b, images_dev, frame_stride, row_stride, channels, frames, max_points);
+    if (rc) return rc;
+    int h_tail[2] = {0, 0};     // {total queries, largest raw-extrema count}
+    DUNK_CUDA(cudaMemcpyAsync(h_tail, b.q_off + frames, 8, cudaMemcpyDeviceToHost, st));
     DUNK_CUDA(cudaStreamSynchronize(st));
+    *total_q = h_tail[0];
+    DUNK_REQUIRE(h_tail[1] <= p.cand_cap, DUNK_ERR_NO_MEM,
+                 "pipeline: a frame produced %d raw extrema, candidate capacity %d (w*h/32)", h_tail[1], p.cand_cap);
     return DUNK_OK;
 }
 
@@ -198,7 +324,7 @@ static int pipeline_extract(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& 
 // top2: merged top-2 per query; db_kps: keypoints addressed by (train index - index_base)
 static int pipeline_finish(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& p, const PipelineBuffers& b,
                            const uint4* top2, const DunkKeyPoint* db_kps, uint32_t index_base, int frames, float ratio,
-                           float thr) {
+                           float thr, const DunkPoseConfig* pose = nullptr) {
     {
         ProfScope ps(ctx, st, "pipe.frame_pairs", 0.0);
         k_frame_pairs<<<frames, 1024, 0, st>>>(top2, b.ws.kp_count, b.q_off, ratio, b.ws.kps, p.kp_cap, db_kps, index_base, b.src,
@@ -215,13 +341,44 @@ static int pipeline_finish(dunk_ctx* ctx, cudaStream_t st, const PipelinePlan& p
         k_pack_results<<<div_up(frames, 128), 128, 0, st>>>(b.H, b.info, b.n_pairs, b.ws.kp_count, frames, b.results);
         DUNK_KERNEL_CHECK(ctx);
     }
+    if (!pose) return DUNK_OK;
+    // stage 3b: the correspondences the homography kept -> ECEF object points -> PnP-RANSAC pose per frame
+    PoseParams pp;
+    pp.geo = make_geo_params(pose->elevation);
+    pp.heights = pose->elevation->heights;
+    for (int i = 0; i < 9; ++i) pp.K[i] = pose->K[i];
+    for (int i = 0; i < 3; ++i) pp.origin[i] = pose->origin[i];
+    {
+        ProfScope ps(ctx, st, "pose.inputs", 0.0);
+        k_pose_inputs<<<frames, 1024, 0, st>>>(b.src, b.dst, b.mask, b.q_off, b.n_pairs, b.info, pp, b.p_obj, b.p_img, b.p_count, b.p_K);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, st, "ransac.pnp", 0.0);
+        if ((rc = launch_pnp_ransac(ctx, st, b.p_obj, b.p_img, b.q_off, b.p_count, frames, b.p_K, 0, pose->method, pose->iters,
+                                    pose->thr, pose->confidence, b.p_rt, b.p_mask, b.p_info)))
+            return rc;
+    }
+    {
+        ProfScope ps(ctx, st, "pipe.pack_results", 0.0);
+        k_pack_poses<<<div_up(frames, 128), 128, 0, st>>>(b.p_rt, b.p_info, frames, b.poses);
+        DUNK_KERNEL_CHECK(ctx);
+    }
+    return DUNK_OK;
+}
+
+static int check_pose(const char* fn, const DunkPoseConfig* pose) {
+    if (!pose) return DUNK_OK;
+    DUNK_REQUIRE(pose->elevation, DUNK_ERR_BAD_ARG, "%s: pose config without an elevation / geotransform handle", fn);
+    DUNK_REQUIRE(pose->method == DUNK_PNP_EPNP || pose->method == DUNK_PNP_P3P || pose->method == DUNK_PNP_ITERATIVE, DUNK_ERR_BAD_ARG,
+                 "%s: PnP method %d not implemented", fn, pose->method);
     return DUNK_OK;
 }
 
 // all three stages for `frames` device-resident images against one shard; results (device) in b.results
 static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const PipelinePlan& p, const PipelineBuffers& b,
                         const unsigned char* images_dev, size_t frame_stride, int row_stride, int channels, int frames,
-                        float ratio, float thr, int max_points, int* h_total_q /*unused*/) {
+                        float ratio, float thr, int max_points, const DunkPoseConfig* pose) {
     int total_q = 0;
     int rc = pipeline_extract(ctx, st, p, b, images_dev, frame_stride, row_stride, channels, frames, max_points, &total_q);
     if (rc) return rc;
@@ -235,7 +392,7 @@ static int run_pipeline(dunk_ctx* ctx, cudaStream_t st, dunk_db* db, const Pipel
     } else if (total_q > 0) {
         DUNK_CUDA(cudaMemsetAsync(b.top2, 0xFF, (size_t)total_q * 16, st));
     }
-    return pipeline_finish(ctx, st, p, b, b.top2, db->kps, 0, frames, ratio, thr);
+    return pipeline_finish(ctx, st, p, b, b.top2, db->kps, 0, frames, ratio, thr, pose);
 }
 
 }  // namespace dunk
@@ -257,14 +414,16 @@ size_t dunk_register_workspace_bytes(dunk_db* db, int n_frames, int rows, int co
     return plan_pipeline(db->ctx, rows, cols, n_frames, db->size).total_bytes;
 }
 
-int dunk_register_frames_dev(dunk_db* db, int slot, const void* images_dev, int n_frames, int rows, int cols, int channels,
-                             int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
-                             void* workspace_dev, size_t workspace_bytes, void* results_dev) {
+int dunk_register_frames_pose_dev(dunk_db* db, int slot, const void* images_dev, int n_frames, int rows, int cols, int channels,
+                                  int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
+                                  const DunkPoseConfig* pose, void* workspace_dev, size_t workspace_bytes, void* results_dev,
+                                  void* poses_dev) {
     DUNK_REQUIRE(db && images_dev && workspace_dev && results_dev, DUNK_ERR_BAD_ARG, "dunk_register_frames_dev: NULL argument");
+    DUNK_REQUIRE(!pose || poses_dev, DUNK_ERR_BAD_ARG, "dunk_register_frames_pose_dev: pose config without a pose output");
     dunk_ctx* ctx = db->ctx;
     DUNK_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), DUNK_ERR_BAD_ARG, "dunk_register_frames_dev: bad slot");
     int rc = check_frames("dunk_register_frames_dev", n_frames, rows, cols, channels, row_stride_bytes);
-    if (rc) return rc;
+    if (rc || (rc = check_pose("dunk_register_frames_pose_dev", pose))) return rc;
     if (n_frames == 0) return DUNK_OK;
     if (frame_stride_bytes == 0) frame_stride_bytes = (size_t)rows * row_stride_bytes;
     DUNK_CUDA(cudaSetDevice(ctx->device));
@@ -275,19 +434,31 @@ int dunk_register_frames_dev(dunk_db* db, int slot, const void* images_dev, int 
     carve_pipeline(workspace_dev, p, &b);
     cudaStream_t st = ctx->slots[slot].stream;
     if ((rc = run_pipeline(ctx, st, db, p, b, (const unsigned char*)images_dev, frame_stride_bytes, row_stride_bytes, channels,
-                           n_frames, ratio, (float)thr, max_points <= 0 ? 0 : max_points, nullptr)))
+                           n_frames, ratio, (float)thr, max_points <= 0 ? 0 : max_points, pose)))
         return rc;
     DUNK_CUDA(cudaMemcpyAsync(results_dev, b.results, (size_t)n_frames * sizeof(DunkRegistration), cudaMemcpyDeviceToDevice, st));
+    if (pose) DUNK_CUDA(cudaMemcpyAsync(poses_dev, b.poses, (size_t)n_frames * sizeof(DunkPose), cudaMemcpyDeviceToDevice, st));
     return DUNK_OK;
 }
 
-int dunk_register_frames(dunk_db* db, const uint8_t* images, int n_frames, int rows, int cols, int channels,
-                         int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
-                         DunkRegistration* results) {
+int dunk_register_frames_dev(dunk_db* db, int slot, const void* images_dev, int n_frames, int rows, int cols, int channels,
+                             int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
+                             void* workspace_dev, size_t workspace_bytes, void* results_dev) {
+    return dunk_register_frames_pose_dev(db, slot, images_dev, n_frames, rows, cols, channels, row_stride_bytes, frame_stride_bytes,
+                                         ratio, thr, max_points, nullptr, workspace_dev, workspace_bytes, results_dev, nullptr);
+}
+
+/* Host buffers in, host records out.  The frames move through two pinned staging halves filled by the calling
+ * thread while the previous sub-batch is on the device, so pageable callers (a Rust Vec<u8>) get an async
+ * H2D copy at pinned speed that overlaps the kernels instead of the driver's staged synchronous copy. */
+int dunk_register_frames_pose(dunk_db* db, const uint8_t* images, int n_frames, int rows, int cols, int channels,
+                              int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
+                              const DunkPoseConfig* pose, DunkRegistration* results, DunkPose* poses) {
     DUNK_REQUIRE(db && results, DUNK_ERR_BAD_ARG, "dunk_register_frames: NULL argument");
+    DUNK_REQUIRE(!pose || poses, DUNK_ERR_BAD_ARG, "dunk_register_frames_pose: pose config without a pose output");
     dunk_ctx* ctx = db->ctx;
     int rc = check_frames("dunk_register_frames", n_frames, rows, cols, channels, row_stride_bytes);
-    if (rc) return rc;
+    if (rc || (rc = check_pose("dunk_register_frames_pose", pose))) return rc;
     if (n_frames == 0) return DUNK_OK;
     DUNK_REQUIRE(images, DUNK_ERR_ASSERT, "dunk_register_frames: empty image");
     if (frame_stride_bytes == 0) frame_stride_bytes = (size_t)rows * row_stride_bytes;
@@ -296,23 +467,43 @@ int dunk_register_frames(dunk_db* db, const uint8_t* images, int n_frames, int r
     // sub-batches of <= 64 frames keep the workspace bounded
     const int sub = std::min(n_frames, 64);
     const PipelinePlan p = plan_pipeline(ctx, rows, cols, sub, db->size);
-    const size_t need = al(p.total_bytes) + al((size_t)sub * frame_stride_bytes);
-    void* scratch = ctx->dev_scratch(g.s, need);
+    const size_t img_bytes = al((size_t)sub * frame_stride_bytes);
+    void* scratch = ctx->dev_scratch(g.s, al(p.total_bytes) + 2 * img_bytes);
     if (!scratch) return DUNK_ERR_NO_MEM;
+    const size_t res_bytes = al((size_t)n_frames * sizeof(DunkRegistration));
+    unsigned char* pin = (unsigned char*)ctx->pin_scratch(g.s, 2 * img_bytes + res_bytes + al((size_t)n_frames * sizeof(DunkPose)));
+    if (!pin) return DUNK_ERR_NO_MEM;
+    DunkRegistration* pin_res = (DunkRegistration*)(pin + 2 * img_bytes);     // pageable outputs would make the D2H copy block
+    DunkPose* pin_pose = (DunkPose*)(pin + 2 * img_bytes + res_bytes);
     PipelineBuffers b;
     carve_pipeline(scratch, p, &b);
     unsigned char* d_img = (unsigned char*)scratch + al(p.total_bytes);
-    for (int f0 = 0; f0 < n_frames; f0 += sub) {
+    cudaEvent_t staged[2] = {g.slot().ev0, g.slot().ev1};   // H2D of half h has left the pinned half
+    int half = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += sub, half ^= 1) {
         const int nf = std::min(sub, n_frames - f0);
-        DUNK_CUDA(cudaMemcpyAsync(d_img, images + (size_t)f0 * frame_stride_bytes, (size_t)nf * frame_stride_bytes,
+        if (f0 >= 2 * sub) DUNK_CUDA(cudaEventSynchronize(staged[half]));
+        memcpy(pin + half * img_bytes, images + (size_t)f0 * frame_stride_bytes, (size_t)nf * frame_stride_bytes);
+        DUNK_CUDA(cudaMemcpyAsync(d_img + half * img_bytes, pin + half * img_bytes, (size_t)nf * frame_stride_bytes,
                                   cudaMemcpyHostToDevice, st));
-        if ((rc = run_pipeline(ctx, st, db, p, b, d_img, frame_stride_bytes, row_stride_bytes, channels, nf, ratio, (float)thr,
-                               max_points <= 0 ? 0 : max_points, nullptr)))
+        DUNK_CUDA(cudaEventRecord(staged[half], st));
+        if ((rc = run_pipeline(ctx, st, db, p, b, d_img + half * img_bytes, frame_stride_bytes, row_stride_bytes, channels, nf, ratio,
+                               (float)thr, max_points <= 0 ? 0 : max_points, pose)))
             return rc;
-        DUNK_CUDA(cudaMemcpyAsync(results + f0, b.results, (size_t)nf * sizeof(DunkRegistration), cudaMemcpyDeviceToHost, st));
-        DUNK_CUDA(cudaStreamSynchronize(st));
+        DUNK_CUDA(cudaMemcpyAsync(pin_res + f0, b.results, (size_t)nf * sizeof(DunkRegistration), cudaMemcpyDeviceToHost, st));
+        if (pose) DUNK_CUDA(cudaMemcpyAsync(pin_pose + f0, b.poses, (size_t)nf * sizeof(DunkPose), cudaMemcpyDeviceToHost, st));
     }
+    DUNK_CUDA(cudaStreamSynchronize(st));
+    memcpy(results, pin_res, (size_t)n_frames * sizeof(DunkRegistration));
+    if (pose) memcpy(poses, pin_pose, (size_t)n_frames * sizeof(DunkPose));
     return DUNK_OK;
+}
+
+int dunk_register_frames(dunk_db* db, const uint8_t* images, int n_frames, int rows, int cols, int channels,
+                         int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
+                         DunkRegistration* results) {
+    return dunk_register_frames_pose(db, images, n_frames, rows, cols, channels, row_stride_bytes, frame_stride_bytes, ratio, thr,
+                                     max_points, nullptr, results, nullptr);
 }
 
 /* ---- sharded pipeline phases: extract on the frame owner, match on every shard,
@@ -381,6 +572,99 @@ int dunk_pipeline_finish_dev(dunk_ctx* ctx, int slot, int n_frames, int rows, in
     if ((rc = pipeline_finish(ctx, st, p, b, top2, (const DunkKeyPoint*)db_keypoints_dev, index_base, n_frames, ratio, (float)thr)))
         return rc;
     DUNK_CUDA(cudaMemcpyAsync(results_dev, b.results, (size_t)n_frames * sizeof(DunkRegistration), cudaMemcpyDeviceToDevice, st));
+    return DUNK_OK;
+}
+
+/* ---- the sharded registration step, one call per step and rank (BASELINE config 5) ---------------- */
+size_t dunk_register_sharded_workspace_bytes(dunk_shard_group* g, int n_frames, int rows, int cols) {
+    if (!g || n_frames <= 0) return 0;
+    return plan_pipeline(g->ctx, rows, cols, n_frames, 1).total_bytes;
+}
+
+int dunk_register_frames_sharded_dev(dunk_shard_group* g, dunk_db* shard, int slot, const void* images_dev, int n_frames, int rows,
+                                     int cols, int channels, int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr,
+                                     int max_points, const DunkPoseConfig* pose, void* workspace_dev, size_t workspace_bytes,
+                                     void* results_dev, void* poses_dev) {
+    DUNK_REQUIRE(g && shard && images_dev && workspace_dev && results_dev, DUNK_ERR_BAD_ARG, "dunk_register_frames_sharded_dev: NULL argument");
+    DUNK_REQUIRE(!pose || poses_dev, DUNK_ERR_BAD_ARG, "dunk_register_frames_sharded_dev: pose config without a pose output");
+    dunk_ctx* ctx = g->ctx;
+    DUNK_REQUIRE(shard->ctx == ctx, DUNK_ERR_BAD_ARG, "dunk_register_frames_sharded_dev: the shard lives on another context");
+    DUNK_REQUIRE(slot >= 0 && slot < (int)ctx->slots.size(), DUNK_ERR_BAD_ARG, "dunk_register_frames_sharded_dev: bad slot");
+    DUNK_REQUIRE(g->kps_all && g->total_rows == g->bases[g->world], DUNK_ERR_BAD_ARG,
+                 "dunk_register_frames_sharded_dev: the group holds no keypoint column (dunk_shard_group_balance first)");
+    int rc = check_frames("dunk_register_frames_sharded_dev", n_frames, rows, cols, channels, row_stride_bytes);
+    if (rc || (rc = check_pose("dunk_register_frames_sharded_dev", pose))) return rc;
+    DUNK_REQUIRE(n_frames > 0, DUNK_ERR_BAD_ARG, "dunk_register_frames_sharded_dev: no frames (the call is collective)");
+    if (frame_stride_bytes == 0) frame_stride_bytes = (size_t)rows * row_stride_bytes;
+    DUNK_CUDA(cudaSetDevice(ctx->device));
+    const PipelinePlan p = plan_pipeline(ctx, rows, cols, n_frames, 1);
+    DUNK_REQUIRE(workspace_bytes >= p.total_bytes, DUNK_ERR_NO_MEM, "dunk_register_frames_sharded_dev: workspace %zu < %zu bytes",
+                 workspace_bytes, p.total_bytes);
+    PipelineBuffers b;
+    carve_pipeline(workspace_dev, p, &b);
+    cudaStream_t st = ctx->slots[slot].stream;
+    const int W = g->world, me = g->rank;
+    // phase 1 (frame owner): extract + pack; then the ranks learn each other's {query count, raw-extrema maximum}
+    if ((rc = pipeline_extract_async(ctx, st, p, b, (const unsigned char*)images_dev, frame_stride_bytes, row_stride_bytes, channels,
+                                     n_frames, max_points <= 0 ? 0 : max_points)))
+        return rc;
+    int* d_cnt = (int*)g->d_counts;          // [W][2] int32
+    int* h_cnt = (int*)g->h_counts;
+    {
+        ProfScope ps(ctx, st, "shard.all_gather_counts", 8.0 * W);
+        if ((rc = shard_all_gather(g, b.q_off + n_frames, d_cnt, 8, st))) return rc;
+    }
+    DUNK_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)W * 8, cudaMemcpyDeviceToHost, st));
+    DUNK_CUDA(cudaStreamSynchronize(st));     // the step's one host sync (grids and message sizes depend on the counts)
+    int qmax = 0, cand_max = 0;
+    for (int r = 0; r < W; ++r) {
+        qmax = std::max(qmax, h_cnt[2 * r]);
+        cand_max = std::max(cand_max, h_cnt[2 * r + 1]);
+    }
+    DUNK_REQUIRE(cand_max <= p.cand_cap, DUNK_ERR_NO_MEM, "pipeline: a frame produced %d raw extrema, candidate capacity %d (w*h/32)",
+                 cand_max, p.cand_cap);
+    const int my_q = h_cnt[2 * me];
+    const uint4* top2 = b.top2;
+    if (qmax > 0) {
+        // phase 2 (every shard): all ranks' query rows, padded to the largest count of this step (rows past a rank's
+        // count are stale rows of its workspace: matched and ignored), against the local shard in ONE launch
+        const size_t all_q = (size_t)W * qmax;
+        uint4* q_all = W == 1 ? b.q64 : (uint4*)g->ensure(0, all_q * 64, st);
+        uint4* t_out = W == 1 ? b.top2 : (uint4*)g->ensure(1, all_q * 16, st);
+        uint4* parts = W == 1 ? b.top2 : (uint4*)g->ensure(2, all_q * 16, st);
+        if (!q_all || !t_out || !parts) return DUNK_ERR_NO_MEM;
+        if (W > 1) {
+            ProfScope ps(ctx, st, "shard.all_gather_queries", (double)all_q * 64);
+            if ((rc = shard_all_gather(g, b.q64, q_all, (size_t)qmax * 64, st))) return rc;
+        }
+        if (shard->size > 0) {
+            const KnnPlan kp = plan_knn2(ctx, (int)all_q, (uint32_t)shard->size);
+            uint4* partial = W == 1 ? b.partial : (uint4*)g->ensure(3, knn2_partial_bytes(kp, (int)all_q), st);
+            if (!partial) return DUNK_ERR_NO_MEM;
+            if (W == 1 && knn2_partial_bytes(kp, (int)all_q) > p.partial_bytes) {
+                set_error("pipeline: matcher partial buffer too small");
+                return DUNK_ERR_NO_MEM;
+            }
+            if ((rc = launch_knn2(ctx, st, shard->desc64, (uint32_t)shard->size, q_all, (int)all_q, (uint32_t)g->bases[me], partial, t_out, kp)))
+                return rc;
+        } else {
+            DUNK_CUDA(cudaMemsetAsync(t_out, 0xFF, all_q * 16, st));
+        }
+        if (W > 1) {
+            // phase 3 (frame owner): every shard's top-2 of MY queries, merged by (distance, index)
+            {
+                ProfScope ps(ctx, st, "shard.all_to_all_top2", (double)all_q * 16);
+                if ((rc = shard_all_to_all(g, t_out, parts, (size_t)qmax * 16, st))) return rc;
+            }
+            if (my_q > 0) {
+                ProfScope ps(ctx, st, "match.top2_merge", (double)my_q * W * 16);
+                if ((rc = launch_top2_merge_strided(ctx, st, parts, W, qmax, my_q, b.top2))) return rc;
+            }
+        }
+    }
+    if ((rc = pipeline_finish(ctx, st, p, b, top2, g->kps_all, 0, n_frames, ratio, (float)thr, pose))) return rc;
+    DUNK_CUDA(cudaMemcpyAsync(results_dev, b.results, (size_t)n_frames * sizeof(DunkRegistration), cudaMemcpyDeviceToDevice, st));
+    if (pose) DUNK_CUDA(cudaMemcpyAsync(poses_dev, b.poses, (size_t)n_frames * sizeof(DunkPose), cudaMemcpyDeviceToDevice, st));
     return DUNK_OK;
 }
 
@@ -462,7 +746,7 @@ int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int ro
     const int cap = (int)c;
     const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cap, cap);
     const size_t meta = al((size_t)n_tiles * 4);
-    const size_t need = al(ws_bytes) + al((size_t)sub * frame_stride_bytes) + al((sub + 1) * 4) + 4 * meta;
+    const size_t need = al(ws_bytes) + al((size_t)sub * frame_stride_bytes) + al((sub + 2) * 4) + 4 * meta;
     void* scratch = ctx->dev_scratch(g.s, need);
     if (!scratch) return DUNK_ERR_NO_MEM;
     char* ptr = (char*)scratch;
@@ -470,7 +754,7 @@ int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int ro
     akaze_carve_workspace(ptr, lt, sub, cap, cap, &ws);
     ptr += al(ws_bytes);
     unsigned char* d_img = (unsigned char*)ptr; ptr += al((size_t)sub * frame_stride_bytes);
-    int* d_off = (int*)ptr; ptr += al((sub + 1) * 4);
+    int* d_off = (int*)ptr; ptr += al((sub + 2) * 4);
     float* d_xo = (float*)ptr; ptr += meta;
     float* d_yo = (float*)ptr; ptr += meta;
     float* d_sc = (float*)ptr; ptr += meta;
@@ -479,18 +763,20 @@ int dunk_db_append_tiles(dunk_db* db, const uint8_t* images, int n_tiles, int ro
     if (y_off) DUNK_CUDA(cudaMemcpyAsync(d_yo, y_off, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
     if (scale) DUNK_CUDA(cudaMemcpyAsync(d_sc, scale, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
     if (image_ids) DUNK_CUDA(cudaMemcpyAsync(d_id, image_ids, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
-    std::vector<int> h_off(sub + 1), h_cnt(sub);
+    std::vector<int> h_off(sub + 2), h_cnt(sub);
     for (int t0 = 0; t0 < n_tiles; t0 += sub) {
         const int nf = std::min(sub, n_tiles - t0);
         DUNK_CUDA(cudaMemcpyAsync(d_img, images + (size_t)t0 * frame_stride_bytes, (size_t)nf * frame_stride_bytes,
                                   cudaMemcpyHostToDevice, st));
         if ((rc = akaze_run(ctx, st, lt, ws, d_img, frame_stride_bytes, row_stride_bytes, channels, nf, max_points <= 0 ? 0 : max_points)))
             return rc;
-        k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off);
+        k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off, ws.cand_count);
         DUNK_KERNEL_CHECK(ctx);
-        DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 1) * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 2) * 4, cudaMemcpyDeviceToHost, st));
         DUNK_CUDA(cudaMemcpyAsync(h_cnt.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
         DUNK_CUDA(cudaStreamSynchronize(st));
+        DUNK_REQUIRE(h_off[nf + 1] <= cap, DUNK_ERR_NO_MEM, "dunk_db_append_tiles: a tile produced %d raw extrema, candidate capacity %d",
+                     h_off[nf + 1], cap);
         const int total = h_off[nf];
         DUNK_REQUIRE(db->size + total <= db->capacity, DUNK_ERR_NO_MEM,
                      "dunk_db_append_tiles: %lld + %d rows exceed capacity %lld", (long long)db->size, total,
@@ -637,7 +923,7 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
     const int cap = (int)c;
     const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cap, cap);
     const size_t tile_bytes = (size_t)tile_w * tile_h * 4;
-    const size_t need = (bands_on_device ? 0 : 3 * al(plane * 4)) + al(ws_bytes) + al(sub * tile_bytes) + al((sub + 1) * 4) + 4 * al(sub * 4);
+    const size_t need = (bands_on_device ? 0 : 3 * al(plane * 4)) + al(ws_bytes) + al(sub * tile_bytes) + al((sub + 2) * 4) + 4 * al(sub * 4);
     void* scratch = ctx->dev_scratch(g.s, need);
     if (!scratch) return DUNK_ERR_NO_MEM;
     char* ptr = (char*)scratch;
@@ -646,7 +932,10 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
         const float* h_band[3] = {red, green, blue};
         for (int b = 0; b < 3; ++b) {
             d_band[b] = (const float*)ptr;
-            DUNK_CUDA(cudaMemcpyAsync(ptr, h_band[b], plane * 4, cudaMemcpyHostToDevice, st));
+            // pageable 482 MB planes: through the slot's pinned ring (the driver's staged copy is ~11 GB/s and was
+            // 130 of the 150 ms of a host-buffer build)
+            int rcu = ctx->upload_pageable(g.s, ptr, h_band[b], plane * 4);
+            if (rcu) return rcu;
             ptr += al(plane * 4);
         }
     }
@@ -654,7 +943,7 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
     akaze_carve_workspace(ptr, lt, sub, cap, cap, &ws);
     ptr += al(ws_bytes);
     unsigned char* d_tiles = (unsigned char*)ptr; ptr += al(sub * tile_bytes);
-    int* d_off = (int*)ptr; ptr += al((sub + 1) * 4);
+    int* d_off = (int*)ptr; ptr += al((sub + 2) * 4);
     float* d_xo = (float*)ptr; ptr += al(sub * 4);
     float* d_yo = (float*)ptr; ptr += al(sub * 4);
     float* d_sc = (float*)ptr; ptr += al(sub * 4);
@@ -672,7 +961,7 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
     const float* thr = gamma_table(ctx, st);
     DUNK_REQUIRE(thr, DUNK_ERR_CUDA, "dunk_db_build_from_bands: gamma table");
     int n_tiles = 0;
-    std::vector<int> h_off(sub + 1), h_cnt(sub);
+    std::vector<int> h_off(sub + 2), h_cnt(sub);
     for (size_t j0 = 0; j0 < jobs.size(); j0 += sub) {
         const int nf = (int)std::min<size_t>(sub, jobs.size() - j0);
         for (int f0 = 0; f0 < nf;) {            // one resample launch per run of equal LoD
@@ -692,11 +981,13 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
         }
         int rc = akaze_run(ctx, st, lt, ws, d_tiles, tile_bytes, tile_w * 4, 4, nf, max_points <= 0 ? 0 : max_points);
         if (rc) return rc;
-        k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off);
+        k_frame_offsets<<<1, 1024, 0, st>>>(ws.kp_count, nf, d_off, ws.cand_count);
         DUNK_KERNEL_CHECK(ctx);
-        DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 1) * 4, cudaMemcpyDeviceToHost, st));
+        DUNK_CUDA(cudaMemcpyAsync(h_off.data(), d_off, (size_t)(nf + 2) * 4, cudaMemcpyDeviceToHost, st));
         DUNK_CUDA(cudaMemcpyAsync(h_cnt.data(), ws.kp_count, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
         DUNK_CUDA(cudaStreamSynchronize(st));
+        DUNK_REQUIRE(h_off[nf + 1] <= cap, DUNK_ERR_NO_MEM, "dunk_db_build_from_bands: a tile produced %d raw extrema, candidate capacity %d",
+                     h_off[nf + 1], cap);
         const int rows_new = h_off[nf];
         DUNK_REQUIRE(db->size + rows_new <= db->capacity, DUNK_ERR_NO_MEM, "dunk_db_build_from_bands: %lld + %d rows exceed capacity %lld",
                      (long long)db->size, rows_new, (long long)db->capacity);

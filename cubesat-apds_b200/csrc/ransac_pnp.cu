@@ -137,7 +137,7 @@ __device__ bool solve_minimal(const float* obj, const float* img, const int* idx
 // obj: [total][3] f32, img: [total][2] f32 (already rounded from the caller's f64, as OpenCV does)
 __global__ void __launch_bounds__(kThreads)
 pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ img_all, const int* __restrict__ starts,
-                  const int* __restrict__ counts, const double* __restrict__ K_all, int method, int max_iters, float thr,
+                  const int* __restrict__ counts, const double* __restrict__ K_all, int k_stride, int method, int max_iters, float thr,
                   double confidence, double* __restrict__ rt_out /* [B][6] rvec, tvec */, uint8_t* __restrict__ mask_out,
                   int* __restrict__ info_out /* [B][4]: found, inliers, iterations, hypotheses */) {
     __shared__ Shared sh;
@@ -146,7 +146,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
     const float* obj = obj_all + (size_t)off * 3;
     const float* img = img_all + (size_t)off * 2;
     uint8_t* mask = mask_out + off;
-    const double* Kp = K_all + (size_t)b * 9;
+    const double* Kp = K_all + (size_t)b * k_stride;
     const Camera cam{Kp[0], Kp[4], Kp[2], Kp[5]};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float thr2 = (float)((double)thr * (double)thr);
@@ -322,6 +322,19 @@ pnp_score_kernel(const float* __restrict__ obj, const float* __restrict__ img, i
 }
 
 }  // namespace
+
+// device-resident launcher (pipeline.cu composes it behind the homography stage): obj [total][3] f32, img [total][2] f32,
+// problem b = points [starts[b], starts[b] + counts[b]), camera matrix at K + b * k_stride (k_stride 0: one K for all)
+int launch_pnp_ransac(dunk_ctx* ctx, cudaStream_t st, const float* obj, const float* img, const int* starts, const int* counts,
+                      int n_problems, const double* K, int k_stride, int method, int iters, float thr, double confidence,
+                      double* rt, uint8_t* mask, int* info) {
+    pnp_ransac_kernel<<<n_problems, kThreads, 0, st>>>(obj, img, starts, counts, K, k_stride, method, iters, thr, confidence, rt, mask,
+                                                       info);
+    ctx->launches.fetch_add(1);
+    DUNK_CUDA(cudaGetLastError());
+    return DUNK_OK;
+}
+
 }  // namespace dunk
 
 using namespace dunk;
@@ -375,10 +388,9 @@ int dunk_pnp_ransac_batch(dunk_ctx* ctx, const double* obj, const double* img, c
     DUNK_CUDA(cudaMemcpyAsync(d_K, K, (size_t)n_problems * 72, cudaMemcpyHostToDevice, st));
     {
         ProfScope ps(ctx, st, "ransac.pnp", 0.0);
-        pnp_ransac_kernel<<<n_problems, kThreads, 0, st>>>(d_obj, d_img, d_off, d_cnt, d_K, method, iters, thr, confidence, d_rt, d_mask,
-                                                           d_info);
-        ctx->launches.fetch_add(1);
-        DUNK_CUDA(cudaGetLastError());
+        const int rc = launch_pnp_ransac(ctx, st, d_obj, d_img, d_off, d_cnt, n_problems, d_K, 9, method, iters, thr, confidence, d_rt,
+                                         d_mask, d_info);
+        if (rc) return rc;
     }
     std::vector<double> h_rt((size_t)n_problems * 6);
     DUNK_CUDA(cudaMemcpyAsync(h_rt.data(), d_rt, h_rt.size() * 8, cudaMemcpyDeviceToHost, st));

@@ -123,10 +123,16 @@ class DescriptorDatabase:
         return self._read(level_of_detail=level_of_detail, box=(float(x_start), float(y_start), float(x_end), float(y_end)))
 
     def read_keypoint_from_id(self, id: int) -> np.void:
-        """keypointdb.rs:28-36 — ids are 1 + row index"""
-        if not 1 <= id <= len(self):
+        """keypointdb.rs:28-36 — the `id` column: 1 + row index in a base DB, the source row's id in a
+        `select()` result (looked up through dunk_db_read_ids)"""
+        n = len(self)
+        ids = np.zeros(n, dtype=np.int32)
+        if n:
+            check(_lib.load().dunk_db_read_ids(self.handle, 0, n, ptr(ids)))
+        hit = np.nonzero(ids == id)[0]
+        if hit.size == 0:
             raise NotFound(id)
-        d, k, im = self.read_rows(id - 1, 1)
+        d, k, im = self.read_rows(int(hit[0]), 1)
         out = np.zeros(1, dtype=DB_KEYPOINT_DTYPE)
         out["id"], out["descriptor"], out["image_id"] = id, d, im
         out["x_coord"], out["y_coord"] = k["x"], k["y"]
@@ -143,8 +149,7 @@ class DescriptorDatabase:
         ctx = ctx or _lib.default_context()
         h = C.c_void_p()
         check(_lib.load().dunk_db_load(ctx.handle, str(path).encode(), int(min_capacity), C.byref(h)))
-        db = cls(ctx, _handle=h)
-        return db
+        return cls(ctx, desc_bytes=int(_lib.load().dunk_db_desc_bytes(h)), _handle=h)
 
     @property
     def handle(self):
@@ -223,10 +228,11 @@ class DescriptorDatabase:
         return n.value, (tw.value, th.value)
 
     def register_frames(self, frames: np.ndarray, ratio: float = 0.8, reproj_threshold: float = 3.0,
-                        max_points: int = _lib.MAX_POINTS) -> np.ndarray:
+                        max_points: int = _lib.MAX_POINTS, pose: Optional["PoseStage"] = None):
         """The whole hot path for a frame batch [B, H, W(, C)] u8 against this shard: extract ->
         2-NN + Lowe ratio -> RANSAC homography.  Returns REGISTRATION_DTYPE records (H maps frame
-        pixels to scene pixels)."""
+        pixels to scene pixels); with `pose` (a PoseStage) also POSE_DTYPE records — the attitude from
+        get_world_coordinates + pnp_solver_ransac over the correspondences the homography kept."""
         a = np.asarray(frames)
         if a.ndim == 3:
             a = a[..., None]
@@ -235,9 +241,15 @@ class DescriptorDatabase:
         a = np.ascontiguousarray(a)
         B, rows, cols, ch = a.shape
         out = np.zeros(B, dtype=_lib.REGISTRATION_DTYPE)
-        check(_lib.load().dunk_register_frames(self.handle, ptr(a), B, rows, cols, ch, cols * ch, rows * cols * ch,
-                                               float(ratio), float(reproj_threshold), int(max_points), ptr(out)))
-        return out
+        if pose is None:
+            check(_lib.load().dunk_register_frames(self.handle, ptr(a), B, rows, cols, ch, cols * ch, rows * cols * ch,
+                                                   float(ratio), float(reproj_threshold), int(max_points), ptr(out)))
+            return out
+        poses = np.zeros(B, dtype=_lib.POSE_DTYPE)
+        check(_lib.load().dunk_register_frames_pose(self.handle, ptr(a), B, rows, cols, ch, cols * ch, rows * cols * ch,
+                                                    float(ratio), float(reproj_threshold), int(max_points), C.byref(pose.config),
+                                                    ptr(out), ptr(poses)))
+        return out, poses
 
     def append_random(self, n: int, seed: int, global_row_offset: Optional[int] = None):
         if global_row_offset is None:
@@ -320,6 +332,119 @@ class Geotransform:
         return tuple(float(v) for v in xyz[0])
 
 
+class PoseStage:
+    """Arguments of the pose stage (DunkPoseConfig): the scene's Geotransform (pixel -> ECEF), the camera matrix and the
+    pnp_solver_ransac parameters (homographier mod.rs:320-328: iter_count, reproj_thres, confidence, method)."""
+
+    def __init__(self, geotransform: Geotransform, camera_matrix, origin=(0.0, 0.0, 0.0), iter_count: int = 1000,
+                 reproj_thres: float = 3.0, confidence: float = 0.99, method: int = 1):
+        self.geotransform = geotransform            # keeps the handle alive
+        K = np.ascontiguousarray(camera_matrix, dtype=np.float64).reshape(9)
+        o = np.ascontiguousarray(origin, dtype=np.float64).reshape(3)
+        self.config = _lib.PoseConfig(geotransform._h, (C.c_double * 9)(*K), (C.c_double * 3)(*o), int(method), int(iter_count),
+                                      float(reproj_thres), float(confidence))
+
+
+class ShardGroup:
+    """`dunk_shard_group`: the ranks holding the row-range shards of the reference DB, one process per GPU, NCCL
+    inside the library.  Rank 0 creates the id (`ShardGroup.unique_id()`), the host application
+    hands it to the other ranks, every rank constructs the group (collective)."""
+
+    def __init__(self, ctx: _lib.Context, rank: int, world: int, unique_id: Optional[bytes] = None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        idbuf = None
+        if world > 1:
+            if unique_id is None or len(unique_id) != _lib.SHARD_ID_BYTES:
+                raise DunkError(_lib.ERR_BAD_ARG, "ShardGroup: world > 1 needs rank 0's 128-byte unique id")
+            idbuf = (C.c_uint8 * _lib.SHARD_ID_BYTES).from_buffer_copy(unique_id)
+        check(_lib.load().dunk_shard_group_create(ctx.handle, int(rank), int(world), idbuf, C.byref(h)))
+        self._h, self.rank, self.world = h, int(rank), int(world)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * _lib.SHARD_ID_BYTES)()
+        check(_lib.load().dunk_shard_unique_id(buf))
+        return bytes(buf)
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise DunkError(_lib.ERR_BAD_ARG, "shard group destroyed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.load().dunk_shard_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def balance(self, built: "DescriptorDatabase") -> "DescriptorDatabase":
+        """collective: re-cut the ranks' locally built rows into equal contiguous row ranges; returns this rank's shard"""
+        h = C.c_void_p()
+        check(_lib.load().dunk_shard_group_balance(self.handle, built.handle, C.byref(h)))
+        return DescriptorDatabase(self.ctx, desc_bytes=built.desc_bytes, _handle=h)
+
+    @property
+    def total_rows(self) -> int:
+        return int(_lib.load().dunk_shard_group_total_rows(self.handle))
+
+    def base(self, rank: int) -> int:
+        return int(_lib.load().dunk_shard_group_base(self.handle, int(rank)))
+
+    def match(self, shard: "DescriptorDatabase", query_desc: np.ndarray, ratio: float, index_base: int) -> np.ndarray:
+        """collective get_knn_matches against the sharded DB (host buffers; every rank passes the same queries)"""
+        q = _lib.as_desc(query_desc)
+        out = np.empty(max(q.shape[0], 1), dtype=DMATCH_DTYPE)
+        n = C.c_int(0)
+        check(_lib.load().dunk_db_match_sharded(self.handle, shard.handle, ptr(q), q.shape[0], int(index_base), float(ratio),
+                                                ptr(out), out.shape[0], C.byref(n)))
+        return out[: n.value].copy()
+
+    def register_frames(self, shard: "DescriptorDatabase", frames: np.ndarray, ratio: float = 0.8,
+                        reproj_threshold: float = 3.0, max_points: int = _lib.MAX_POINTS, pose: Optional[PoseStage] = None):
+        """collective: this rank's frame batch [B, H, W(, C)] u8 through extract -> sharded match -> RANSAC (-> PnP)"""
+        lib = _lib.load()
+        a = np.asarray(frames)
+        if a.ndim == 3:
+            a = a[..., None]
+        a = np.ascontiguousarray(a)
+        B, rows, cols, ch = a.shape
+        ctx = self.ctx
+        f_dev = _lib.DeviceBuffer(ctx, a.nbytes)
+        ws_bytes = int(lib.dunk_register_sharded_workspace_bytes(self.handle, B, rows, cols))
+        ws = _lib.DeviceBuffer(ctx, ws_bytes)
+        res_dev = _lib.DeviceBuffer(ctx, B * _lib.REGISTRATION_DTYPE.itemsize)
+        pose_dev = _lib.DeviceBuffer(ctx, B * _lib.POSE_DTYPE.itemsize)
+        res = np.zeros(B, dtype=_lib.REGISTRATION_DTYPE)
+        poses = np.zeros(B, dtype=_lib.POSE_DTYPE)
+        slot = None
+        try:
+            slot = ctx.reserve_slot()
+            f_dev.upload(slot, a)
+            check(lib.dunk_register_frames_sharded_dev(self.handle, shard.handle, slot, C.c_void_p(f_dev.ptr), B, rows, cols, ch,
+                                                       cols * ch, rows * cols * ch, float(ratio), float(reproj_threshold),
+                                                       int(max_points), C.byref(pose.config) if pose else None,
+                                                       C.c_void_p(ws.ptr), ws_bytes, C.c_void_p(res_dev.ptr),
+                                                       C.c_void_p(pose_dev.ptr) if pose else None))
+            res_dev.download(slot, res)
+            if pose:
+                pose_dev.download(slot, poses)
+            ctx.sync(slot)
+        finally:
+            if slot is not None:
+                ctx.sync(slot)
+                ctx.release_slot(slot)
+            for b in (f_dev, ws, res_dev, pose_dev):
+                b.free()
+        return (res, poses) if pose else res
+
+
 def merge_top2(ctx: _lib.Context, parts: Sequence[np.ndarray]) -> np.ndarray:
     """(distance, index)-lexicographic merge of per-shard top-2 records on the GPU — the step
     that follows the allgather in the sharded matcher.  Host arrays in/out."""
@@ -363,12 +488,13 @@ def register_frames_sharded_local(ctx: _lib.Context, shards: Sequence["Descripto
     bases = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     kps_all = torch.empty(int(bases[-1]) * 28, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize(dev)
-    slot = ctx.reserve_slot()
-    for s, b0, n in zip(shards, bases, sizes):
-        if n:
-            check(lib.dunk_memcpy_dev(ctx.handle, slot, kps_all.data_ptr() + int(b0) * 28,
-                                      lib.dunk_db_keypoints_dev(s.handle), n * 28))
+    slot = None
     try:
+        slot = ctx.reserve_slot()
+        for s, b0, n in zip(shards, bases, sizes):
+            if n:
+                check(lib.dunk_memcpy_dev(ctx.handle, slot, kps_all.data_ptr() + int(b0) * 28,
+                                          lib.dunk_db_keypoints_dev(s.handle), n * 28))
         view = _lib.PipelineView()
         check(lib.dunk_pipeline_extract_dev(ctx.handle, slot, f_dev.data_ptr(), B, rows, cols, ch, cols * ch,
                                             rows * cols * ch, int(max_points), ws.data_ptr(), ws_bytes, C.byref(view)))
@@ -383,5 +509,6 @@ def register_frames_sharded_local(ctx: _lib.Context, shards: Sequence["Descripto
                                            ws_bytes, res.data_ptr()))
         ctx.sync(slot)
     finally:
-        ctx.release_slot(slot)
+        if slot is not None:
+            ctx.release_slot(slot)
     return res.cpu().numpy().view(_lib.REGISTRATION_DTYPE).copy()

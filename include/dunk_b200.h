@@ -75,6 +75,7 @@ enum DunkPnPMethod { DUNK_PNP_ITERATIVE = 0, DUNK_PNP_EPNP = 1, DUNK_PNP_P3P = 2
 
 typedef struct dunk_ctx dunk_ctx;
 typedef struct dunk_db dunk_db;
+typedef struct dunk_elevation dunk_elevation;
 
 /* ---- context ------------------------------------------------------------------ */
 int dunk_ctx_create(int device, int n_slots, dunk_ctx** out);
@@ -142,6 +143,7 @@ int dunk_db_append_random(dunk_db* db, int64_t n, uint64_t seed);
  * so the union of the shards equals the unsharded DB whatever the shard count */
 int dunk_db_append_random_at(dunk_db* db, int64_t n, uint64_t seed, uint64_t global_row_offset);
 int64_t dunk_db_size(dunk_db* db);
+int dunk_db_desc_bytes(dunk_db* db);   /* descriptor width of the shard (a loaded dump carries its own) */
 /* forget every keypoint and ref_image row (capacity and device buffers are kept): TRUNCATE keypoint, ref_image */
 int dunk_db_clear(dunk_db* db);
 /* read back rows [first, first+n) (any of the outputs may be NULL) */
@@ -318,7 +320,6 @@ int dunk_raster_to_mat(dunk_ctx* ctx, const uint8_t* rgba, int w, int h, uint8_t
  * EPSG:4326 -> EPSG:4978 (WGS-84 geodetic -> ECEF metres): the object points of pnp_solver_ransac.
  * gt_elevation / heights may be NULL: height 0, as the reference falls back to (:76-79).
  * heights: y_size x x_size f64 (the `elevation` table in row-id order), kept in HBM by the handle. */
-typedef struct dunk_elevation dunk_elevation;
 int dunk_elevation_create(dunk_ctx* ctx, const double* gt_dataset, const double* gt_elevation,
                           const double* heights, int x_size, int y_size, dunk_elevation** out);
 void dunk_elevation_destroy(dunk_elevation* e);
@@ -348,6 +349,34 @@ int dunk_register_frames_dev(dunk_db* db, int slot, const void* images_dev, int 
                              int cols, int channels, int row_stride_bytes, size_t frame_stride_bytes,
                              float ratio, double thr, int max_points, void* workspace_dev,
                              size_t workspace_bytes, void* results_dev);
+/* ---- ... continued to the attitude (north_star stage 3: "RANSAC homography/PnP scoring that yields the attitude
+ * estimate").  The correspondences the homography kept go through geotransform::get_world_coordinates
+ * (feature_database/src/elevationdb.rs:64-104: reference pixel -> geotransform -> elevation sample -> ECEF) and
+ * pnp_solver_ransac (homographier/src/homographier/mod.rs:320-369), all on the device.  The caller's `origin` is
+ * subtracted from the ECEF coordinates in f64 before the f32 rounding OpenCV applies to solvePnPRansac inputs
+ * (|ECEF| = 6.4e6 m would otherwise quantise object points to 0.5 m); tvec is relative to that origin. */
+typedef struct DunkPoseConfig {
+    const dunk_elevation* elevation; /* geotransform + elevation table of the reference scene (dunk_elevation_create) */
+    double K[9];                     /* camera matrix, row-major */
+    double origin[3];                /* ECEF metres subtracted from every object point (zeros: raw ECEF as the reference) */
+    int32_t method;                  /* DunkPnPMethod */
+    int32_t iters;                   /* iter_count (mod.rs:323) */
+    float thr;                       /* reproj_thres */
+    double confidence;
+} DunkPoseConfig;
+typedef struct DunkPose {
+    double rvec[3], tvec[3];         /* zeros when !found */
+    int32_t found, inliers, ransac_iters, hypotheses;
+} DunkPose;
+/* pose == NULL: identical to dunk_register_frames(_dev); otherwise poses (n_frames records) is filled too */
+int dunk_register_frames_pose(dunk_db* db, const uint8_t* images, int n_frames, int rows, int cols, int channels,
+                              int row_stride_bytes, size_t frame_stride_bytes, float ratio, double thr, int max_points,
+                              const DunkPoseConfig* pose, DunkRegistration* results, DunkPose* poses);
+int dunk_register_frames_pose_dev(dunk_db* db, int slot, const void* images_dev, int n_frames, int rows, int cols,
+                                  int channels, int row_stride_bytes, size_t frame_stride_bytes, float ratio,
+                                  double thr, int max_points, const DunkPoseConfig* pose, void* workspace_dev,
+                                  size_t workspace_bytes, void* results_dev, void* poses_dev);
+
 /* ---- the same path with the DB sharded over GPUs (one process per GPU) ----------
  * phase 1 (frame owner): extract + pack the batch's descriptors as 64-B query rows;
  * phase 2 (every shard): dunk_db_knn2_dev of all ranks' query rows against the local shard;
@@ -375,6 +404,54 @@ int dunk_pipeline_finish_dev(dunk_ctx* ctx, int slot, int n_frames, int rows, in
                              int total_queries, const void* db_keypoints_dev, uint32_t index_base,
                              float ratio, double thr, void* workspace_dev, size_t workspace_bytes,
                              void* results_dev);
+/* ---- the shard group: the exchange step inside the library (NCCL over NVLink / NVSwitch) ---------------
+ * One process per GPU; rank 0 calls dunk_shard_unique_id and hands the 128 bytes to the other ranks out of band
+ * (MPI / a file / any rendezvous the host application has); every rank then calls dunk_shard_group_create, which is
+ * ncclCommInitRank.  world == 1 needs no id and no NCCL.  All calls below are COLLECTIVE: every rank of the group
+ * makes the same call with the same sizes. */
+#define DUNK_SHARD_ID_BYTES 128
+typedef struct dunk_shard_group dunk_shard_group;
+int dunk_shard_unique_id(uint8_t* id128);
+int dunk_shard_group_create(dunk_ctx* ctx, int rank, int world, const uint8_t* id128, dunk_shard_group** out);
+void dunk_shard_group_destroy(dunk_shard_group* g);
+int dunk_shard_group_rank(dunk_shard_group* g);
+int dunk_shard_group_world(dunk_shard_group* g);
+int dunk_nccl_version(void);   /* e.g. 22809; 0 when libnccl.so.2 cannot be loaded */
+/* Re-cut the rows the ranks built locally (dunk_db_append_tiles / dunk_db_build_from_bands of each rank's share of the
+ * tiles; global order = rank-major) into `world` equal contiguous row ranges and replicate the 28-byte keypoint column
+ * on every rank (global row -> reference point).  *shard_out: this rank's shard, rows [base(rank), base(rank + 1)). */
+int dunk_shard_group_balance(dunk_shard_group* g, dunk_db* built, dunk_db** shard_out);
+int64_t dunk_shard_group_total_rows(dunk_shard_group* g);
+int64_t dunk_shard_group_base(dunk_shard_group* g, int rank);   /* rank in 0..world (world: total rows) */
+/* get_knn_matches (feature_extraction/src/lib.rs:94-114) against the sharded DB (BASELINE config 3): local top-2 of
+ * the replicated queries on every shard, one ncclAllGather of the 16-byte records, (distance, index) merge, ratio test
+ * after the merge -> identical to the unsharded result incl. ties.  index_base = global row of the shard's row 0.
+ * _dev: nq x 64-B query rows in device memory; outputs (any may be NULL): merged top-2 records, DunkDMatch list + count. */
+int dunk_db_match_sharded(dunk_shard_group* g, dunk_db* shard, const uint8_t* query, int nq, uint32_t index_base,
+                          float ratio, DunkDMatch* out, int out_cap, int* n_out);
+int dunk_db_match_sharded_dev(dunk_shard_group* g, dunk_db* shard, int slot, const void* query64_dev, int nq,
+                              uint32_t index_base, float ratio, void* top2_merged_dev, void* matches_dev,
+                              void* count_dev);
+/* The whole registration step with the DB sharded (BASELINE config 5), ONE call per step and rank: every rank extracts
+ * its own frame batch; the ranks exchange their query counts (one 16-byte ncclAllGather + the step's only host sync,
+ * which the single-GPU path has too), all-gather the query rows padded to the largest count of THIS step, match all
+ * ranks' queries against the local shard in one launch, return the 16-byte top-2 records to the frame owners (grouped
+ * ncclSend / ncclRecv), merge by (distance, index), ratio test, RANSAC homography and, with `pose`, PnP — the last
+ * three partitioned by frame with no collective.  The group must hold the keypoint column (dunk_shard_group_balance). */
+size_t dunk_register_sharded_workspace_bytes(dunk_shard_group* g, int n_frames, int rows, int cols);
+int dunk_register_frames_sharded_dev(dunk_shard_group* g, dunk_db* shard, int slot, const void* images_dev, int n_frames,
+                                     int rows, int cols, int channels, int row_stride_bytes, size_t frame_stride_bytes,
+                                     float ratio, double thr, int max_points, const DunkPoseConfig* pose,
+                                     void* workspace_dev, size_t workspace_bytes, void* results_dev, void* poses_dev);
+/* async copies on a slot's stream for callers that drive the _dev entry points from pinned host buffers */
+int dunk_memcpy_h2d(dunk_ctx* ctx, int slot, void* dst_dev, const void* src_host, size_t nbytes);
+int dunk_memcpy_d2h(dunk_ctx* ctx, int slot, void* dst_host, const void* src_dev, size_t nbytes);
+/* device / pinned-host buffers owned by the caller (so a host application needs no CUDA binding of its own) */
+int dunk_dev_alloc(dunk_ctx* ctx, size_t nbytes, void** out_dev);
+int dunk_dev_free(dunk_ctx* ctx, void* dev);
+int dunk_host_alloc(dunk_ctx* ctx, size_t nbytes, void** out_host);
+int dunk_host_free(dunk_ctx* ctx, void* host);
+
 /* append n rows whose columns already live on the device (64-B descriptor rows, DunkKeyPoint,
  * int32 image ids; the last two may be NULL) — used to re-cut shards into equal row ranges */
 int dunk_db_append_dev(dunk_db* db, int slot, const void* desc64_dev, const void* kps_dev,

@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ by running the reference's OpenCV entry
 points (through cv2, the same C++ library the `opencv` crate binds) with the reference's exact
-arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|lmeds|akaze|pnp|pnp_iter|warp|l2|all]
+arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|lmeds|akaze|config1|pnp|pnp_iter|warp|l2|all]
 The OpenCV version is recorded in every file (parity is defined against that version)."""
 import os
 import sys
@@ -164,6 +164,32 @@ def make_akaze():
     print("akaze_golden.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_config1():
+    """BASELINE config 1 at FULL size: g = synth(1024, 0), w = warpPerspective(g, H_TRUE) with the reference's
+    warp settings (mod.rs:286-294); extract both (lib.rs:64-79), knnMatch(w -> g, 2) + ratio in {0.3, 0.7, 0.8}
+    (lib.rs:101-111), findHomography(RANSAC, 3.0) (mod.rs:243-250).  Expected [probe]: 3163 / 3033 keypoints,
+    1347 / 2269 / 2377 matches.  The 1024^2 images exercise octave 3 and its 17/20/24/29-step FED chains."""
+    g = synth(1024, 0)
+    w = cv2.warpPerspective(g, H_TRUE, (1024, 1024), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=1)
+    kg, dg = akaze_cv(g)
+    kw, dw = akaze_cv(w)
+    idx, dist = knn_cv(dw, dg)
+    out = {"opencv_version": np.array(cv2.__version__), "g_img": g, "w_img": w, "g_kps": kg, "g_desc": dg, "w_kps": kw,
+           "w_desc": dw, "knn_idx": idx, "knn_dist": dist}
+    for ratio in (0.3, 0.7, 0.8):
+        keep = dist[:, 0].astype(np.float32) < dist[:, 1].astype(np.float32) * np.float32(ratio)
+        qi = np.nonzero(keep)[0]
+        src = np.stack([kg["x"][idx[qi, 0]], kg["y"][idx[qi, 0]]], 1).astype(np.float32)      # tile points
+        dst = np.stack([kw["x"][qi], kw["y"][qi]], 1).astype(np.float32)                      # warped-image points
+        H, mask = cv2.findHomography(src, dst, cv2.RANSAC, 3.0)
+        tag = f"r{int(ratio * 10)}"
+        out[f"{tag}_query"], out[f"{tag}_H"], out[f"{tag}_mask"] = qi.astype(np.int32), H, mask.ravel().astype(np.uint8)
+        print(f"config1 ratio {ratio}: {len(qi)} matches, {int(mask.sum())} inliers, H err "
+              f"{np.abs(H - H_TRUE).max() / np.abs(H_TRUE).max():.2e}")
+    print("config1:", len(kg), "/", len(kw), "keypoints")
+    np.savez_compressed(os.path.join(HERE, "config1_golden.npz"), **out)
+
+
 PNP_K = np.array([[800., 0, 512], [0, 820., 500], [0, 0, 1]])
 # (n, outlier fraction, pixel noise sigma, iterations, reprojection threshold, confidence, relief)
 PNP_CASES = [(100, 0.3, 0.5, 100, 8.0, 0.99, "cube"), (1000, 0.4, 0.5, 1000, 2.0, 0.99, "cube"),
@@ -295,6 +321,8 @@ if __name__ == "__main__":
         make_lmeds()
     if what in ("akaze", "all") and "make_akaze" in globals():
         make_akaze()
+    if what in ("config1", "all"):
+        make_config1()
     if what in ("pnp", "all") and "make_pnp" in globals():
         make_pnp()
     if what in ("pnp_iter", "all") and "make_pnp_iter" in globals():
