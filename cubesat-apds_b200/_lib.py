@@ -151,6 +151,7 @@ SIGNATURES = {
     "dunk_db_append_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.c_size_t, _vp, _vp, _vp, _vp, _i, _vp]),
     "dunk_db_build_from_bands": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _pi, _pi, _pi]),
     "dunk_db_build_from_bands_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _pi, _pi, _pi]),
+    "dunk_db_build_from_bands_part_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _pi, _pi, _pi]),
     "dunk_find_homography": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _pi]),
     "dunk_find_homography_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
     "dunk_ransac_score_hypotheses": (_i, [_vp, _vp, _vp, _i, _vp, _i, _d, _vp, _vp]),

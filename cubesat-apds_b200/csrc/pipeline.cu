@@ -902,7 +902,8 @@ namespace {
 // bands_on_device: red/green/blue are device pointers (the scene already in HBM); otherwise host pointers copied in first
 int build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue, bool bands_on_device, int width, int height,
                      const double* min_max, int lods, int resample, int max_points, int* n_tiles_out, int* tile_w_out,
-                     int* tile_h_out) {
+                     int* tile_h_out, int part = 0, int n_parts = 1) {
+    DUNK_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: part %d of %d", part, n_parts);
     DUNK_REQUIRE(db && red && green && blue && min_max, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: NULL argument");
     DUNK_REQUIRE(lods >= 1 && lods <= 5, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: lods=%d (1..5)", lods);
     DUNK_REQUIRE(resample == 0 || resample == 1, DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: resample %d (0 = area, 1 = Lanczos-3)", resample);
@@ -958,12 +959,23 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
         DUNK_REQUIRE(make_taps(scale, resample, &taps), DUNK_ERR_BAD_ARG, "dunk_db_build_from_bands: decimation %d too large", scale);
         for (int t = 0; t < tiles_x * tiles_y; ++t) jobs.push_back({lod, t, tiles_x});
     }
+    // every part inserts ALL ref_image rows (InsertImage, main.rs:283-289; ids follow the walk order, so they agree
+    // across the ranks of a partitioned build) and extracts only its contiguous share of the tiles
+    const int32_t id_base = (int32_t)db->images.size();
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        const TileJob& jb = jobs[j];
+        const int scale = 1 << jb.lod, col = jb.t % jb.tiles_x, row = jb.t / jb.tiles_x;
+        const int xs = col * tile_w * scale, ys = row * tile_h * scale;
+        db->images.push_back(DunkImage{id_base + (int32_t)j + 1, xs, ys, xs + tile_w * scale - 1, ys + tile_h * scale - 1, jb.lod});
+    }
+    db->image_lod_dirty = true;
+    const size_t j_begin = jobs.size() * (size_t)part / n_parts, j_end = jobs.size() * (size_t)(part + 1) / n_parts;
     const float* thr = gamma_table(ctx, st);
     DUNK_REQUIRE(thr, DUNK_ERR_CUDA, "dunk_db_build_from_bands: gamma table");
     int n_tiles = 0;
     std::vector<int> h_off(sub + 2), h_cnt(sub);
-    for (size_t j0 = 0; j0 < jobs.size(); j0 += sub) {
-        const int nf = (int)std::min<size_t>(sub, jobs.size() - j0);
+    for (size_t j0 = j_begin; j0 < j_end; j0 += sub) {
+        const int nf = (int)std::min<size_t>(sub, j_end - j0);
         for (int f0 = 0; f0 < nf;) {            // one resample launch per run of equal LoD
             int f1 = f0;
             while (f1 < nf && jobs[j0 + f1].lod == jobs[j0 + f0].lod) ++f1;
@@ -998,14 +1010,10 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
             const TileJob& jb = jobs[j0 + f];
             const int scale = 1 << jb.lod, col = jb.t % jb.tiles_x, row = jb.t / jb.tiles_x;
             const int xs = col * tile_w * scale, ys = row * tile_h * scale;
-            // InsertImage, main.rs:283-289
-            DunkImage im{(int32_t)db->images.size() + 1, xs, ys, xs + tile_w * scale - 1, ys + tile_h * scale - 1, jb.lod};
-            db->images.push_back(im);
-            ids[f] = im.id;
+            ids[f] = id_base + (int32_t)(j0 + f) + 1;
             xo[f] = (float)xs; yo[f] = (float)ys; sc[f] = (float)scale;
             maxc = std::max(maxc, h_cnt[f]);
         }
-        db->image_lod_dirty = true;
         DUNK_CUDA(cudaMemcpyAsync(d_xo, xo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
         DUNK_CUDA(cudaMemcpyAsync(d_yo, yo.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
         DUNK_CUDA(cudaMemcpyAsync(d_sc, sc.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
@@ -1030,6 +1038,14 @@ extern "C" int dunk_db_build_from_bands(dunk_db* db, const float* red, const flo
                                         int* tile_w_out, int* tile_h_out) {
     return dunk::build_from_bands(db, red, green, blue, false, width, height, min_max, lods, resample, max_points, n_tiles_out,
                                   tile_w_out, tile_h_out);
+}
+
+extern "C" int dunk_db_build_from_bands_part_dev(dunk_db* db, const void* red_dev, const void* green_dev, const void* blue_dev,
+                                                 int width, int height, const double* min_max, int lods, int resample,
+                                                 int max_points, int part, int n_parts, int* n_tiles_out, int* tile_w_out,
+                                                 int* tile_h_out) {
+    return dunk::build_from_bands(db, (const float*)red_dev, (const float*)green_dev, (const float*)blue_dev, true, width, height,
+                                  min_max, lods, resample, max_points, n_tiles_out, tile_w_out, tile_h_out, part, n_parts);
 }
 
 extern "C" int dunk_db_build_from_bands_dev(dunk_db* db, const void* red_dev, const void* green_dev, const void* blue_dev, int width,

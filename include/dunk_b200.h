@@ -485,6 +485,14 @@ int dunk_db_build_from_bands_dev(dunk_db* db, const void* red_dev, const void* g
                                  int width, int height, const double* min_max, int lods, int resample,
                                  int max_points, int* n_tiles_out, int* tile_w_out, int* tile_h_out);
 
+/* one part of a build partitioned over ranks (tiles are independent, preprocessor/src/main.rs:258-277: no halo, no
+ * collective): part p of n_parts extracts the contiguous share [jobs*p/n, jobs*(p+1)/n) of the lod-major tile walk and
+ * inserts ALL ref_image rows, so image ids agree across ranks; follow with dunk_shard_group_balance */
+int dunk_db_build_from_bands_part_dev(dunk_db* db, const void* red_dev, const void* green_dev, const void* blue_dev,
+                                      int width, int height, const double* min_max, int lods, int resample,
+                                      int max_points, int part, int n_parts, int* n_tiles_out, int* tile_w_out,
+                                      int* tile_h_out);
+
 /* ---- roofline denominators measured on the box ---------------------------------------- */
 /* per-kernel-class device times: between begin and end every launch site brackets its kernels
  * with CUDA events on the launching stream.  end() returns the number of classes n and fills

@@ -40,6 +40,18 @@ def resample_window(band, x0, y0, tile_w, tile_h, scale, resample):
     H, W = band.shape
     if scale == 1:
         return band[y0:y0 + tile_h, x0:x0 + tile_w].copy()
+    if resample == "area" and x0 + tile_w * scale <= W and y0 + tile_h * scale <= H:
+        # box mean of an interior window: the same sequential f64 sums as the general path below (unit weights,
+        # taps kx = 0..scale-1 then ky = 0..scale-1), formed with strided slices instead of per-tap gathers
+        win = band[y0:y0 + tile_h * scale, x0:x0 + tile_w * scale].astype(np.float64)
+        rows = np.zeros((tile_h * scale, tile_w))
+        for kx in range(scale):
+            rows = rows + win[:, kx::scale]
+        rows = rows / float(scale)
+        out = np.zeros((tile_h, tile_w))
+        for ky in range(scale):
+            out = out + rows[ky::scale]
+        return (out / float(scale)).astype(np.float32)
     first, w = taps(scale, resample)
     cx = x0 + np.arange(tile_w) * scale + scale // 2
     cy = y0 + np.arange(tile_h) * scale + scale // 2
