@@ -301,10 +301,8 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
     }
 }
 
-bool g_tables_ready = false;
-
-int upload_tables() {
-    if (g_tables_ready) return DUNK_OK;
+// __device__ / __constant__ symbols exist once per DEVICE: uploaded by dunk_ctx_create on the context's device
+int upload_tables(dunk_ctx*) {
     OriTable t;
     int k = 0;
     for (int i = -6; i <= 6; ++i)
@@ -342,15 +340,13 @@ int upload_tables() {
     unsigned short ab[512] = {0};
     for (int i = 0; i < 486; ++i) ab[i] = (unsigned short)(a[i] | (b[i] << 8));
     DUNK_CUDA(cudaMemcpyToSymbol(g_cmp, ab, sizeof ab));
-    g_tables_ready = true;
     return DUNK_OK;
 }
+DeviceInitReg desc_tables_reg(upload_tables);
 
 }  // namespace
 
 int akaze_describe(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt, const AkazeWorkspace& ws, int frames) {
-    int rc = upload_tables();
-    if (rc) return rc;
     const LevelsDev lv = make_levels_dev(lt);
     const dim3 grid(div_up(ws.kp_cap, kWarpsPerBlock), frames);
     {

@@ -75,8 +75,11 @@ def main():
         i1, d1 = dunk.feature_extraction.knn2(a, b, c1)
         e0 = dunk.feature_extraction.akaze_keypoint_descriptor_extraction_def(tiles[3], None, ctx)
         e1 = dunk.feature_extraction.akaze_keypoint_descriptor_extraction_def(tiles[3], None, c1)
-        two = np.array_equal(i0, i1) and np.array_equal(d0, d1) and e0.keypoints.tobytes() == e1.keypoints.tobytes()
-        print("contexts on two devices in one process agree:", two)
+        knn_same = np.array_equal(i0, i1) and np.array_equal(d0, d1)
+        kp_same = e0.keypoints.tobytes() == e1.keypoints.tobytes()
+        desc_same = e0.descriptors.tobytes() == e1.descriptors.tobytes()
+        two = knn_same and kp_same and desc_same and len(e0.keypoints) > 100
+        print(f"contexts on two devices in one process agree: {two} (knn {knn_same}, keypoints {kp_same}, descriptors {desc_same})")
         ok = ok and two
         c1.close()
     flag = torch.tensor([1 if ok else 0], device=torch.device("cuda", local))
