@@ -227,6 +227,51 @@ __device__ void jacobi_eigen(double* A, double* V, double* w, int n) {
     for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
 }
 
+// The same cyclic Jacobi run by ONE WARP on matrices in shared memory: lane k owns element k of the two rows /
+// columns a rotation touches, so a rotation is three warp-wide steps instead of 3 n serial round trips through
+// shared memory (the single-thread version was the critical path of the refit + LM tail: ~100 cycles per element).
+// Every element goes through exactly the arithmetic of jacobi_eigen, in the same order -> identical bits.
+// All 32 lanes must call it; n <= 32.
+__device__ void jacobi_eigen_warp(double* A, double* V, double* w, int n) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n * n; i += 32) V[i] = (i / n == i % n);
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0, diag = 0;                      // every lane sums in the serial order (broadcast reads)
+        for (int p = 0; p < n; ++p) {
+            diag += A[p * n + p] * A[p * n + p];
+            for (int q = p + 1; q < n; ++q) off += A[p * n + q] * A[p * n + q];
+        }
+        if (off <= 1e-32 * diag || off == 0) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[p * n + q];
+                if (apq == 0) continue;                // uniform: every lane read the same value
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                __syncwarp();                          // all lanes hold c, s before anything is overwritten
+                if (lane < n) {                        // columns p, q
+                    const double akp = A[lane * n + p], akq = A[lane * n + q];
+                    A[lane * n + p] = c * akp - s * akq;
+                    A[lane * n + q] = s * akp + c * akq;
+                }
+                __syncwarp();
+                if (lane < n) {                        // rows p, q of A and of V
+                    const double apk = A[p * n + lane], aqk = A[q * n + lane];
+                    A[p * n + lane] = c * apk - s * aqk;
+                    A[q * n + lane] = s * apk + c * aqk;
+                    const double vpk = V[p * n + lane], vqk = V[q * n + lane];
+                    V[p * n + lane] = c * vpk - s * vqk;
+                    V[q * n + lane] = s * vpk + c * vqk;
+                }
+                __syncwarp();
+            }
+    }
+    for (int i = lane; i < n; i += 32) w[i] = A[i * n + i];
+    __syncwarp();
+}
+
 // x = V^T diag(1/w) V b with OpenCV's SVBkSb threshold (2*eps*sum|w|): cv::solve(DECOMP_EIG)
 __device__ void eig_backsolve(const double* V, const double* w, const double* b, double* x, int n) {
     double thr = 0;
@@ -329,15 +374,20 @@ __device__ bool dlt_refit(Shared& sh, const float2* __restrict__ src, const floa
                 for (int b = a; b < 9; ++b) L[k++] += Lx[a] * Lx[b] + Ly[a] * Ly[b];
         }
     block_reduce<45>(L, sh.red_buf, sh.red);
+    if (tid < 32) {
+        if (tid == 0) {
+            int k = 0;
+            for (int a = 0; a < 9; ++a)
+                for (int b = a; b < 9; ++b) {
+                    sh.A[a * 9 + b] = sh.red[k];
+                    sh.A[b * 9 + a] = sh.red[k];
+                    ++k;
+                }
+        }
+        __syncwarp();
+        jacobi_eigen_warp(sh.A, sh.V, sh.w, 9);
+    }
     if (tid == 0) {
-        int k = 0;
-        for (int a = 0; a < 9; ++a)
-            for (int b = a; b < 9; ++b) {
-                sh.A[a * 9 + b] = sh.red[k];
-                sh.A[b * 9 + a] = sh.red[k];
-                ++k;
-            }
-        jacobi_eigen(sh.A, sh.V, sh.w, 9);
         int mi = 0;
         for (int i = 1; i < 9; ++i)
             if (sh.w[i] < sh.w[mi]) mi = i;
@@ -436,8 +486,9 @@ template <class Use>
 __device__ void lm_refine(Shared& sh, const float2* __restrict__ src, const float2* __restrict__ dst,
                           int n, Use use) {
     const int tid = threadIdx.x;
-    __shared__ double S, Sd, lambda, lc, maxd;
-    __shared__ int proceed;
+    __shared__ double S, Sd, lambda, lc, maxd, nu_s;
+    __shared__ int proceed, need_inv;
+    if (tid == 0) need_inv = 0;
     auto load_normal_eq = [&]() {  // red -> JtJ, v, S   (thread 0)
         int k = 0;
         for (int p = 0; p < 8; ++p)
@@ -460,10 +511,14 @@ __device__ void lm_refine(Shared& sh, const float2* __restrict__ src, const floa
     }
     __syncthreads();
     for (int iter = 0; iter < 10;) {
+        if (tid < 32) {
+            for (int i = tid; i < 64; i += 32) sh.Ap[i] = sh.JtJ[i];
+            __syncwarp();
+            if (tid < 8) sh.Ap[tid * 8 + tid] += lambda * sh.D[tid];
+            __syncwarp();
+            jacobi_eigen_warp(sh.Ap, sh.V, sh.w, 8);
+        }
         if (tid == 0) {
-            for (int i = 0; i < 64; ++i) sh.Ap[i] = sh.JtJ[i];
-            for (int p = 0; p < 8; ++p) sh.Ap[p * 8 + p] += lambda * sh.D[p];
-            jacobi_eigen(sh.Ap, sh.V, sh.w, 8);
             eig_backsolve(sh.V, sh.w, sh.v, sh.d, 8);
             double md = 0;
             for (int p = 0; p < 8; ++p) {
@@ -490,10 +545,22 @@ __device__ void lm_refine(Shared& sh, const float2* __restrict__ src, const floa
             } else if (R < 0.25) {
                 double nu = (Sd - S) / (fabs(t) > DBL_EPSILON ? t : 1.0) + 2.0;
                 nu = fmin(fmax(nu, 2.0), 10.0);
-                if (lambda == 0) {
-                    // invert(A, DECOMP_EIG): diag of V^T diag(1/w) V
-                    for (int i = 0; i < 64; ++i) sh.Ap[i] = sh.JtJ[i];
-                    jacobi_eigen(sh.Ap, sh.V, sh.w, 8);
+                nu_s = nu;
+                if (lambda == 0) need_inv = 1;
+                else lambda *= nu;
+            }
+        }
+        __syncthreads();
+        if (need_inv) {                                // block-uniform (shared flag)
+            if (tid < 32) {
+                // invert(A, DECOMP_EIG): diag of V^T diag(1/w) V
+                for (int i = tid; i < 64; i += 32) sh.Ap[i] = sh.JtJ[i];
+                __syncwarp();
+                jacobi_eigen_warp(sh.Ap, sh.V, sh.w, 8);
+            }
+            if (tid == 0) {
+                {
+                    double nu = nu_s;
                     double thr = 0;
                     for (int i = 0; i < 8; ++i) thr += fabs(sh.w[i]);
                     thr *= 2 * DBL_EPSILON;
@@ -506,11 +573,12 @@ __device__ void lm_refine(Shared& sh, const float2* __restrict__ src, const floa
                     }
                     lambda = lc = 1.0 / maxval;
                     nu *= 0.5;
+                    lambda *= nu;
                 }
-                lambda *= nu;
+                need_inv = 0;
             }
+            __syncthreads();
         }
-        __syncthreads();
         const bool improved = Sd < S;
         if (improved) {
             if (tid < 8) sh.x[tid] = sh.xd[tid];

@@ -3,9 +3,12 @@
 Restates the SQL the reference issues through diesel (feature_database/src/keypointdb.rs:38-90,
 src/imagedb.rs:39-66) over in-memory numpy columns: WHERE clause, inner join on ref_image for the
 level of detail, ORDER BY response DESC (ties: ascending row id — Postgres leaves them unspecified),
-LIMIT 2^18 - 1.  No golden vectors exist for this path in the reference (its DB tests need a live
-Postgres, feature_database/src/lib.rs tests are `#[ignore]`-style integration tests): parity
-unpinned by the reference, the semantics are the SQL text itself.
+LIMIT 2^18 - 1.  The reference holds no golden vectors for this path (its DB tests need a live Postgres).
+PINNED instead against a real SQL engine: tests/test_oracle_db_sql.py creates the tables of the reference's
+migrations (ref_image, keypoint) in sqlite3 and runs the same statements (join on the foreign key, bounds
+floor()/ceil()-ed as keypointdb.rs:80-83 binds them, ORDER BY response DESC, LIMIT); result sets are identical
+(rows of equal response compared as sets — SQL leaves their order unspecified, the oracle and the device use
+ascending row id).
 """
 import numpy as np
 
