@@ -1,5 +1,8 @@
 // C ABI for stage 1 (AKAZE extraction) + workspace management.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "akaze.h"
 #include "match.h"
@@ -146,12 +149,18 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
 
     const LevelTable lt = make_level_table(cols, rows);
     int cand_cap = default_cand_cap(cols, rows);
+    static const bool trace = getenv("DUNK_TRACE") != nullptr;     // host-side phase times on stderr (diagnostics)
+    auto ms_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
     SlotGuard g(ctx);
     cudaStream_t st = g.stream();
     size_t free_b = 0, total_b = 0;
     DUNK_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)8 << 30);
     cudaEvent_t done[2] = {g.slot().ev0, g.slot().ev1};
+    cudaEvent_t copied[2] = {g.slot().ev2, g.slot().ev3};
+    const auto t_entry = std::chrono::steady_clock::now();
     int f0 = 0;
     // The raw-candidate capacity (w*h/32 by default) is exceeded only by pathological textures (random 4x4 blocks
     // reach w*h/29); k_extrema keeps counting past the capacity, so on overflow the sub-batch is simply re-run
@@ -186,12 +195,19 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
         auto d_off = [&](int h) { return (int*)(d_out + h * out_half + al(out_rows * 61) + al(out_rows * sizeof(DunkKeyPoint))); };
         auto h_off = [&](int h) { return (int*)(pin + pin_off + h * al((size_t)(sub + 2) * 4)); };
         bool overflow = false;
+        cudaStream_t st2 = g.slot().stream2;      // copies in both directions run beside the kernels of the other half
         // stage sub-batch starting at frame `fs` into half h (asynchronous after the host memcpy)
         auto stage = [&](int fs, int h) -> int {
             const int nf = std::min(sub, n_frames - fs);
             const size_t in_bytes = (size_t)nf * frame_stride_bytes;
+            const auto t0 = std::chrono::steady_clock::now();
             par_memcpy(pin + h * in_half, images + (size_t)fs * frame_stride_bytes, in_bytes);
-            DUNK_CUDA(cudaMemcpyAsync(d_in + h * in_half, pin + h * in_half, in_bytes, cudaMemcpyHostToDevice, st));
+            if (trace) fprintf(stderr, "[dunk] +%.1f ms stage %d: memcpy %.1f MB in %.2f ms\n", ms_since(t_entry), fs, in_bytes / 1e6, ms_since(t0));
+            // the copy rides the slot's second stream so that it overlaps the previous sub-batch's kernels; the
+            // compute stream waits for it (the input half was released when sub-batch i - 1 finished, see below)
+            DUNK_CUDA(cudaMemcpyAsync(d_in + h * in_half, pin + h * in_half, in_bytes, cudaMemcpyHostToDevice, st2));
+            DUNK_CUDA(cudaEventRecord(copied[h], st2));
+            DUNK_CUDA(cudaStreamWaitEvent(st, copied[h], 0));
             int rc = akaze_run(ctx, st, lt, ws, d_in + h * in_half, frame_stride_bytes, row_stride_bytes, channels, nf, max_points);
             if (rc) return rc;
             if ((rc = launch_pack_outputs(ctx, st, ws, nf, d_off(h), d_kps(h), d_desc61(h)))) return rc;
@@ -201,18 +217,20 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
         };
         int rc = stage(f0, 0);
         if (rc) return rc;
-        cudaStream_t st2 = g.slot().stream2;      // output copies run beside the next sub-batch's kernels
         for (int h = 0; f0 < n_frames && !overflow; h ^= 1) {
             const int nf = std::min(sub, n_frames - f0);
             const int next = f0 + nf;
             // host stages sub-batch i + 1 while the device runs sub-batch i (its pinned half and packed-output half
             // were released when sub-batch i - 1 was unpacked)
             if (next < n_frames && (rc = stage(next, h ^ 1))) return rc;
+            const auto tw = std::chrono::steady_clock::now();
             DUNK_CUDA(cudaEventSynchronize(done[h]));
+            if (trace) fprintf(stderr, "[dunk] sub-batch %d: waited %.2f ms for the device\n", f0, ms_since(tw));
             const int* off = h_off(h);
             if (off[nf + 1] > cand_cap) {              // re-run from this sub-batch with a larger candidate capacity
                 DUNK_REQUIRE(off[nf + 1] <= (1 << 22), DUNK_ERR_NO_MEM, "dunk_akaze_extract: %d raw extrema in one frame", off[nf + 1]);
                 DUNK_CUDA(cudaStreamSynchronize(st));
+                DUNK_CUDA(cudaStreamSynchronize(st2));
                 cand_cap = off[nf + 1] + off[nf + 1] / 4;
                 overflow = true;
                 break;
@@ -227,6 +245,7 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
             if (total > 0) {
                 if ((size_t)total * 89 > pin_out_cap) {     // denser than typical: grow the pinned block (rare, slow path)
                     DUNK_CUDA(cudaStreamSynchronize(st));
+                    DUNK_CUDA(cudaStreamSynchronize(st2));
                     std::vector<int> keep0(h_off(0), h_off(0) + sub + 2), keep1(h_off(1), h_off(1) + sub + 2);
                     pin_out_cap = (size_t)total * 89 * 2;
                     pin = (unsigned char*)ctx->pin_scratch(g.s, pin_out + pin_out_cap);
@@ -239,18 +258,23 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
                 uint8_t* p_desc = (uint8_t*)(p_kps + total);
                 DUNK_CUDA(cudaMemcpyAsync(p_kps, d_kps(h), (size_t)total * sizeof(DunkKeyPoint), cudaMemcpyDeviceToHost, st2));
                 DUNK_CUDA(cudaMemcpyAsync(p_desc, d_desc61(h), (size_t)total * 61, cudaMemcpyDeviceToHost, st2));
+                const auto td = std::chrono::steady_clock::now();
                 DUNK_CUDA(cudaStreamSynchronize(st2));
+                const double d2h_ms = ms_since(td);
+                const auto tu = std::chrono::steady_clock::now();
                 for (int f = 0; f < nf; ++f) {
                     const int n = off[f + 1] - off[f];
                     if (n == 0) continue;
                     memcpy(kps + (size_t)(f0 + f) * cap_per_frame, p_kps + off[f], (size_t)n * sizeof(DunkKeyPoint));
                     memcpy(desc + (size_t)(f0 + f) * cap_per_frame * 61, p_desc + (size_t)off[f] * 61, (size_t)n * 61);
                 }
+                if (trace) fprintf(stderr, "[dunk] sub-batch %d: D2H %.1f MB in %.2f ms, unpack %.2f ms\n", f0, total * 89 / 1e6, d2h_ms, ms_since(tu));
             }
             f0 = next;
         }
         DUNK_CUDA(cudaStreamSynchronize(st));
     }
+    if (trace) fprintf(stderr, "[dunk] +%.1f ms done\n", ms_since(t_entry));
     return DUNK_OK;
 }
 

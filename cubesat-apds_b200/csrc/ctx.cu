@@ -20,8 +20,9 @@ void set_error(const char* fmt, ...) {
 }
 
 void par_memcpy(void* dst, const void* src, size_t n) {
-    const size_t kMin = (size_t)8 << 20;
-    const int parts = (int)std::min<size_t>(4, n / kMin);
+    const size_t kMin = (size_t)4 << 20;
+    static const int max_threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    const int parts = (int)std::min<size_t>((size_t)max_threads, n / kMin);
     if (parts <= 1) {
         memcpy(dst, src, n);
         return;
@@ -167,6 +168,8 @@ int dunk_ctx_create(int device, int n_slots, dunk_ctx** out) {
         DUNK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         DUNK_CUDA(cudaEventCreate(&s.ev0));
         DUNK_CUDA(cudaEventCreate(&s.ev1));
+        DUNK_CUDA(cudaEventCreateWithFlags(&s.ev2, cudaEventDisableTiming));
+        DUNK_CUDA(cudaEventCreateWithFlags(&s.ev3, cudaEventDisableTiming));
         DUNK_CUDA(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
     }
     for (dunk::DeviceInitFn fn : dunk::device_init_hooks()) {
@@ -190,6 +193,8 @@ void dunk_ctx_destroy(dunk_ctx* c) {
         if (s.ring) cudaFreeHost(s.ring);
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.ev2) cudaEventDestroy(s.ev2);
+        if (s.ev3) cudaEventDestroy(s.ev3);
         if (s.stream2) { cudaStreamSynchronize(s.stream2); cudaStreamDestroy(s.stream2); }
         if (s.stream) cudaStreamDestroy(s.stream);
     }

@@ -12,7 +12,7 @@
 namespace dunk {
 
 void set_error(const char* fmt, ...);
-// host memcpy on up to 4 threads (a single core moves ~10 GB/s, less than PCIe 5 or the kernels consume)
+// host memcpy on up to 8 threads (a single core moves 5-10 GB/s, less than PCIe 5 or the kernels consume)
 void par_memcpy(void* dst, const void* src, size_t n);
 
 // One stream + growable device / pinned-host scratch.  A host-API call owns exactly one
@@ -25,7 +25,7 @@ struct Slot {
     void* pin = nullptr;
     size_t pin_bytes = 0;
     void* ring = nullptr;             // 2 x 64 MB pinned halves of upload_pageable
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     bool busy = false;
 };
 
@@ -145,5 +145,21 @@ struct Carver {
     } while (0)
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Phase timestamps of the latency-bound tail kernels (RANSAC homography, PnP): compiled in only for the
+// `make timing` variant (libdunk_b200_timing.so, tools/phase_times.py); a no-op in the product build.
+#if defined(DUNK_PHASE_TIMING) && defined(__CUDACC__)
+static __device__ long long g_phase[64];     // one copy per translation unit (no relocatable device code)
+#endif
+#if defined(DUNK_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define DUNK_PHASE(k)                                                     \
+    do {                                                                  \
+        if (blockIdx.x == 0 && threadIdx.x == 0) g_phase[k] = clock64();  \
+    } while (0)
+#else
+#define DUNK_PHASE(k) \
+    do {              \
+    } while (0)
+#endif
 
 }  // namespace dunk

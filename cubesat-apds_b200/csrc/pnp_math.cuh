@@ -17,6 +17,12 @@
 #else
 #define DUNK_HD
 #endif
+// phase stamps exist only in the `make timing` build (ctx.h); the host check compiles this header alone
+#ifndef DUNK_PHASE
+#define DUNK_PHASE(k) \
+    do {              \
+    } while (0)
+#endif
 
 namespace dunk {
 namespace pnp {
@@ -258,6 +264,7 @@ DUNK_HD inline void rodrigues_to_vector(const double* Rin, double* r) {
 
 // One thread owns the whole point set: `idx` (may be null = identity) selects `n` points.
 struct SerialExec {
+    static constexpr bool kBlock = false;
     const float* obj;
     const float* img;
     const int* idx;
@@ -302,6 +309,7 @@ DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], dou
             for (int j = 0; j < 3; ++j) cws[i][j] = cws[0][j] + k * At[3 * (i - 1) + j];
         }
     }
+    if (Exec::kBlock) DUNK_PHASE(6);
     // ---- compute_barycentric_coordinates: alphas[1..3] = CC^-1 (pw - cw0)
     double ci[9];
     {
@@ -343,7 +351,9 @@ DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], dou
                 ++k;
             }
         double d[12];
+        if (Exec::kBlock) DUNK_PHASE(7);
         jacobi_svd<12, 12, false>(ut, d, nullptr);
+        if (Exec::kBlock) DUNK_PHASE(8);
     }
     const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
     // ---- compute_L_6x10, compute_rho
@@ -361,6 +371,7 @@ DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], dou
         for (int j = 0; j < 3; ++j) d2 += (cws[pa[p]][j] - cws[pb[p]][j]) * (cws[pa[p]][j] - cws[pb[p]][j]);
         rho[p] = d2;
     }
+    if (Exec::kBlock) DUNK_PHASE(9);
     // ---- betas: three approximations, each refined by 5 Gauss-Newton steps
     double betas[3][4];
     {   // find_betas_approx_1: columns 0 1 3 6 (B11 B12 B13 B14)
@@ -393,6 +404,7 @@ DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], dou
         be[2] = b5[3] / be[0];
         be[3] = 0.0;
     }
+    if (Exec::kBlock) DUNK_PHASE(10);
     double ccs[3][4][3];   // candidate, control point, xyz
     for (int c = 0; c < 3; ++c) {
         double* be = betas[c];
@@ -415,6 +427,7 @@ DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], dou
             for (int k = 0; k < 3; ++k)
                 ccs[c][j][k] = be[0] * v[0][3 * j + k] + be[1] * v[1][3 * j + k] + be[2] * v[2][3 * j + k] + be[3] * v[3][3 * j + k];
     }
+    if (Exec::kBlock) DUNK_PHASE(11);
     // ---- solve_for_sign: the first point must lie in front of the camera
     {
         double a[4];
@@ -470,6 +483,7 @@ DUNK_HD double epnp_solve(const Exec& ex, const Camera& cam, double (&R)[9], dou
             for (int k = 0; k < 3; ++k) ts[c][k] = pc0[c][k] - (Rc[3 * k] * c0x + Rc[3 * k + 1] * c0y + Rc[3 * k + 2] * c0z);
         }
     }
+    if (Exec::kBlock) DUNK_PHASE(12);
     // ---- reprojection_error, pick the best candidate
     double err[3];
     ex.template sum<3>(

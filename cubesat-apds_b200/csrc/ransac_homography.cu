@@ -653,6 +653,7 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
     }
     __syncthreads();
     int total_hyp = 0;
+    DUNK_PHASE(32);
 
     while (true) {
         // ---- (1) candidate generation + checkSubset, warp 0 ---------------------------------
@@ -771,6 +772,7 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
         finish(0, 0, sh.iter, total_hyp);
         return;
     }
+    DUNK_PHASE(33);
     // ---- (4) refit on the inliers of the best minimal model + LM (fundam.cpp) ----------------
     float Hf[8];
 #pragma unroll
@@ -779,7 +781,9 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
     const float fit2 = sh.fit_thr2;
     auto inlier = [&](int i) { return reproj_err(Hf, src[i], dst[i]) <= fit2; };
     dlt_refit(sh, src, dst, n, inlier);   // on failure keeps the minimal-sample model
+    DUNK_PHASE(34);
     lm_refine(sh, src, dst, n, inlier);
+    DUNK_PHASE(35);
     // ---- (5) returned mask = inliers of the final H (cv2 4.13) ------
     float Hf2[8];
 #pragma unroll
@@ -792,6 +796,7 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
     }
     block_reduce<1>(cnt, sh.red_buf, sh.red);
     finish(1, (int)sh.red[0], sh.iter, total_hyp);
+    DUNK_PHASE(36);
 }
 
 // parity / diagnostics: score explicit hypothesis sets (one warp each)
@@ -924,5 +929,14 @@ int dunk_ransac_score_hypotheses(dunk_ctx* ctx, const float* src, const float* d
     DUNK_CUDA(cudaStreamSynchronize(st));
     return DUNK_OK;
 }
+
+#ifdef DUNK_PHASE_TIMING
+/* timing variant only: clock64() stamps of block 0 (32-36) */
+int dunk_debug_phases_homography(long long* out, int n) {
+    DUNK_CUDA(cudaDeviceSynchronize());
+    DUNK_CUDA(cudaMemcpyFromSymbol(out, g_phase, (size_t)(n < 64 ? n : 64) * 8));
+    return DUNK_OK;
+}
+#endif
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 //     result is what the sequential CPU loop produces;
 //   * the final pose is EPnP over all inliers of the best hypothesis, CTA-wide: every thread runs
 //     the scalar part redundantly, the sums over points are block reductions.
+#include <algorithm>
 #include <vector>
 #include "ctx.h"
 #include "pnp_math.cuh"
@@ -65,6 +66,7 @@ struct Shared {
 
 // CTA-wide executor for the final solve: the used points are those with mask[i] != 0
 struct BlockExec {
+    static constexpr bool kBlock = true;
     const float* obj;
     const float* img;
     const uint8_t* mask;
@@ -196,6 +198,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
     }
     __syncthreads();
     int total_hyp = 0, round = 0;
+    DUNK_PHASE(0);
 
     while (!sh.done) {
         // ---- (1) sample stream, thread 0 ----------------------------------------------------
@@ -221,6 +224,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
         }
         __syncthreads();
         const int nh = sh.nh;
+        if (round == 0) DUNK_PHASE(1);
         // ---- (2) solve: one thread per hypothesis -------------------------------------------
         if (tid < nh) {
             double model[12];
@@ -229,6 +233,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
             sh.counts[tid] = ok ? 0 : -1;
         }
         __syncthreads();
+        if (round == 0) DUNK_PHASE(2);
         // ---- (3) score: one warp per hypothesis ---------------------------------------------
         for (int h = warp; h < nh; h += kWarps) {
             if (sh.counts[h] < 0) continue;
@@ -236,6 +241,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
             if (lane == 0) sh.counts[h] = c;
         }
         __syncthreads();
+        if (round == 0) DUNK_PHASE(3);
         // ---- (4) sequential accept rule in stream order (ptsetreg.cpp run()) -----------------
         if (tid == 0) {
             for (int h = 0; h < nh && sh.iter < sh.niters; ++h) {
@@ -259,6 +265,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
         finish(0, 0, sh.iter, total_hyp, nullptr, nullptr);
         return;
     }
+    DUNK_PHASE(4);
     // ---- (5) inlier mask of the best minimal model, then EPnP over those inliers ------------
     if (tid == 0) { sh.first_inlier = n; sh.n_inliers = 0; }
     __syncthreads();
@@ -279,7 +286,9 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
     __syncthreads();   // also orders the global mask writes before the block-wide reads below
     BlockExec ex{obj, img, mask, n, sh.n_inliers, sh.first_inlier, cam, &sh};
     double R[9], t[3], r[3];
+    DUNK_PHASE(5);
     epnp_solve(ex, cam, R, t);
+    DUNK_PHASE(20);
     // SOLVEPNP_ITERATIVE: same RANSAC stage, then the Levenberg-Marquardt minimum over the inliers (solvepnp.cpp calls
     // solvePnP(inliers, flags); with exactly model_points points OpenCV returns the kernel's pose unrefined)
     if (method == DUNK_PNP_ITERATIVE && n > mp) pnp_refine(ex, cam, R, t);
@@ -287,6 +296,7 @@ pnp_ransac_kernel(const float* __restrict__ obj_all, const float* __restrict__ i
     bool ok = true;
     for (int i = 0; i < 3; ++i) ok = ok && isfinite(r[i]) && isfinite(t[i]);
     finish(ok ? 1 : 0, sh.n_inliers, sh.iter, total_hyp, r, t);
+    DUNK_PHASE(21);
 }
 
 // parity hook: explicit 5-index samples -> per-hypothesis inlier count and pose (one thread solves,
@@ -466,5 +476,14 @@ int dunk_pnp_score_hypotheses(dunk_ctx* ctx, const double* obj, const double* im
     DUNK_CUDA(cudaStreamSynchronize(st));
     return DUNK_OK;
 }
+
+#ifdef DUNK_PHASE_TIMING
+/* timing variant only: clock64() stamps of block 0 (PnP: 0-21, homography: 32-47) */
+int dunk_debug_phases_pnp(long long* out, int n) {
+    DUNK_CUDA(cudaDeviceSynchronize());
+    DUNK_CUDA(cudaMemcpyFromSymbol(out, g_phase, (size_t)std::min(n, 64) * 8));
+    return DUNK_OK;
+}
+#endif
 
 }  // extern "C"
