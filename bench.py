@@ -693,7 +693,7 @@ def run_extract(args):
     dunk, lib, ctx, slot, _lib = h.dunk, h.lib, h.ctx, h.slot, h._lib
     check = _lib.check
     rank, world = h.rank, h.world
-    B, sub = args.extract_frames, 64
+    B, sub = args.extract_frames, args.extract_sub
     frames = config2_frames(B)
     f_dev = h.dev_buffer(frames.nbytes)
     f_dev.upload(slot, frames)
@@ -945,6 +945,7 @@ def main():
                     help="pipeline = config 5 (default, the headline metric); match = config 3 (sharded matcher only); "
                          "extract = config 2 (extraction only); build = config 4 (reference-DB build from a scene)")
     ap.add_argument("--extract-frames", type=int, default=256, help="--workload extract: frames per step per GPU")
+    ap.add_argument("--extract-sub", type=int, default=64, help="--workload extract: frames per library call (sub-batch)")
     ap.add_argument("--build-scene", type=int, default=10980, help="--workload build: scene edge (pixels)")
     ap.add_argument("--db-rows", type=int, default=50_000_000, help="--workload match: reference descriptors")
     ap.add_argument("--queries", type=int, default=3163, help="--workload match: query descriptors per frame")

@@ -157,10 +157,11 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
     cudaStream_t st = g.stream();
     size_t free_b = 0, total_b = 0;
     DUNK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)8 << 30);
+    const size_t budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)16 << 30);
     cudaEvent_t done[2] = {g.slot().ev0, g.slot().ev1};
     cudaEvent_t copied[2] = {g.slot().ev2, g.slot().ev3};
     const auto t_entry = std::chrono::steady_clock::now();
+    static thread_local cudaEvent_t t_start[2] = {nullptr, nullptr};      // trace only
     int f0 = 0;
     // The raw-candidate capacity (w*h/32 by default) is exceeded only by pathological textures (random 4x4 blocks
     // reach w*h/29); k_extrema keeps counting past the capacity, so on overflow the sub-batch is simply re-run
@@ -170,7 +171,8 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
         // sub-batch so the workspace stays bounded (~100 MB per 1024^2 frame)
         const size_t per_frame = akaze_workspace_bytes(lt, 1, cand_cap, kp_cap) + 2 * frame_stride_bytes + 4096;
         int sub = (int)std::max<size_t>(1, std::min<size_t>(n_frames - f0, budget / per_frame));
-        sub = std::min(sub, 64);
+        // the small octaves are latency-bound at 64 frames (T(n) ~ 1.4 ms + 0.089 ms * n on B200): 128-frame sub-batches
+        sub = std::min(sub, 128);
         const size_t ws_bytes = akaze_workspace_bytes(lt, sub, cand_cap, kp_cap);
         // Two-deep software pipeline over sub-batches (one stream): while the device works on sub-batch i the calling
         // thread stages sub-batch i + 1 into the other pinned half (pageable caller memory would otherwise go through
@@ -195,10 +197,17 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
         auto d_off = [&](int h) { return (int*)(d_out + h * out_half + al(out_rows * 61) + al(out_rows * sizeof(DunkKeyPoint))); };
         auto h_off = [&](int h) { return (int*)(pin + pin_off + h * al((size_t)(sub + 2) * 4)); };
         bool overflow = false;
+        // chunk schedule: a first chunk of at most 64 frames (the device starts after half a staging copy), full
+        // sub-batches after it
+        const int first_f0 = f0;
+        auto chunk_len = [&](int fs) {
+            const int left = n_frames - fs;
+            return (fs == first_f0 && left > 64) ? std::min(sub, 64) : std::min(sub, left);
+        };
         cudaStream_t st2 = g.slot().stream2;      // copies in both directions run beside the kernels of the other half
         // stage sub-batch starting at frame `fs` into half h (asynchronous after the host memcpy)
         auto stage = [&](int fs, int h) -> int {
-            const int nf = std::min(sub, n_frames - fs);
+            const int nf = chunk_len(fs);
             const size_t in_bytes = (size_t)nf * frame_stride_bytes;
             const auto t0 = std::chrono::steady_clock::now();
             par_memcpy(pin + h * in_half, images + (size_t)fs * frame_stride_bytes, in_bytes);
@@ -208,6 +217,10 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
             DUNK_CUDA(cudaMemcpyAsync(d_in + h * in_half, pin + h * in_half, in_bytes, cudaMemcpyHostToDevice, st2));
             DUNK_CUDA(cudaEventRecord(copied[h], st2));
             DUNK_CUDA(cudaStreamWaitEvent(st, copied[h], 0));
+            if (trace) {
+                if (!t_start[h]) cudaEventCreate(&t_start[h]);
+                cudaEventRecord(t_start[h], st);
+            }
             int rc = akaze_run(ctx, st, lt, ws, d_in + h * in_half, frame_stride_bytes, row_stride_bytes, channels, nf, max_points);
             if (rc) return rc;
             if ((rc = launch_pack_outputs(ctx, st, ws, nf, d_off(h), d_kps(h), d_desc61(h)))) return rc;
@@ -218,14 +231,19 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
         int rc = stage(f0, 0);
         if (rc) return rc;
         for (int h = 0; f0 < n_frames && !overflow; h ^= 1) {
-            const int nf = std::min(sub, n_frames - f0);
+            const int nf = chunk_len(f0);
             const int next = f0 + nf;
             // host stages sub-batch i + 1 while the device runs sub-batch i (its pinned half and packed-output half
             // were released when sub-batch i - 1 was unpacked)
             if (next < n_frames && (rc = stage(next, h ^ 1))) return rc;
             const auto tw = std::chrono::steady_clock::now();
             DUNK_CUDA(cudaEventSynchronize(done[h]));
-            if (trace) fprintf(stderr, "[dunk] sub-batch %d: waited %.2f ms for the device\n", f0, ms_since(tw));
+            if (trace) {
+                float dev_ms = 0;
+                cudaEventElapsedTime(&dev_ms, t_start[h], done[h]);
+                fprintf(stderr, "[dunk] +%.1f ms sub-batch %d (%d frames): waited %.2f ms for the device, its kernels took %.2f ms\n",
+                        ms_since(t_entry), f0, nf, ms_since(tw), dev_ms);
+            }
             const int* off = h_off(h);
             if (off[nf + 1] > cand_cap) {              // re-run from this sub-batch with a larger candidate capacity
                 DUNK_REQUIRE(off[nf + 1] <= (1 << 22), DUNK_ERR_NO_MEM, "dunk_akaze_extract: %d raw extrema in one frame", off[nf + 1]);
@@ -262,12 +280,12 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
                 DUNK_CUDA(cudaStreamSynchronize(st2));
                 const double d2h_ms = ms_since(td);
                 const auto tu = std::chrono::steady_clock::now();
-                for (int f = 0; f < nf; ++f) {
+                par_for((size_t)nf, [&](size_t f) {
                     const int n = off[f + 1] - off[f];
-                    if (n == 0) continue;
+                    if (n == 0) return;
                     memcpy(kps + (size_t)(f0 + f) * cap_per_frame, p_kps + off[f], (size_t)n * sizeof(DunkKeyPoint));
                     memcpy(desc + (size_t)(f0 + f) * cap_per_frame * 61, p_desc + (size_t)off[f] * 61, (size_t)n * 61);
-                }
+                });
                 if (trace) fprintf(stderr, "[dunk] sub-batch %d: D2H %.1f MB in %.2f ms, unpack %.2f ms\n", f0, total * 89 / 1e6, d2h_ms, ms_since(tu));
             }
             f0 = next;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -12,8 +13,10 @@
 namespace dunk {
 
 void set_error(const char* fmt, ...);
-// host memcpy on up to 8 threads (a single core moves 5-10 GB/s, less than PCIe 5 or the kernels consume)
+// host memcpy on the persistent host workers (a single core moves ~15 GB/s, less than PCIe 5 or the kernels consume)
 void par_memcpy(void* dst, const void* src, size_t n);
+// f(0) ... f(items - 1) on the library's persistent host workers (and the calling thread); returns when all are done
+void par_for(size_t items, const std::function<void(size_t)>& f);
 
 // One stream + growable device / pinned-host scratch.  A host-API call owns exactly one
 // slot for its duration (SURVEY 8b "Threading").
@@ -62,6 +65,7 @@ struct dunk_ctx {
     // each shipped with an async copy while the other half is being filled.  Asynchronous on the slot's stream for
     // the last chunk only (callers order later work on the same stream).  Uses stream2-free events ev0 / ev1.
     int upload_pageable(int s, void* dst_dev, const void* src_host, size_t nbytes);
+    void* upload_ring(int s);          // the slot's 2 x 64 MB pinned ring (allocated on first use); nullptr = no memory
 };
 
 namespace dunk {

@@ -5,7 +5,11 @@
 // points) followed by find_homography_mat (homographier/src/homographier/mod.rs:231-259).
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include "akaze.h"
 #include "gamma_lut.cuh"
 #include "geo.cuh"
@@ -899,6 +903,71 @@ bool make_taps(int scale, int resample, ResampleTaps* t) {
 
 namespace dunk {
 namespace {
+// Helper thread of the host-band build: copies the three planes stripe by stripe (pageable -> pinned ring half ->
+// device, on `stream`) and records one event per finished stripe.  The owner waits host-side until the event of the
+// stripe it needs has been RECORDED (cudaStreamWaitEvent on a never-recorded event would be a no-op).
+struct StripeUpload {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    int recorded = 0, rc = DUNK_OK;
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t ring_ev[2] = {nullptr, nullptr};
+
+    void start(int device, cudaStream_t stream, char* ring, const float* const (&host)[3], float* const (&dev)[3], int width,
+               int height, int stripe_rows) {
+        const float* h0 = host[0]; const float* h1 = host[1]; const float* h2 = host[2];
+        float* d0 = dev[0]; float* d1 = dev[1]; float* d2 = dev[2];
+        th = std::thread([=] {
+            const float* hb[3] = {h0, h1, h2};
+            float* db[3] = {d0, d1, d2};
+            const size_t half = (size_t)64 << 20;
+            int h = 0, err = DUNK_OK;
+            auto ok = [&](cudaError_t e) {
+                if (e != cudaSuccess && err == DUNK_OK) err = DUNK_ERR_CUDA;
+                return e == cudaSuccess;
+            };
+            ok(cudaSetDevice(device));
+            for (size_t s = 0; s < ev.size(); ++s) {
+                const size_t r0 = s * (size_t)stripe_rows, r1 = std::min<size_t>(height, r0 + stripe_rows);
+                const size_t bytes = (r1 - r0) * (size_t)width * 4;
+                for (int b = 0; b < 3 && err == DUNK_OK; ++b) {
+                    const char* src = (const char*)(hb[b] + r0 * width);
+                    char* dst = (char*)(db[b] + r0 * width);
+                    for (size_t off = 0; off < bytes && err == DUNK_OK; off += half, h ^= 1) {
+                        const size_t n = std::min(half, bytes - off);
+                        if (!ok(cudaEventSynchronize(ring_ev[h]))) break;      // the half's previous copy has left it
+                        par_memcpy(ring + h * half, src + off, n);
+                        ok(cudaMemcpyAsync(dst + off, ring + h * half, n, cudaMemcpyHostToDevice, stream));
+                        ok(cudaEventRecord(ring_ev[h], stream));
+                    }
+                }
+                if (err == DUNK_OK) ok(cudaEventRecord(ev[s], stream));
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    rc = err;
+                    if (err == DUNK_OK) recorded = (int)s + 1;
+                }
+                cv.notify_all();
+                if (err != DUNK_OK) return;
+            }
+        });
+    }
+    // blocks until stripe `s` has been enqueued + its event recorded (or the upload failed)
+    int wait_recorded(int s) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return rc != DUNK_OK || recorded > s; });
+        return rc;
+    }
+    ~StripeUpload() {
+        if (th.joinable()) th.join();
+        for (cudaEvent_t e : ev)
+            if (e) { cudaEventSynchronize(e); cudaEventDestroy(e); }
+        for (cudaEvent_t e : ring_ev)
+            if (e) { cudaEventSynchronize(e); cudaEventDestroy(e); }
+    }
+};
+
 // bands_on_device: red/green/blue are device pointers (the scene already in HBM); otherwise host pointers copied in first
 int build_from_bands(dunk_db* db, const float* red, const float* green, const float* blue, bool bands_on_device, int width, int height,
                      const double* min_max, int lods, int resample, int max_points, int* n_tiles_out, int* tile_w_out,
@@ -929,16 +998,26 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
     if (!scratch) return DUNK_ERR_NO_MEM;
     char* ptr = (char*)scratch;
     const float* d_band[3] = {red, green, blue};
+    // Host bands (3 x 482 MB pageable planes at config 4) are uploaded by a helper thread in STRIPES of one LoD-0 tile
+    // row, in the order the tile walk needs them, through the slot's pinned ring on the second stream; the tile
+    // batches below wait (stream-side) for the last stripe they read, so extraction of row r overlaps the upload of
+    // rows r+1...  (The plain sequence upload -> build spent 45 of its 66 ms in the copy.)
+    StripeUpload up;
+    const int n_stripes = bands_on_device ? 0 : div_up(height, tile_h);
     if (!bands_on_device) {
-        const float* h_band[3] = {red, green, blue};
+        if (!ctx->upload_ring(g.s)) return DUNK_ERR_NO_MEM;
+        float* dev[3];
         for (int b = 0; b < 3; ++b) {
-            d_band[b] = (const float*)ptr;
-            // pageable 482 MB planes: through the slot's pinned ring (the driver's staged copy is ~11 GB/s and was
-            // 130 of the 150 ms of a host-buffer build)
-            int rcu = ctx->upload_pageable(g.s, ptr, h_band[b], plane * 4);
-            if (rcu) return rcu;
+            dev[b] = (float*)ptr;
+            d_band[b] = dev[b];
             ptr += al(plane * 4);
         }
+        up.ev.resize(n_stripes, nullptr);
+        for (auto& e : up.ev) DUNK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        DUNK_CUDA(cudaEventCreateWithFlags(&up.ring_ev[0], cudaEventDisableTiming));
+        DUNK_CUDA(cudaEventCreateWithFlags(&up.ring_ev[1], cudaEventDisableTiming));
+        const float* h_band[3] = {red, green, blue};
+        up.start(ctx->device, g.slot().stream2, (char*)g.slot().ring, h_band, dev, width, height, tile_h);
     }
     AkazeWorkspace ws;
     akaze_carve_workspace(ptr, lt, sub, cap, cap, &ws);
@@ -974,8 +1053,29 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
     DUNK_REQUIRE(thr, DUNK_ERR_CUDA, "dunk_db_build_from_bands: gamma table");
     int n_tiles = 0;
     std::vector<int> h_off(sub + 2), h_cnt(sub);
-    for (size_t j0 = j_begin; j0 < j_end; j0 += sub) {
-        const int nf = (int)std::min<size_t>(sub, j_end - j0);
+    for (size_t j0 = j_begin, j_next; j0 < j_end; j0 = j_next) {
+        int nf = (int)std::min<size_t>(sub, j_end - j0);
+        if (n_stripes) {
+            // host bands: LoD-0 batches are one tile row (= one upload stripe) so they start as soon as it has landed
+            if (jobs[j0].lod == 0) {
+                const int row = jobs[j0].t / jobs[j0].tiles_x;
+                int k = 1;
+                while (k < nf && jobs[j0 + k].lod == 0 && jobs[j0 + k].t / jobs[j0 + k].tiles_x == row) ++k;
+                nf = k;
+            }
+            int need = 0;
+            for (int f = 0; f < nf; ++f) {
+                const TileJob& jb = jobs[j0 + f];
+                const int scale = 1 << jb.lod, row = jb.t / jb.tiles_x;
+                // rows [row * tile_h * scale, (row + 1) * tile_h * scale) plus the Lanczos support of 3 * scale rows
+                const int last_row = std::min(height - 1, (row + 1) * tile_h * scale - 1 + (resample ? 3 * scale : 0));
+                need = std::max(need, last_row / tile_h);
+            }
+            const int rcu = up.wait_recorded(need);
+            DUNK_REQUIRE(rcu == DUNK_OK, rcu, "dunk_db_build_from_bands: band upload failed");
+            DUNK_CUDA(cudaStreamWaitEvent(st, up.ev[need], 0));
+        }
+        j_next = j0 + nf;
         for (int f0 = 0; f0 < nf;) {            // one resample launch per run of equal LoD
             int f1 = f0;
             while (f1 < nf && jobs[j0 + f1].lod == jobs[j0 + f0].lod) ++f1;
