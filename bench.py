@@ -344,7 +344,10 @@ def run_pipeline(args):
     RS, PS = _lib.REGISTRATION_DTYPE.itemsize, _lib.POSE_DTYPE.itemsize
     ws_bytes = int(lib.dunk_register_sharded_workspace_bytes(group.handle, B, FRAME, FRAME))
     ws = h.dev_buffer(ws_bytes)
-    stage_dev = h.dev_buffer(B * FRAME * FRAME)              # e2e: the step's frames arrive here from pinned host memory
+    # e2e: the frames arrive from pinned host memory, double-buffered: while step i computes on `slot`, the frames of
+    # step i + 1 are copied on a second slot (stream) -- what a caller streaming frames through the public API does
+    stage_dev = [h.dev_buffer(B * FRAME * FRAME), h.dev_buffer(B * FRAME * FRAME)]
+    slot_up = ctx.reserve_slot()
     res_dev, pose_dev = h.dev_buffer(B * RS), h.dev_buffer(B * PS)
     res_pin, pose_pin = h.pinned((B,), _lib.REGISTRATION_DTYPE), h.pinned((B,), _lib.POSE_DTYPE)
     n_batches = ND // B
@@ -357,13 +360,27 @@ def run_pipeline(args):
     def device_step(i):                                       # frames already resident in HBM; a different batch every step
         step_on(frames_dev.ptr + (i % n_batches) * B * FRAME * FRAME)
 
-    def e2e_step(i):                                          # host buffers: pinned H2D of the frames, D2H of the records
-        k = i % n_batches
-        stage_dev.upload(slot, frames_pin.array[k * B:(k + 1) * B])
-        step_on(stage_dev.ptr)
+    seq = {"next": 0, "resident": [None, None]}               # running step counter; batch index held by each staging half
+
+    def upload(j):
+        k = j % n_batches
+        stage_dev[j % 2].upload(slot_up, frames_pin.array[k * B:(k + 1) * B])
+        seq["resident"][j % 2] = k
+
+    def e2e_step(_):
+        # host buffers: every step issues one pinned H2D of B frames (the NEXT step's, on the second slot, overlapping this
+        # step's kernels) and reads this step's records back (D2H) before it returns
+        j = seq["next"]
+        seq["next"] = j + 1
+        if seq["resident"][j % 2] != j % n_batches:           # very first step: nothing was prefetched
+            upload(j)
+        ctx.sync(slot_up)                                     # this step's frames have landed
+        upload(j + 1)
+        step_on(stage_dev[j % 2].ptr)
         res_dev.download(slot, res_pin.array)
         pose_dev.download(slot, pose_pin.array)
         ctx.sync(slot)
+        return j % n_batches
 
     for i in range(args.warmup):
         device_step(i)
@@ -383,8 +400,8 @@ def run_pipeline(args):
     # ---- quality over every distinct frame of this rank (untimed), stage times (profiled extra steps on every rank)
     all_res = np.zeros(ND, _lib.REGISTRATION_DTYPE)
     all_pose = np.zeros(ND, _lib.POSE_DTYPE)
-    for k in range(n_batches):
-        e2e_step(k)
+    for _ in range(n_batches):
+        k = e2e_step(0)
         all_res[k * B:(k + 1) * B] = res_pin.array
         all_pose[k * B:(k + 1) * B] = pose_pin.array
     quality = summarize_quality(all_res, all_pose, Hs, Rs, ts)
@@ -401,7 +418,9 @@ def run_pipeline(args):
             "dtype": DTYPE, "data": "synthetic", "config": pipeline_config(args, world),
             "e2e": {"value": world * B * 1e3 / (e2e_ms / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(B * FRAME * FRAME) * world,
                     "d2h_bytes_per_step": int(B * (RS + PS)) * world,
-                    "call": "dunk_register_frames_sharded_dev between dunk_memcpy_h2d / _d2h on pinned host buffers"},
+                    "call": "dunk_register_frames_sharded_dev between dunk_memcpy_h2d / _d2h on pinned host buffers; the H2D of step "
+                            "i + 1 is issued on a second slot while step i computes (one H2D of B frames and one D2H of the "
+                            "records inside every timed step)"},
             "gpu_launches": int(launches), "clocks": clocks,
             "measured": {"db_rows": int(db_rows), "db_rows_this_shard": len(shard), "db_build_s_this_rank": db_build_s,
                          "db_tiles_this_rank": int(n_t.value), "tile": [tw.value, th.value], "homography_fit_residual_px": fit_resid,
@@ -934,7 +953,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="query frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=256, help="query frames per step per GPU")
     ap.add_argument("--distinct", type=int, default=512, help="distinct query frames per GPU, cycled over the steps")
     ap.add_argument("--scene", type=int, default=10980, help="config-4 scene edge (pixels)")
     ap.add_argument("--ratio", type=float, default=0.8)
@@ -945,7 +964,7 @@ def main():
                     help="pipeline = config 5 (default, the headline metric); match = config 3 (sharded matcher only); "
                          "extract = config 2 (extraction only); build = config 4 (reference-DB build from a scene)")
     ap.add_argument("--extract-frames", type=int, default=256, help="--workload extract: frames per step per GPU")
-    ap.add_argument("--extract-sub", type=int, default=64, help="--workload extract: frames per library call (sub-batch)")
+    ap.add_argument("--extract-sub", type=int, default=256, help="--workload extract: frames per library call (sub-batch)")
     ap.add_argument("--build-scene", type=int, default=10980, help="--workload build: scene edge (pixels)")
     ap.add_argument("--db-rows", type=int, default=50_000_000, help="--workload match: reference descriptors")
     ap.add_argument("--queries", type=int, default=3163, help="--workload match: query descriptors per frame")

@@ -153,14 +153,23 @@ int dunk_akaze_extract_batch(dunk_ctx* ctx, const uint8_t* images, int n_frames,
     auto ms_since = [](std::chrono::steady_clock::time_point t) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
     };
+    const auto t_entry = std::chrono::steady_clock::now();
     SlotGuard g(ctx);
     cudaStream_t st = g.stream();
-    size_t free_b = 0, total_b = 0;
-    DUNK_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)16 << 30);
+    // workspace budget: what the slot already holds is used without asking the driver (cudaMemGetInfo takes up to
+    // 13 ms while other streams are busy); a call that needs more queries the free memory once
+    size_t budget = g.slot().dev_bytes;
+    {
+        const size_t want = (akaze_workspace_bytes(lt, 1, cand_cap, cand_cap) + 2 * frame_stride_bytes + 4096) * (size_t)std::min(n_frames, 128);
+        if (budget < want) {
+            size_t free_b = 0, total_b = 0;
+            DUNK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            budget = std::min<size_t>((free_b + g.slot().dev_bytes) / 2, (size_t)16 << 30);
+        }
+    }
+    if (trace) fprintf(stderr, "[dunk] +%.1f ms slot %d acquired\n", ms_since(t_entry), g.s);
     cudaEvent_t done[2] = {g.slot().ev0, g.slot().ev1};
     cudaEvent_t copied[2] = {g.slot().ev2, g.slot().ev3};
-    const auto t_entry = std::chrono::steady_clock::now();
     static thread_local cudaEvent_t t_start[2] = {nullptr, nullptr};      // trace only
     int f0 = 0;
     // The raw-candidate capacity (w*h/32 by default) is exceeded only by pathological textures (random 4x4 blocks

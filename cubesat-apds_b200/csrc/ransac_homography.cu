@@ -20,7 +20,7 @@
 namespace dunk {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxHyp = 64;          // hypothesis queue per round
 constexpr int kRoundTarget = 2 * kWarps;

@@ -24,7 +24,7 @@ namespace {
 
 using namespace pnp;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxRound = 128;       // hypotheses solved + scored per round
 constexpr int kFirstRound = 32;      // the adaptive stop usually fires inside the first round
