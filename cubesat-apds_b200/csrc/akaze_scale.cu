@@ -1540,7 +1540,9 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
                 static const bool fed_old = getenv("DUNK_FED_OLD") != nullptr;
                 // the row-walking cascade needs many spans x bands x frames to fill the GPU: measured faster than the
                 // tiled kernel at 1024^2 and 512^2 (1.6x / 1.3x), slower at 256^2 and below (0.8x)
-                if (!fed_old && e.w % 2 == 0 && e.w >= 384 && e.h >= 192 && in_stride % 2 == 0 && out_stride % 2 == 0 && plane % 2 == 0 &&
+                // (64 frames); with 128 or more frames the 256-px levels have enough spans too (5.65 vs 6.02 ms / 256 frames)
+                const int fed_minw = frames >= 128 ? 256 : 384;
+                if (!fed_old && e.w % 2 == 0 && e.w >= fed_minw && e.h >= fed_minw / 2 && in_stride % 2 == 0 && out_stride % 2 == 0 && plane % 2 == 0 &&
                     ((uintptr_t)in & 7) == 0 && ((uintptr_t)out & 7) == 0) {
                     const int kh = (fs.k + 1) / 2 * 2, nspans = div_up(e.w, 64 - 2 * kh);
                     int R = 128;

@@ -138,6 +138,8 @@ int dunk_db_select(dunk_db* db, const DunkRowFilter* filter, int64_t limit, dunk
                 floorf(filter->y_start), ceilf(filter->y_end)};
     int64_t n_sel = 0;
     uint32_t* d_order = nullptr;
+    // the CUB select / radix-sort entry points used below take 32-bit item counts
+    DUNK_REQUIRE(n <= 0x7fffffffll, DUNK_ERR_BAD_ARG, "dunk_db_select: %lld rows in one shard (at most 2^31 - 1 per keyed read)", (long long)n);
     if (n > 0) {
         size_t tmp_select = 0, tmp_sort = 0;
         cub::DeviceSelect::Flagged(nullptr, tmp_select, (float*)nullptr, (unsigned char*)nullptr, (float*)nullptr, (int*)nullptr, (int)n, st);
@@ -193,8 +195,13 @@ int dunk_db_select(dunk_db* db, const DunkRowFilter* filter, int64_t limit, dunk
         k_gather_rows<<<div_up(n_sel * 4, 256), 256, 0, st>>>(db->desc64, db->kps, db->image_id, db->row_id, d_order, n_sel, sub->desc64,
                                                             sub->kps, sub->image_id, sub->row_id);
         ctx->launches.fetch_add(1);
-        DUNK_CUDA(cudaGetLastError());
-        DUNK_CUDA(cudaStreamSynchronize(st));
+        cudaError_t ge = cudaGetLastError();
+        if (ge == cudaSuccess) ge = cudaStreamSynchronize(st);
+        if (ge != cudaSuccess) {
+            dunk_db_destroy(sub);
+            set_error("dunk_db_select: gather failed: %s", cudaGetErrorString(ge));
+            return DUNK_ERR_CUDA;
+        }
     }
     sub->size = n_sel;
     *out = sub;
@@ -261,10 +268,23 @@ int dunk_db_load(dunk_ctx* ctx, const char* path, int64_t min_capacity_rows, dun
     DUNK_REQUIRE(fp, DUNK_ERR_BAD_ARG, "dunk_db_load: cannot open %s", path);
     FileHeader h{};
     if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "DUNKDB01", 8) != 0 || h.rows < 0 || h.desc_bytes < 1 || h.desc_bytes > 64 ||
-        h.n_images < 0) {
+        h.n_images < 0 || h.n_images > (1 << 26) || h.reserved != 0) {       // `reserved` doubles as the format version (0)
         fclose(fp);
         set_error("dunk_db_load: %s is not a dunk_b200 database dump", path);
         return DUNK_ERR_BAD_ARG;
+    }
+    {   // the file must hold what the header announces before anything is allocated from it
+        const long pos = ftell(fp);
+        fseek(fp, 0, SEEK_END);
+        const long long file_bytes = ftell(fp);
+        fseek(fp, pos, SEEK_SET);
+        const long long per_row = 64 + (long long)sizeof(DunkKeyPoint) + 4 + (h.has_row_id ? 4 : 0);
+        const long long want = (long long)sizeof h + (long long)h.n_images * (long long)sizeof(DunkImage) + (long long)h.rows * per_row;
+        if (file_bytes < want) {
+            fclose(fp);
+            set_error("dunk_db_load: %s is truncated (%lld bytes, the header announces %lld)", path, file_bytes, want);
+            return DUNK_ERR_BAD_ARG;
+        }
     }
     dunk_db* db = nullptr;
     int rc = dunk_db_create(ctx, std::max<int64_t>(std::max<int64_t>(h.rows, min_capacity_rows), 1), h.desc_bytes, &db);

@@ -25,7 +25,8 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kMaxHyp = 64;          // hypothesis queue per round
 constexpr int kRoundTarget = 2 * kWarps;
 constexpr unsigned long long kRngCoeff = 4164903690ull;
-constexpr int kMaxAttempts = 10000;
+constexpr int kMaxAttempts = 10000;        // RANSACPointSetRegistrator::run passes 10000 to getSubset
+constexpr int kMaxAttemptsLmeds = 1000;    // LMeDSPointSetRegistrator::run uses getSubset's default (ptsetreg.cpp)
 
 struct Rng {
     unsigned long long state;
@@ -693,7 +694,7 @@ find_homography_kernel(const float2* __restrict__ src_all, const float2* __restr
                             sh.hyp[h][0] = sh.cand[c][0]; sh.hyp[h][1] = sh.cand[c][1];
                             sh.hyp[h][2] = sh.cand[c][2]; sh.hyp[h][3] = sh.cand[c][3];
                             if (sh.nh == kMaxHyp) { ++c; break; }
-                        } else if (++sh.rejects >= kMaxAttempts) {
+                        } else if (++sh.rejects >= (lmeds ? kMaxAttemptsLmeds : kMaxAttempts)) {
                             sh.exhausted = 1; ++c;
                             break;
                         }
@@ -842,8 +843,13 @@ int dunk_find_homography_batch(dunk_ctx* ctx, const float* src, const float* dst
     DUNK_REQUIRE(ctx && offsets && H && info && n_problems >= 0, DUNK_ERR_BAD_ARG,
                  "dunk_find_homography_batch: NULL argument");
     if (n_problems == 0) return DUNK_OK;
-    DUNK_REQUIRE(method == DUNK_H_RANSAC || method == DUNK_H_LMEDS || method == DUNK_H_DEFAULT, DUNK_ERR_BAD_ARG,
-                 "dunk_find_homography: method %d not implemented (RANSAC=8, LMEDS=4 and Default=0 are)", method);
+    DUNK_REQUIRE(method == DUNK_H_RANSAC || method == DUNK_H_LMEDS || method == DUNK_H_DEFAULT || method == DUNK_H_RHO, DUNK_ERR_BAD_ARG,
+                 "dunk_find_homography: unknown method %d (Default=0, LMEDS=4, RANSAC=8, RHO=16)", method);
+    // HomographyMethod::RHO (mod.rs:25-31): OpenCV's rho.cpp is PROSAC sampling + SPRT verification with its own
+    // generator; its result depends on the ORDER of the pairs and is not restated here.  A RHO request is served by the
+    // RANSAC estimator with RHO's contract (same threshold, 2000 iterations, confidence 0.995, robust H + inlier mask);
+    // parity for this method is by tolerance only (tests/test_ransac_gpu.py::test_rho_vs_cv2), see DESIGN.md section 1.
+    if (method == DUNK_H_RHO) method = DUNK_H_RANSAC;
     const int total = offsets[n_problems];
     for (int b = 0; b < n_problems; ++b) {
         const int n = offsets[b + 1] - offsets[b];

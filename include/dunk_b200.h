@@ -238,7 +238,8 @@ int dunk_akaze_debug_level(dunk_ctx* ctx, const uint8_t* image, int rows, int co
  * src/dst: n x 2 f32 (Point2f).  H: 9 f64 row-major, H[8] = 1.  mask: n u8 (may be NULL).
  * method: DUNK_H_RANSAC (8), DUNK_H_LMEDS (4: 55 iterations of the same sample stream, least median of the
  * f32 errors, sigma-inliers refitted; thr only shapes the returned mask) or DUNK_H_DEFAULT (0, least squares on
- * all pairs); RHO -> DUNK_ERR_BAD_ARG.  n < 4 -> DUNK_ERR_VEC_LENGTH (-28, OpenCV's StsVecLengthErr).
+ * all pairs); DUNK_H_RHO (16) is served by the RANSAC estimator (OpenCV's PROSAC + SPRT schedule is not restated:
+ * same contract, tolerance parity only).  n < 4 -> DUNK_ERR_VEC_LENGTH (-28, OpenCV's StsVecLengthErr).
  * *found = 0 when no model was found (OpenCV returns an empty Mat -> MatError::Empty). */
 int dunk_find_homography(dunk_ctx* ctx, const float* src, const float* dst, int n, int method,
                          double thr, double* H, uint8_t* mask, int* found);

@@ -1,6 +1,6 @@
 """Generates the golden vectors under tests/golden/ by running the reference's OpenCV entry
 points (through cv2, the same C++ library the `opencv` crate binds) with the reference's exact
-arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|lmeds|akaze|config1|pnp|pnp_iter|warp|l2|all]
+arguments.  Run in the build container:  python tests/golden/make_golden.py [match|ransac|lmeds|rho|akaze|config1|pnp|pnp_iter|warp|l2|all]
 The OpenCV version is recorded in every file (parity is defined against that version)."""
 import os
 import sys
@@ -100,6 +100,22 @@ def make_pnp_iter():
         out[f"c{i}_inliers"] = np.zeros(0, np.int32) if inl is None else inl.ravel().astype(np.int32)
         print(f"pnp iterative case {i}: n={n} found={ok} inliers={len(out[f'c{i}_inliers'])}")
     np.savez_compressed(os.path.join(HERE, "pnp_iter_golden.npz"), **out)
+
+
+def make_rho():
+    """cv2.findHomography(src, dst, RHO, thr) — HomographyMethod::RHO, mod.rs:25-31.  RHO is PROSAC: it assumes the pairs
+    are ordered by quality, so the outliers ransac_case() puts FIRST make it fail; the cases are shuffled (what a
+    matcher's query-ordered output looks like)."""
+    out = {"opencv_version": np.array(cv2.__version__), "n_cases": np.array(len(RANSAC_CASES))}
+    for i, (n, of, sg) in enumerate(RANSAC_CASES):
+        src, dst = ransac_case(n, of, sg, 200 + i)
+        p = np.random.default_rng(i).permutation(n)
+        src, dst = src[p], dst[p]
+        H, mask = cv2.findHomography(src, dst, cv2.RHO, 3.0)
+        out[f"c{i}_src"], out[f"c{i}_dst"], out[f"c{i}_thr"] = src, dst, np.array(3.0)
+        out[f"c{i}_H"], out[f"c{i}_mask"] = H, mask.ravel().astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "rho_golden.npz"), **out)
+    print("rho_golden.npz:", len(RANSAC_CASES), "cases")
 
 
 LMEDS_CASES = [(50, 0.2, 0.5), (200, 0.4, 0.5), (1000, 0.3, 1.0), (2000, 0.4, 2.0), (100, 0.0, 0.1), (300, 0.45, 1.5),
@@ -319,6 +335,8 @@ if __name__ == "__main__":
         make_ransac()
     if what in ("lmeds", "all") and "make_lmeds" in globals():
         make_lmeds()
+    if what in ("rho", "all"):
+        make_rho()
     if what in ("akaze", "all") and "make_akaze" in globals():
         make_akaze()
     if what in ("config1", "all"):

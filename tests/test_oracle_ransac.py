@@ -76,3 +76,13 @@ def test_lmeds_iteration_count_and_mask_rule():
     _, sig_mask, sigma, iters = ro.lmeds_loop(src, dst)
     assert iters == 55 and sigma > 6.0
     assert int(sig_mask.sum()) > int(GL[f"c{i}_mask"].sum())
+
+
+def test_rho_goldens_within_tolerance_of_the_ransac_estimator():
+    """RHO is served by the RANSAC estimator (parity unpinned, see oracle.ransac_oracle.find_homography_rho): on the
+    shuffled cv2 RHO goldens H agrees within 3e-2 and the masks on >= 75 % of the pairs."""
+    R = np.load(os.path.join(os.path.dirname(__file__), "golden", "rho_golden.npz"))
+    for i in range(int(R["n_cases"])):
+        H, m = ro.find_homography_rho(R[f"c{i}_src"], R[f"c{i}_dst"], float(R[f"c{i}_thr"]))
+        assert np.abs(H - R[f"c{i}_H"]).max() / np.abs(R[f"c{i}_H"]).max() < 3e-2, i
+        assert (m == R[f"c{i}_mask"]).mean() >= 0.75, i
