@@ -258,6 +258,19 @@ def pipeline_config(args, world):
     }
 
 
+def fill_descriptor_bytes(stages, n_keypoints_per_step):
+    """k_orientation / k_mldb launch before the keypoint count is known on the host, so the library records no byte
+    count for them; the USEFUL bytes per keypoint are fixed by the sampling patterns: orientation = 109 samples x
+    (Lx, Ly) f32, MLDB = the shared 21 x 21 lattice (441 samples) x (Lt, Lx, Ly) f32 + the 64-byte row written.  Every
+    4-byte sample is a gather that moves a 32-byte sector, so sector traffic is ~8x these figures (L2-gather bound)."""
+    per_kp = {"describe.orientation": 109 * 2 * 4, "describe.mldb": 441 * 3 * 4 + 64}
+    for k, b in per_kp.items():
+        if k in stages and not stages[k]["alg_bytes_or_ops"]:
+            stages[k]["alg_bytes_or_ops"] = float(n_keypoints_per_step) * b
+            stages[k]["sector_bytes"] = float(n_keypoints_per_step) * (b - (64 if "mldb" in k else 0)) * 8
+            stages[k]["bound"] = "L2 gather (one 32-byte sector per 4-byte sample)"
+
+
 def summarize_quality(res, poses, Hs, Rs, ts):
     import synthdata
     errs = []
@@ -406,6 +419,19 @@ def run_pipeline(args):
         all_pose[k * B:(k + 1) * B] = pose_pin.array
     quality = summarize_quality(all_res, all_pose, Hs, Rs, ts)
     stages = h.profile(device_step, max(2, min(args.steps, 8)))
+    fill_descriptor_bytes(stages, quality["keypoints_mean"] * B)
+    # rates of the two latency-bound tail kernels (one CTA per frame): hypotheses and point evaluations per second of
+    # kernel time, next to the FP32 FMA peak they would be measured against if they were throughput-bound
+    fp32_peak = 148 * 128 * 2 * 1.965e9
+    tail = {}
+    for key, recs, n_pts, flop in (("ransac.find_homography", all_res, all_res["matches"], 30), ("ransac.pnp", all_pose, all_res["inliers"], 40)):
+        if key in stages and stages[key]["ms"] > 0:
+            hyp = float(recs["hypotheses"].sum()) * B / ND
+            evals = float((recs["hypotheses"].astype(np.float64) * n_pts).sum()) * B / ND
+            sec = stages[key]["ms"] * 1e-3
+            tail[key] = {"hypotheses_per_step": hyp, "hypotheses_per_s": hyp / sec, "point_evals_per_s": evals / sec,
+                         "flop_per_eval": flop, "frac_fp32_peak": evals * flop / sec / fp32_peak, "ctas": B, "threads_per_cta": 128,
+                         "bound": "latency (serial f64 solves per CTA: DLT refit + LM / EPnP 12x12 Jacobi), see profiles/r2_tail_phase_times*.txt"}
     total_ms, e2e_ms = h.max_over_ranks([total_ms, e2e_ms])
     agg = h.sum_over_ranks([quality["registered"], quality["poses_found"], quality["H_err_below_5e-3"], quality["frames"]])
 
@@ -427,7 +453,7 @@ def run_pipeline(args):
                          "nccl_version": int(lib.dunk_nccl_version()) if world > 1 else None},
             "quality": dict(quality, all_ranks={"registered": int(agg[0]), "poses_found": int(agg[1]), "H_err_below_5e-3": int(agg[2]),
                                                 "frames": int(agg[3])}),
-            "stages_ms_per_step": stages,
+            "stages_ms_per_step": stages, "tail_kernels": tail,
             "roofline": pipeline_roofline(stages, ctx, clocks, peaks, peak_src, f"pipeline frames={B} scene={S}"),
         }
         if not args.no_cpu_baseline and world == 1:
@@ -755,6 +781,7 @@ def run_extract(args):
     n_e2e = int(counts.sum())
     total_ms, e2e_ms = h.max_over_ranks([total_ms, e2e_ms])
     stages = h.profile(device_step, max(2, args.steps))
+    fill_descriptor_bytes(stages, n_kp[0])
     if rank == 0:
         peaks, peak_src = measured_peaks()
         ms = total_ms / args.steps

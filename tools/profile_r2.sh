@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 OUT=gpurun_out
-B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --distinct 128"
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 case "$1" in
 launches)
   $B > $OUT/r2p_plain.log 2>&1 &&
@@ -24,7 +24,7 @@ tailsrc)
   ncu -i $OUT/r2p_tailsrc.ncu-rep --page source --print-source cuda --csv > $OUT/r2p_tailsrc_cuda.csv 2>/dev/null
   gzip -f $OUT/r2p_tailsrc_raw.csv $OUT/r2p_tailsrc_cuda.csv; rm -f $OUT/r2p_tailsrc.ncu-rep ;;
 extract)
-  E="python bench.py --workload extract --steps 1 --warmup 3 --no-cpu-baseline --extract-frames 64"
+  E="python bench.py --workload extract --steps 1 --warmup 3 --no-cpu-baseline"
   $E > $OUT/r2p_plain3.log 2>&1 &&
   ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section SchedulerStats --section Occupancy --section LaunchStats --section InstructionStats \
       --clock-control none -k regex:"k_fed|k_hessian|k_prep_level|k_extrema|k_mldb|k_orientation|k_contrast|k_gray|k_halfsample" -s 294 -c 98 -o $OUT/r2p_extract $E > $OUT/r2p_ncu3.log 2>&1
