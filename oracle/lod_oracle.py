@@ -6,7 +6,8 @@ extractor; keypoints go back to scene pixels as x * 2^lod + window offset; one r
 The reference reads the windows through GDAL `read_as(.., Some(ResampleAlg::Lanczos))`
 (geotiff_extractor/src/image_extractor/mod.rs:332-343), whose pixels also depend on GDAL's overview
 selection inside the COG — GDAL is not available here and the reference holds no fixture for it:
-PARITY UNPINNED for the resampled pixel values.  Two deterministic resamplers are restated, both with
+PARITY UNPINNED for the GDAL / Lanczos pixel values; the box mean is pinned against cv2.resize(INTER_AREA) to one f32
+ulp (tests/test_oracle_lod.py).  Two deterministic resamplers are restated, both with
 f64 accumulation in row-major tap order and renormalisation at the scene border: the box mean and the
 Lanczos-3 convolution stretched by the decimation factor (the kernel GDAL's RasterIO uses when
 down-sampling)."""
