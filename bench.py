@@ -258,6 +258,11 @@ def pipeline_config(args, world):
     }
 
 
+# hamming_top2_kernel, SASS per (query, row) pair: 15 XOR + 14 LOP3 (7 carry-save adders) + 3 IADD3 + 1 ISETP on the ALU pipe,
+# 8 POPC on the XU pipe (match_hamming.cu: hamming480; the 16th word is added only on rows that pass the vote)
+POPC_PER_PAIR, ALU_PER_PAIR = 8.0, 33.0
+
+
 def fill_descriptor_bytes(stages, n_keypoints_per_step):
     """k_orientation / k_mldb launch before the keypoint count is known on the host, so the library records no byte
     count for them; the USEFUL bytes per keypoint are fixed by the sampling patterns: orientation = 109 samples x
@@ -474,10 +479,12 @@ def pipeline_roofline(stages, ctx, clocks, peaks, peak_src, shape_key):
         peak = popc * 1e3 / 16.0
         return {"bound": "int", "kernel": top, "achieved": ach, "peak": peak, "unit": "Gpairs/s (SURVEY 8d: 16 POPC per pair)",
                 "frac": ach / peak,
-                # the kernel executes 9 POPC + 34 ALU-class + 3 IMAD per pair (7 carry-save adders compress the 16 XOR words):
-                # fractions of the physical pipes on EXECUTED instructions
-                "frac_executed": ach * 9.0 / (popc * 1e3), "frac_executed_unit": "POPC pipe (9 POPC per pair executed)",
-                "frac_executed_alu": ach * 34.0 / (popc * 4.0 * 1e3),
+                # the kernel executes POPC_PER_PAIR POPC + ALU_PER_PAIR ALU-class + 3 IMAD per pair (15 XOR words compressed by
+                # 7 carry-save adders; the 16th word only on the rare rows that pass the vote): fractions of the physical
+                # pipes on EXECUTED instructions
+                "frac_executed": ach * POPC_PER_PAIR / (popc * 1e3),
+                "frac_executed_unit": "POPC pipe (%d POPC per pair executed)" % POPC_PER_PAIR,
+                "frac_executed_alu": ach * ALU_PER_PAIR / (popc * 4.0 * 1e3),
                 "peak_popc_tpopc_per_s": popc, "peak_clock_mhz": (clocks or {}).get("sm_mhz"),
                 "peak_source": "POPC-pipe microbenchmark run by this process (148 SMs x 16 lanes/clk x SM clock); not in MEASURED_PEAKS.json",
                 "traffic": measured_traffic("hamming_top2_kernel", shape_key),
@@ -705,7 +712,8 @@ def run_match(args):
                "gpu_launches": int(launches), "clocks": clocks,
                "roofline": {"bound": "int", "kernel": "hamming_top2_kernel", "achieved": ach, "peak": peak,
                             "unit": "Gpairs/s (16 POPC per pair, all GPUs)", "frac": ach / peak,
-                            "frac_executed": ach * 9.0 / (popc * 1e3 * world), "frac_executed_unit": "POPC pipe (9 POPC per pair executed)",
+                            "frac_executed": ach * POPC_PER_PAIR / (popc * 1e3 * world),
+                            "frac_executed_unit": "POPC pipe (%d POPC per pair executed)" % POPC_PER_PAIR,
                             "peak_popc_tpopc_per_s": popc, "peak_clock_mhz": (clocks or {}).get("sm_mhz"),
                             "peak_source": "POPC-pipe microbenchmark run by this process; not in MEASURED_PEAKS.json",
                             "hbm_achieved_gbs": (nt * 64.0) / (ms * 1e-3) / 1e9, "traffic": None}}
