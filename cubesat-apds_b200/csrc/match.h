@@ -43,8 +43,11 @@ int launch_pad_rows(dunk_ctx* ctx, cudaStream_t st, const uint8_t* src, int64_t 
                     uint4* dst64);
 int launch_unpad_rows(dunk_ctx* ctx, cudaStream_t st, const uint4* src64, int64_t n, int desc_bytes,
                       uint8_t* dst);
+// seg_counts / seg_len (sharded pipeline only): the queries are segments of seg_len rows, segment r holds
+// seg_counts[2 * r] real rows (device array); groups wholly inside a segment's padding are skipped
 int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, const uint4* q64,
-                int nq, uint32_t index_base, uint4* partial, uint4* top2_out, const KnnPlan& plan);
+                int nq, uint32_t index_base, uint4* partial, uint4* top2_out, const KnnPlan& plan,
+                const int* seg_counts = nullptr, int seg_len = 0);
 int launch_top2_merge(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_parts, int nq,
                       uint4* out);
 int launch_top2_merge_strided(dunk_ctx* ctx, cudaStream_t st, const uint4* parts, int n_parts, long long part_stride,

@@ -164,12 +164,18 @@ template <int QT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __restrict__ q, int nq,
                     int n_qgroups, int n_slabs, int tiles_per_slab, uint32_t index_base,
-                    uint4* __restrict__ partial) {
+                    uint4* __restrict__ partial, const int* __restrict__ seg_counts, int seg_len) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (item >= (long long)n_qgroups * n_slabs) return;
     const int qg = (int)(item % n_qgroups), slab = (int)(item / n_qgroups);
+    // sharded pipeline: the query array is W segments of seg_len rows, segment r holding seg_counts[2 r] real rows and
+    // padding behind them; a query group that lies wholly in the padding of one segment has nothing to match
+    if (seg_counts) {
+        const int a = qg * 32 * QT, seg = a / seg_len;
+        if ((a + 32 * QT - 1) / seg_len == seg && a - seg * seg_len >= seg_counts[2 * seg]) return;
+    }
     uint4* tiles = reinterpret_cast<uint4*>(smem_raw) + (size_t)warp * kStages * kTileRows * 4;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarpsPerCta * kStages * kTileRows * 64) +
                      warp * kStages;
@@ -467,7 +473,8 @@ int launch_unpad_rows(dunk_ctx* ctx, cudaStream_t st, const uint4* src64, int64_
 }
 
 int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, const uint4* q64,
-                int nq, uint32_t index_base, uint4* partial, uint4* top2_out, const KnnPlan& p) {
+                int nq, uint32_t index_base, uint4* partial, uint4* top2_out, const KnnPlan& p, const int* seg_counts,
+                int seg_len) {
     if (nq <= 0) return DUNK_OK;
     // with a single slab the kernel's partial IS the result
     uint4* dst = (p.gx == 1) ? top2_out : partial;
@@ -475,7 +482,7 @@ int launch_knn2(dunk_ctx* ctx, cudaStream_t st, const uint4* db64, uint32_t nt, 
         ProfScope ps(ctx, st, "match.hamming_top2", (double)nq * (double)nt);   // pairs
         const long long items = (long long)p.gx * p.gy;
         hamming_top2_kernel<kQT><<<(unsigned)div_up(items, kWarpsPerCta), p.threads, p.smem, st>>>(
-            db64, nt, q64, nq, p.gy, p.gx, p.tiles_per_cta, index_base, dst);
+            db64, nt, q64, nq, p.gy, p.gx, p.tiles_per_cta, index_base, dst, seg_len > 0 ? seg_counts : nullptr, seg_len);
         DUNK_LAUNCH_CHECK(ctx);
     }
     if (p.gx > 1) return launch_top2_merge(ctx, st, partial, p.gx, nq, top2_out);

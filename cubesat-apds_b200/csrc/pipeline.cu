@@ -649,7 +649,8 @@ int dunk_register_frames_sharded_dev(dunk_shard_group* g, dunk_db* shard, int sl
                 set_error("pipeline: matcher partial buffer too small");
                 return DUNK_ERR_NO_MEM;
             }
-            if ((rc = launch_knn2(ctx, st, shard->desc64, (uint32_t)shard->size, q_all, (int)all_q, (uint32_t)g->bases[me], partial, t_out, kp)))
+            if ((rc = launch_knn2(ctx, st, shard->desc64, (uint32_t)shard->size, q_all, (int)all_q, (uint32_t)g->bases[me], partial, t_out, kp,
+                                  W > 1 ? d_cnt : nullptr, qmax)))
                 return rc;
         } else {
             DUNK_CUDA(cudaMemsetAsync(t_out, 0xFF, all_q * 16, st));
