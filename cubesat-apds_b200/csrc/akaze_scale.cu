@@ -177,13 +177,26 @@ k_contrast_hist(const float* __restrict__ modg, size_t plane_stride, int W, int 
             const float* r0 = src + (size_t)y * W;
             const bool two = y + 1 < H - 1;
             const float* r1 = r0 + (two ? W : 0);
-            for (int x = 1 + threadIdx.x; x < W - 1; x += blockDim.x) {
-                const float v0 = r0[x], v1 = r1[x];
-                int b0 = (int)__fmul_rn(v0, scale), b1 = (int)__fmul_rn(v1, scale);
-                b0 = min(max(b0, 0), kNBins - 1);
-                b1 = min(max(b1, 0), kNBins - 1);
-                atomicAdd(&sh[b0], 1);
-                if (two) atomicAdd(&sh[b1], 1);
+            // the shared atomics order memory, so loads are not hoisted across them: fetch 4 columns x 2 rows first
+            // (8 independent loads in flight per thread), then count
+            for (int xb = 1 + threadIdx.x; xb < W - 1; xb += 4 * blockDim.x) {
+                float v0[4], v1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int x = xb + u * blockDim.x;
+                    const bool in = x < W - 1;
+                    v0[u] = in ? r0[x] : -1.f;
+                    v1[u] = in ? r1[x] : -1.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (xb + u * (int)blockDim.x >= W - 1) break;
+                    int b0 = (int)__fmul_rn(v0[u], scale), b1 = (int)__fmul_rn(v1[u], scale);
+                    b0 = min(max(b0, 0), kNBins - 1);
+                    b1 = min(max(b1, 0), kNBins - 1);
+                    atomicAdd(&sh[b0], 1);
+                    if (two) atomicAdd(&sh[b1], 1);
+                }
             }
         }
     }
@@ -256,6 +269,21 @@ k_halfsample(const float* __restrict__ src, size_t src_stride, int sw, int sh, f
         v = acc;
     }
     dst[(size_t)f * dst_stride + (size_t)y * dw + x] = v;
+}
+
+// exact 2:1 decimation, two outputs per thread: two 16-byte loads and one 8-byte store (the one-output kernel above
+// kept a single 4-load dependency per thread in flight: long-scoreboard stall ratio 16); same f32 operation order
+__global__ void __launch_bounds__(256)
+k_halfsample_x2(const float* __restrict__ src, size_t src_stride, int sw, float* __restrict__ dst, size_t dst_stride, int dw, int dh) {
+    const int f = blockIdx.z;
+    const int xp = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;      // xp = output pair index
+    if (2 * xp >= dw || y >= dh) return;
+    const float* r0 = src + (size_t)f * src_stride + (size_t)(2 * y) * sw + 4 * xp;
+    const float4 a = *reinterpret_cast<const float4*>(r0);
+    const float4 b = *reinterpret_cast<const float4*>(r0 + sw);
+    const float v0 = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.x, a.y), b.x), b.y), 0.25f);
+    const float v1 = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(a.z, a.w), b.z), b.w), 0.25f);
+    *reinterpret_cast<float2*>(dst + (size_t)f * dst_stride + (size_t)y * dw + 2 * xp) = make_float2(v0, v1);
 }
 
 // ---- per level: Lsmooth = Gauss5(Lt_init), Lflow = PM-G2(Scharr(Lsmooth), k) --------------------
@@ -1493,7 +1521,12 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
             const size_t dstride = out0_is_P ? plane : pyr;
             {
                 ProfScope ps(ctx, st, "scale.halfsample", (double)frames * ((double)p.w * p.h + (double)e.w * e.h) * 4);
-                k_halfsample<<<dim3(div_up(e.w, 256), e.h, frames), 256, 0, st>>>(ws.Lt + p.plane_off, pyr, p.w, p.h, dstbuf,
+                const float* hsrc = ws.Lt + p.plane_off;
+                if (p.w == 2 * e.w && p.h == 2 * e.h && p.w % 4 == 0 && pyr % 4 == 0 && dstride % 2 == 0 && e.w % 2 == 0 &&
+                    ((uintptr_t)hsrc & 15) == 0 && ((uintptr_t)dstbuf & 7) == 0)
+                    k_halfsample_x2<<<dim3(div_up(e.w / 2, 128), e.h, frames), 128, 0, st>>>(hsrc, pyr, p.w, dstbuf, dstride, e.w, e.h);
+                else
+                k_halfsample<<<dim3(div_up(e.w, 256), e.h, frames), 256, 0, st>>>(hsrc, pyr, p.w, p.h, dstbuf,
                                                                                dstride, e.w, e.h);
                 DUNK_KERNEL_CHECK(ctx);
             }
