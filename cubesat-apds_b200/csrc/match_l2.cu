@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "match.h"
@@ -31,7 +32,16 @@ namespace {
 constexpr int kM = 128;            // queries per CTA = UMMA M = TMEM lanes
 constexpr int kKBlock = 32;        // floats per 128-byte swizzle row
 constexpr int kUmmaK = 8;          // K per tcgen05.mma.kind::tf32
-constexpr int kAcc = 2;            // TMEM accumulator ring
+// Tile shape at D = 64, measured with the chunked epilogue below (3 163 x 2 M rows, tf32 TFLOP/s of the main stage):
+// N 256 x 2 accumulators x 2 smem stages 506; N 128 x 4 accumulators x 5 stages 467-476 (the single MMA-issuing thread
+// and the barrier hand-shakes per tile weigh twice as much); with the epilogue arithmetic skipped 711 / 552.
+#ifndef DUNK_L2_ACC
+#define DUNK_L2_ACC 2
+#endif
+#ifndef DUNK_L2_N64
+#define DUNK_L2_N64 256
+#endif
+constexpr int kAcc = DUNK_L2_ACC;  // TMEM accumulator ring
 constexpr int kCand = 4;           // candidates kept per (query, slab)
 constexpr int kSub = 4;            // epilogue warps per TMEM lane quarter = column groups = candidate lists per (query, slab)
 constexpr int kEpiWarps = 4 * kSub;
@@ -41,12 +51,16 @@ constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
 template <int D>
 struct Cfg {
     static constexpr int KB = D / kKBlock;                 // 128-byte K blocks per row
-    static constexpr int N = D <= 64 ? 256 : 128;          // train rows per MMA tile
+    static constexpr int N = D <= 64 ? DUNK_L2_N64 : 128;  // train rows per MMA tile
     static constexpr int A_BYTES = KB * kM * 128;
     static constexpr int B_BYTES = KB * N * 128;
     static constexpr int TMEM_COLS = kAcc * N;             // 512 or 256 (power of two)
-    static constexpr int kStages = D <= 64 ? 3 : 2;        // smem ring for the train tiles (227 KB per CTA)
-    static constexpr int SMEM = A_BYTES + kStages * B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kStages = D <= 64 ? (N == 256 ? 2 : 5) : 2;   // smem ring for the train tiles (227 KB per CTA)
+    // ||t||^2 of a tile travels with it (one 1-D bulk copy on the tile's barrier) into a ring of kStages + kAcc slots:
+    // the producer is at most kStages tiles ahead of the MMA warp, which is at most kAcc tiles ahead of the epilogue
+    static constexpr int kTn = kStages + kAcc;
+    static constexpr int TN_BYTES = N * 4;
+    static constexpr int SMEM = A_BYTES + kStages * B_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + kTn * TN_BYTES;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +97,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -142,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 l2_candidates_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
                      const float* __restrict__ tnorm /* padded to whole tiles, +inf past nt */, int nq, int total_tiles,
                      int tiles_per_slab, const float* __restrict__ tau /* per-query admission threshold or NULL */,
-                     float4* __restrict__ cand_score, uint4* __restrict__ cand_idx) {
+                     float4* __restrict__ cand_score, uint4* __restrict__ cand_idx, int dbg_skip) {
     using C = Cfg<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // 128B swizzle atoms need 1024-byte alignment
@@ -156,6 +175,7 @@ l2_candidates_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     uint64_t* acc_full = empty_b + kStages;     // kAcc
     uint64_t* acc_empty = acc_full + kAcc;      // kAcc
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + kAcc);
+    float* sTn = (float*)(smem + C::A_BYTES + kStages * C::B_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // D = 128 (HBM-heavier): query tile fastest, so the CTAs that share a train slab are launched next to each other,
@@ -188,9 +208,10 @@ l2_candidates_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             for (int j = 0; j < ntiles; ++j) {
                 const int s = j % kStages;
                 mbar_wait(&empty_b[s], ((j / kStages) & 1) ^ 1);
-                mbar_expect_tx(&full_b[s], C::B_BYTES);
+                mbar_expect_tx(&full_b[s], C::B_BYTES + C::TN_BYTES);
                 for (int kb = 0; kb < C::KB; ++kb)
                     tma_load_2d(sB + s * C::B_BYTES + kb * C::N * 128, &map_t, kb * kKBlock, (tile0 + j) * C::N, &full_b[s]);
+                bulk_load_1d(sTn + (j % C::kTn) * C::N, tnorm + (size_t)(tile0 + j) * C::N, C::TN_BYTES, &full_b[s]);
             }
         }
     } else if (warp == 1) {
@@ -231,76 +252,101 @@ l2_candidates_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
             for (int k = 0; k < kCand; ++k) top.s[k] = t0;
         }
-        auto tmem_ld32 = [&](uint32_t taddr, uint32_t (&v)[32]) {
+        // 16 accumulator columns of this thread's TMEM lane -> registers (asynchronous until wait_ld)
+        auto tmem_ld16 = [&](uint32_t taddr, uint32_t (&v)[16]) {
             asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                  "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                  "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                 : "r"(taddr)
                 : "memory");
         };
-        // scores of one 32-column chunk: ||t||^2 - 2 q.t, and their min tree (pure math, no warp sync);
-        // g[k] = min over the 8 columns c with ((c >> 1) & 3) == k
-        auto score = [&](const uint32_t (&v)[32], uint32_t t_first, float (&sc)[32], float (&g)[4], float& all) {
-            const float4* tnp = reinterpret_cast<const float4*>(tnorm + t_first);
+        // tcgen05.wait::ld with the loaded registers as in/out operands: every later use of v depends on the wait
+        auto wait_ld = [&](uint32_t (&v)[16]) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;"
+                         : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                           "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                         :
+                         : "memory");
+        };
+        // scores of one 16-column chunk, ||t||^2 - 2 q.t (||t||^2 from the tile's shared-memory slot: the same address for
+        // all lanes), reduced on the fly to g[k] = min over the 4 columns c with ((c >> 1) & 3) == k; pure math, no warp sync
+        auto score = [&](const uint32_t (&v)[16], const float* tn, float (&g)[4], float& all) {
+            const float4* tnp = reinterpret_cast<const float4*>(tn);
+            float m[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float4 x = __ldg(tnp + k);
-                sc[4 * k] = fmaf(-2.f, __uint_as_float(v[4 * k]), x.x);
-                sc[4 * k + 1] = fmaf(-2.f, __uint_as_float(v[4 * k + 1]), x.y);
-                sc[4 * k + 2] = fmaf(-2.f, __uint_as_float(v[4 * k + 2]), x.z);
-                sc[4 * k + 3] = fmaf(-2.f, __uint_as_float(v[4 * k + 3]), x.w);
+            for (int k = 0; k < 4; ++k) {
+                const float4 x = tnp[k];
+                m[2 * k] = fminf(fmaf(-2.f, __uint_as_float(v[4 * k]), x.x), fmaf(-2.f, __uint_as_float(v[4 * k + 1]), x.y));
+                m[2 * k + 1] = fminf(fmaf(-2.f, __uint_as_float(v[4 * k + 2]), x.z), fmaf(-2.f, __uint_as_float(v[4 * k + 3]), x.w));
             }
-            float m[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) m[k] = fminf(sc[2 * k], sc[2 * k + 1]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) m[k] = fminf(m[k], m[k + 8]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) g[k] = fminf(m[k], m[k + 4]);
             all = fminf(fminf(g[0], g[1]), fminf(g[2], g[3]));
         };
         // the common case (no lane of the warp improves its list) is a single vote; otherwise narrow down to
-        // the column groups, then the columns, that improve some lane (32 lanes share every branch)
-        auto maybe_insert = [&](const float (&sc)[32], const float (&g)[4], float all, uint32_t t_first) {
+        // the column groups, then the columns, that improve some lane (32 lanes share every branch); the few scores
+        // that are looked at are formed again from the accumulator registers
+        auto maybe_insert = [&](const uint32_t (&v)[16], const float* tn, const float (&g)[4], float all, uint32_t t_first) {
             if (__any_sync(0xffffffffu, all < top.s[3])) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (__any_sync(0xffffffffu, g[k] < top.s[3])) {
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
+                        for (int u = 0; u < 4; ++u) {
                             const int c = 2 * k + (u & 1) + 8 * (u >> 1);
-                            if (__any_sync(0xffffffffu, sc[c] < top.s[3])) top.insert(sc[c], t_first + c);
+                            const float sc = fmaf(-2.f, __uint_as_float(v[c]), tn[c]);
+                            if (__any_sync(0xffffffffu, sc < top.s[3])) top.insert(sc, t_first + c);
                         }
                     }
             }
         };
-        for (int j = 0; j < ntiles; ++j) {
-            const int a = j % kAcc;
-            const uint32_t t_row0 = (uint32_t)(tile0 + j) * C::N + half * kCols;
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * C::N + half * kCols);
-            mbar_wait(&acc_full[a], (j / kAcc) & 1);
-            tc_fence_after();
-            // all of this warp's columns are fetched by back-to-back TMEM loads and scored as one dependency
-            // chain (the chain latency, not the instruction count, bounds the epilogue)
-            static_assert(kChunks == 1 || kChunks == 2, "column group = 32 or 64 columns");
-            uint32_t va[32], vb[32];
-            tmem_ld32(taddr0, va);
-            if (kChunks == 2) tmem_ld32(taddr0 + 32, vb);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float sa[32], ga[4], alla, sb[32], gb[4], allb;
-            score(va, t_row0, sa, ga, alla);
-            if (kChunks == 2) score(vb, t_row0 + 32, sb, gb, allb);
-            // the accumulator stage goes back to the MMA warp before the (rare) insertions
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
-            maybe_insert(sa, ga, alla, t_row0);
-            if (kChunks == 2) maybe_insert(sb, gb, allb, t_row0 + 32);
+        // The warp's columns of a tile are walked in chunks of 16; chunk q = tile q / kPer, part q % kPer.  While the
+        // scores of chunk q are reduced, the TMEM load of chunk q + 1 is in flight: one warp sees every tile, so its own
+        // chain (barrier, TMEM load, math) bounds the CTA and the accumulator ring only decouples it from the MMA warp.
+        constexpr int kPer = kCols / 16;
+        const uint32_t taddr_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kCols);
+        auto issue_ld = [&](int q, uint32_t (&v)[16]) {
+            const int j = q / kPer, part = q % kPer, a = j % kAcc;
+            if (part == 0) {
+                mbar_wait(&acc_full[a], (j / kAcc) & 1);
+                tc_fence_after();
+            }
+            tmem_ld16(taddr_base + (uint32_t)(a * C::N + 16 * part), v);
+        };
+        // chunk q has landed in v (tcgen05.wait::ld waits for EVERY outstanding load of the thread, so it is called while
+        // only this chunk's load is in flight, before the next one is issued)
+        auto landed = [&](int q, uint32_t (&v)[16]) {
+            wait_ld(v);
+            const int j = q / kPer, part = q % kPer;
+            if (part == kPer - 1) {     // every column of tile j is in registers: the accumulator stage goes back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[j % kAcc]);
+            }
+        };
+        auto reduce = [&](int q, const uint32_t (&v)[16]) {
+            const int j = q / kPer, part = q % kPer;
+            const float* tn = sTn + (j % C::kTn) * C::N + half * kCols + 16 * part;
+            float g[4], all;
+            score(v, tn, g, all);
+            maybe_insert(v, tn, g, all, (uint32_t)(tile0 + j) * C::N + half * kCols + 16 * part);
+        };
+        {
+            uint32_t va[16], vb[16];
+            const int nchunks = ntiles * kPer;
+            if (nchunks > 0) issue_ld(0, va);
+            for (int q = 0; q < nchunks; q += 2) {
+                landed(q, va);
+                if (q + 1 < nchunks) issue_ld(q + 1, vb);
+                if (!dbg_skip) reduce(q, va);
+                if (q + 1 < nchunks) {
+                    landed(q + 1, vb);
+                    if (q + 2 < nchunks) issue_ld(q + 2, va);
+                    if (!dbg_skip) reduce(q + 1, vb);
+                }
+            }
         }
         if (row < nq) {
             const size_t o = ((size_t)slab * kSub + half) * nq + row;
@@ -532,8 +578,9 @@ int launch_candidates(dunk_ctx* ctx, cudaStream_t st, const float* d_q, int nq, 
     }
     ProfScope ps(ctx, st, label, (double)nq * (double)std::min<long long>((long long)total_tiles * C::N, (long long)nt));
     const dim3 grid = D >= 128 ? dim3(div_up(nq, kM), n_slabs) : dim3(n_slabs, div_up(nq, kM));
+    static const int dbg_skip = getenv("DUNK_L2_SKIP_EPILOGUE") ? atoi(getenv("DUNK_L2_SKIP_EPILOGUE")) : 0;
     l2_candidates_kernel<D><<<grid, kThreads, C::SMEM, st>>>(mq, mt, d_tnorm, nq, total_tiles, tiles_per_slab,
-                                                                                    d_tau, cand_score, cand_idx);
+                                                                                    d_tau, cand_score, cand_idx, dbg_skip);
     ctx->launches.fetch_add(1);
     DUNK_CUDA(cudaGetLastError());
     return DUNK_OK;
@@ -561,7 +608,7 @@ int dunk_knn2_l2_dev(dunk_ctx* ctx, int slot, const void* q_dev, int nq, const v
     DUNK_REQUIRE(((uintptr_t)q_dev & 15) == 0 && ((uintptr_t)t_dev & 15) == 0, DUNK_ERR_BAD_ARG, "dunk_knn2_l2_dev: descriptors must be 16-byte aligned");
     DUNK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->slots[slot].stream;
-    const int N = dim <= 64 ? 256 : 128;
+    const int N = dim <= 64 ? Cfg<64>::N : Cfg<128>::N;
     const int total_tiles = div_up(nt, N);
     const int q_tiles = div_up(nq, kM);
     // two full waves of CTAs (one CTA per SM: 160-197 KB of smem); every query tile re-reads its slab through L2
