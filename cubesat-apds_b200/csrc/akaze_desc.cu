@@ -212,12 +212,16 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
     float* pri = pri_all[warp];
     float2* pxy = pxy_all[warp];
     {
+        const bool kfast = fabsf(co) >= fabsf(si);
         float ri[14], rx[14], ry[14];
         bool ok[14];
 #pragma unroll
         for (int it = 0; it < 14; ++it) {
+            // lattice point of this lane: the index that moves mostly along image x (k when |cos| >= |sin|, else l) is the
+            // fastest over the lanes, so neighbouring lanes read neighbouring pixels of one row and share 32-byte sectors
+            // (with l always fastest every lane of an upright keypoint hit its own row: 32 sectors per gather, l1tex-bound)
             const int p = min(lane + 32 * it, 440);
-            const int k = p / 21 - 10, l = p % 21 - 10;
+            const int k = (kfast ? p % 21 : p / 21) - 10, l = (kfast ? p / 21 : p % 21) - 10;
             const float sy = __fadd_rn(yf, __fadd_rn(__fmul_rn(__fmul_rn((float)l, co), fscale),
                                                      __fmul_rn(__fmul_rn((float)k, si), fscale)));
             const float sx = __fadd_rn(xf, __fadd_rn(__fmul_rn(__fmul_rn((float)(-l), si), fscale),
@@ -233,8 +237,9 @@ k_mldb(const DunkKeyPoint* __restrict__ kps_all, int kp_cap, const int* __restri
         for (int it = 0; it < 14; ++it) {
             const int p = lane + 32 * it;
             if (p < 441) {
-                pri[p] = ok[it] ? ri[it] : __int_as_float(0x7fc00000);     // NaN marks a sample outside the image
-                pxy[p] = make_float2(__fadd_rn(__fmul_rn(-rx[it], si), __fmul_rn(ry[it], co)),
+                const int q = kfast ? (p % 21) * 21 + p / 21 : p;           // slot (k + 10) * 21 + (l + 10)
+                pri[q] = ok[it] ? ri[it] : __int_as_float(0x7fc00000);     // NaN marks a sample outside the image
+                pxy[q] = make_float2(__fadd_rn(__fmul_rn(-rx[it], si), __fmul_rn(ry[it], co)),
                                      __fadd_rn(__fmul_rn(rx[it], co), __fmul_rn(ry[it], si)));
             }
         }

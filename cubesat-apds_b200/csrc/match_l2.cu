@@ -489,15 +489,19 @@ l2_rerank_kernel(const float* __restrict__ q, const float* __restrict__ t, int n
     }
 }
 
-// exact brute force for the queries stage B could not prove (one CTA per query)
+// exact brute force for the queries stage B could not prove: grid (flagged query, part of the train rows); every CTA
+// leaves its two lexicographically smallest (distance, index) pairs in part_out, l2_exact_merge_kernel merges the parts
+// (one CTA per query over all 2 M rows took 22 ms for a single flagged query)
 __global__ void __launch_bounds__(256)
 l2_exact_kernel(const float* __restrict__ q, const float* __restrict__ t, uint32_t nt, int dim, const int* __restrict__ flagged,
-                int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+                float4* __restrict__ part_out /* [n_flagged][gridDim.y]: d1, i1 bits, d2, i2 bits */) {
     const int qi = flagged[blockIdx.x];
     const float* qp = q + (size_t)qi * dim;
+    const uint32_t per = (nt + gridDim.y - 1) / gridDim.y;
+    const uint32_t r0 = blockIdx.y * per, r1 = min(nt, r0 + per);
     float d1 = INFINITY, d2 = INFINITY;
     uint32_t i1 = kNoIdx, i2 = kNoIdx;
-    for (uint32_t r = threadIdx.x; r < nt; r += blockDim.x) {
+    for (uint32_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
         const float d = exact_d2(qp, t + (size_t)r * dim, dim);
         if (lex_less(d, r, d2, i2)) {
             if (lex_less(d, r, d1, i1)) { d2 = d1; i2 = i1; d1 = d; i1 = r; } else { d2 = d; i2 = r; }
@@ -519,9 +523,29 @@ l2_exact_kernel(const float* __restrict__ q, const float* __restrict__ t, uint32
                 if (lex_less(d, i, b1, c1)) { b2 = b1; c2 = c1; b1 = d; c1 = i; } else { b2 = d; c2 = i; }
             }
         }
-        idx_out[2 * qi] = (int32_t)c1; idx_out[2 * qi + 1] = (int32_t)c2;
-        dist_out[2 * qi] = sqrtf(b1); dist_out[2 * qi + 1] = sqrtf(b2);
+        part_out[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = make_float4(b1, __uint_as_float(c1), b2, __uint_as_float(c2));
     }
+}
+
+__global__ void l2_exact_merge_kernel(const float4* __restrict__ part, int n_parts, const int* __restrict__ flagged, int n_flagged,
+                                      int32_t* __restrict__ idx_out, float* __restrict__ dist_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_flagged) return;
+    float b1 = INFINITY, b2 = INFINITY;
+    uint32_t c1 = kNoIdx, c2 = kNoIdx;
+    for (int p = 0; p < n_parts; ++p) {
+        const float4 v = part[(size_t)k * n_parts + p];
+        const float d[2] = {v.x, v.z};
+        const uint32_t i[2] = {__float_as_uint(v.y), __float_as_uint(v.w)};
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            if (lex_less(d[u], i[u], b2, c2)) {
+                if (lex_less(d[u], i[u], b1, c1)) { b2 = b1; c2 = c1; b1 = d[u]; c1 = i[u]; } else { b2 = d[u]; c2 = i[u]; }
+            }
+    }
+    const int qi = flagged[k];
+    idx_out[2 * qi] = (int32_t)c1; idx_out[2 * qi + 1] = (int32_t)c2;
+    dist_out[2 * qi] = sqrtf(b1); dist_out[2 * qi + 1] = sqrtf(b2);
 }
 
 __global__ void max_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
@@ -674,9 +698,11 @@ int dunk_knn2_l2_dev(dunk_ctx* ctx, int slot, const void* q_dev, int nq, const v
     DUNK_CUDA(cudaStreamSynchronize(st));
     if (h_misc[0] > 0) {
         ProfScope ps(ctx, st, "match.l2_exact_fallback", (double)h_misc[0] * (double)nt);
-        l2_exact_kernel<<<h_misc[0], 256, 0, st>>>((const float*)q_dev, (const float*)t_dev, (uint32_t)nt, dim, d_flagged, (int32_t*)idx_dev,
-                                                 (float*)dist_dev);
-        ctx->launches.fetch_add(1);
+        // the candidate-score array is free again: it holds the per-part pairs (at most nq * n_slabs * kSub entries)
+        const int parts = (int)std::max<long long>(1, std::min<long long>({64ll, (long long)n_slabs * kSub, ((long long)nt + 4095) / 4096}));
+        l2_exact_kernel<<<dim3(h_misc[0], parts), 256, 0, st>>>((const float*)q_dev, (const float*)t_dev, (uint32_t)nt, dim, d_flagged, d_cs);
+        l2_exact_merge_kernel<<<div_up(h_misc[0], 128), 128, 0, st>>>(d_cs, parts, d_flagged, h_misc[0], (int32_t*)idx_dev, (float*)dist_dev);
+        ctx->launches.fetch_add(2);
         DUNK_CUDA(cudaGetLastError());
     }
     if (stats) { stats[0] = h_misc[0]; stats[1] = n_slabs; }
