@@ -90,8 +90,9 @@ def find_homography_mat(input: np.ndarray, reference: np.ndarray,
                         reproj_threshold: Optional[float] = None,
                         ctx: Optional[_lib.Context] = None) -> Tuple[Cmat, Optional[Cmat]]:
     """mod.rs:231-259 — findHomography(input, reference, mask, method or Default, thr or 3.0).
-    Returns (Cmat<f64> 3x3, Some(Cmat<u8> N x 1 mask)) — the mask only for RANSAC / LMEDS / RHO (RHO is served by
-    the RANSAC estimator: tolerance parity with cv2's PROSAC-based RHO).
+    Returns (Cmat<f64> 3x3, Some(Cmat<u8> N x 1 mask)) — the mask only for RANSAC / LMEDS, as the reference's
+    `match method` (mod.rs:252-256); RHO is accepted and served by the RANSAC estimator (tolerance parity with cv2's
+    PROSAC-based RHO), its mask is available through find_homography_batch.
     Errors: < 4 pairs -> MatError('Opencv', code -28); no model -> MatError('Empty')."""
     ctx = ctx or default_context()
     src = np.ascontiguousarray(input, dtype=np.float32).reshape(-1, 2)
@@ -111,7 +112,7 @@ def find_homography_mat(input: np.ndarray, reference: np.ndarray,
     if not found.value:
         raise MatError("Empty")
     out_mask = None
-    if method in (HomographyMethod.RANSAC, HomographyMethod.LMEDS, HomographyMethod.RHO):
+    if method in (HomographyMethod.RANSAC, HomographyMethod.LMEDS):
         out_mask = Cmat(mask[: src.shape[0]].reshape(-1, 1), np.uint8)
     return Cmat(H.reshape(3, 3), np.float64), out_mask
 

@@ -99,12 +99,14 @@ def test_rho_vs_cv2(dunk, ctx):
     Ht = np.array([[0.98, -0.12, 60], [0.10, 1.03, -40], [1e-5, -2e-5, 1]])
     for i in range(int(R["n_cases"])):
         src, dst = R[f"c{i}_src"], R[f"c{i}_dst"]
-        H, mask = hg.find_homography_mat(src, dst, hg.HomographyMethod.RHO, float(R[f"c{i}_thr"]), ctx)
+        H, none = hg.find_homography_mat(src, dst, hg.HomographyMethod.RHO, float(R[f"c{i}_thr"]), ctx)
+        assert none is None                   # the reference returns the mask for RANSAC / LMEDS only (mod.rs:252-256)
         Hr, mr = hg.find_homography_mat(src, dst, hg.HomographyMethod.RANSAC, float(R[f"c{i}_thr"]), ctx)
-        assert np.array_equal(H.mat, Hr.mat) and np.array_equal(mask.mat, mr.mat)
+        Hb, masks, info = hg.find_homography_batch([src], [dst], float(R[f"c{i}_thr"]), hg.HomographyMethod.RHO, ctx)
+        assert np.array_equal(H.mat, Hr.mat) and np.array_equal(Hb[0], Hr.mat) and np.array_equal(masks[0], mr.mat.ravel())
         assert rel_err(H.mat, R[f"c{i}_H"]) < 3e-2, i
         assert rel_err(H.mat, Ht) <= max(2e-2, 1.5 * rel_err(R[f"c{i}_H"], Ht)), i
-        agree = (mask.mat.ravel() == R[f"c{i}_mask"]).mean()
+        agree = (masks[0] == R[f"c{i}_mask"]).mean()
         assert agree >= 0.75, (i, agree)
 
 
