@@ -22,6 +22,10 @@ constexpr int kTileRows = 64;            // DB rows per smem stage (4 KB), one r
 constexpr int kStages = 3;
 constexpr int kWarpsPerCta = 8;
 constexpr int kQT = 4;                   // queries per thread
+#ifndef DUNK_MATCH_UNROLL
+#define DUNK_MATCH_UNROLL 2
+#endif
+constexpr int kRowUnroll = DUNK_MATCH_UNROLL;   // DB rows per unrolled loop body
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -228,7 +232,7 @@ hamming_top2_kernel(const uint4* __restrict__ db, uint32_t nt, const uint4* __re
         const int rows = (int)min((uint32_t)kTileRows, nt - row0);
         const uint4* tp = tiles + (size_t)st * kTileRows * 4;
         const uint32_t g0 = index_base + row0;
-#pragma unroll 2
+#pragma unroll kRowUnroll
         for (int r = 0; r < rows; ++r) {
             const uint4 a = tp[r * 4 + 0], b = tp[r * 4 + 1], c = tp[r * 4 + 2], d = tp[r * 4 + 3];
             uint32_t dist[QT];
@@ -425,6 +429,8 @@ KnnPlan plan_knn2(dunk_ctx* ctx, int nq, uint32_t nt) {
         if (eff > best_eff + 0.005) { best_eff = eff; slabs = real_slabs; }
         if (items > 16 * slots) break;
     }
+    static const int force_slabs = getenv("DUNK_MATCH_SLABS") ? atoi(getenv("DUNK_MATCH_SLABS")) : 0;      // A/B switch
+    if (force_slabs > 0) slabs = std::min<long long>(force_slabs, max_slabs);
     p.tiles_per_cta = div_up(total_tiles, slabs);
     if (p.tiles_per_cta < 1) p.tiles_per_cta = 1;
     p.gx = div_up(total_tiles, p.tiles_per_cta);   // slabs
