@@ -27,7 +27,7 @@ extract)
   E="python bench.py --workload extract --steps 1 --warmup 3 --no-cpu-baseline"
   $E > $OUT/r2p_plain3.log 2>&1 &&
   ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section SchedulerStats --section Occupancy --section LaunchStats --section InstructionStats \
-      --clock-control none -k regex:"k_fed|k_hessian|k_prep_level|k_extrema|k_mldb|k_orientation|k_contrast|k_gray|k_halfsample" -s 294 -c 98 -o $OUT/r2p_extract $E > $OUT/r2p_ncu3.log 2>&1
+      --clock-control none -k regex:"k_fed|k_hessian|k_prep_level|k_extrema|k_mldb|k_orientation|k_contrast|k_gray|k_halfsample" -s 249 -c 83 -o $OUT/r2p_extract $E > $OUT/r2p_ncu3.log 2>&1
   ncu -i $OUT/r2p_extract.ncu-rep --page raw --csv > $OUT/r2p_extract_raw.csv
   gzip -f $OUT/r2p_extract_raw.csv; rm -f $OUT/r2p_extract.ncu-rep ;;
 esac
