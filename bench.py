@@ -254,7 +254,8 @@ def pipeline_config(args, world):
         "db_tiles": 85, "ratio": args.ratio, "ransac_thr": RANSAC_THR, "pnp": PNP, "stages": "extract + match + RANSAC homography + PnP",
         "parallelism": f"frames dp{world}" + (f" + DB row-shard{world} (query all-gather, one local top-2 launch, top-2 all-to-all, "
                                               f"(distance, index) merge; NCCL inside libdunk_b200.so)" if world > 1 else ""),
-        "l2": "inputs larger than L2 (frame batch 67 MB + 7 GB scale-space workspace per step per GPU; a different batch every step)",
+        "l2": "inputs larger than L2 (frame batch %.0f MB + %.0f GB scale-space workspace per step per GPU; a different batch every step)"
+              % (args.frames * FRAME * FRAME / 1e6, args.frames * 0.11),
     }
 
 
