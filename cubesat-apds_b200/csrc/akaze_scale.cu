@@ -7,6 +7,7 @@
 // oracle/akaze_oracle.py; the FED step keeps OpenCV's f32 operation order
 // (no FMA contraction) because 166 dependent steps amplify reassociation noise.
 #include "akaze.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -1508,7 +1509,8 @@ int akaze_build_scale_space(dunk_ctx* ctx, cudaStream_t st, const LevelTable& lt
         const LevelInfo& e = lt.lv[i];
         const LevelInfo& p = lt.lv[i - 1];
         const int n = e.n_tau;
-        const int m = div_up(n, kFedMaxK);   // launches; the n steps are split as evenly as possible
+        static const int fed_maxk = getenv("DUNK_FED_MAXK") ? std::min(kFedMaxK, std::max(1, atoi(getenv("DUNK_FED_MAXK")))) : kFedMaxK;
+        const int m = div_up(n, fed_maxk);   // launches; the n steps are split as evenly as possible
         float* P = ws.Lt + e.plane_off;   // final home of this level's Lt (stride pyr)
         float* Q = ws.Ltmp;               // ping-pong partner (stride plane)
         const float* init;
