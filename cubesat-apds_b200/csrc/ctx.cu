@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <thread>
+#include <unistd.h>
 
 namespace dunk {
 
@@ -39,6 +40,7 @@ class HostPool {
     unsigned long long generation = 0;
     int active = 0;
     bool stop = false;
+    pid_t owner = 0;
 
     void drain() {
         for (;;) {
@@ -66,7 +68,12 @@ public:
         unsigned want = std::thread::hardware_concurrency();
         want = want > 3 ? std::min(12u, want - 2) : 0;
         if (const char* e = getenv("DUNK_COPY_THREADS")) want = (unsigned)std::max(0, atoi(e) - 1);
-        for (unsigned i = 0; i < want; ++i) workers.emplace_back([this] { worker(); });
+        owner = getpid();
+        try {
+            for (unsigned i = 0; i < want; ++i) workers.emplace_back([this] { worker(); });
+        } catch (...) {
+            // thread creation refused (resource limit): whatever was started serves; with none the caller copies inline
+        }
     }
     ~HostPool() {
         {
@@ -77,7 +84,8 @@ public:
         for (auto& t : workers) t.join();
     }
     void run(size_t items, const std::function<void(size_t)>& f) {
-        if (items < 2 || workers.empty() || !call_mu.try_lock()) {
+        // a forked child inherits the object but not the worker threads: it runs its items inline
+        if (items < 2 || workers.empty() || getpid() != owner || !call_mu.try_lock()) {
             for (size_t i = 0; i < items; ++i) f(i);
             return;
         }

@@ -1018,7 +1018,12 @@ int build_from_bands(dunk_db* db, const float* red, const float* green, const fl
         DUNK_CUDA(cudaEventCreateWithFlags(&up.ring_ev[0], cudaEventDisableTiming));
         DUNK_CUDA(cudaEventCreateWithFlags(&up.ring_ev[1], cudaEventDisableTiming));
         const float* h_band[3] = {red, green, blue};
-        up.start(ctx->device, g.slot().stream2, (char*)g.slot().ring, h_band, dev, width, height, tile_h);
+        try {
+            up.start(ctx->device, g.slot().stream2, (char*)g.slot().ring, h_band, dev, width, height, tile_h);
+        } catch (...) {      // std::thread could not be created: no exception may cross the C ABI
+            set_error("dunk_db_build_from_bands: cannot start the upload thread");
+            return DUNK_ERR_NO_MEM;
+        }
     }
     AkazeWorkspace ws;
     akaze_carve_workspace(ptr, lt, sub, cap, cap, &ws);
